@@ -1,0 +1,365 @@
+#!/usr/bin/env python3
+"""bench.py -- stream-updates/s of the Precise streaming-inference hot path on B200.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--streams-per-gpu S] [--impl b200|reference]
+
+One "step" = one tick: every stream on the GPU receives one 1024-sample (2048-byte) chunk and is
+fully classified: PCM -> MFCC frames -> 29-step GRU scan -> sigmoid -> threshold decode -> trigger
+(+ for N > 1 the NCCL all-reduce of the detection count).  A (stream, chunk) pair is one
+stream-update; ``value`` = stream-updates/s over all GPUs, weak scaling (S streams per GPU).
+
+Workload (``config.workload``): the per-GPU shard of BASELINE.json configs[3] (1M default-parameter
+streams over 8 GPUs; 131072 = 2^17 streams per GPU so that one tick's PCM, 268 MB, exceeds the
+126 MB L2), default 'hey-mycroft' parameters (n_fft 512, 20 filters, 13 MFCCs, GRU 20).  configs[1]
+(1k streams) is reported beside it under ``small_batch`` with an explicit L2 flush between steps.
+Synthetic data: Gaussian sigma=3000 LSB int16 PCM, 1 % silent and 1 % full-scale-DC streams, seeded
+random weights (no trained model ships with the reference).
+
+The JSON line carries ``roofline`` (MFCC kernel vs measured HBM bandwidth; per-launch time from CUDA
+events inside the timed region), ``roofline_gru`` (fp32-FMA bound scan kernel), ``e2e`` (same metric
+through the host-buffer C-ABI call, pinned host PCM in / confidences out inside the timed region),
+``cpu_baseline`` (the numpy oracle port on the host cores) and ``clocks``.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CHUNK = 1024
+ALG_BYTES_PER_UPDATE = 2048 + 1.28 * 13 * 4           # 2114.56 B (F=13)
+ALG_FLOP_PER_UPDATE_GRU = 2 * (29 * (13 + 20) * 60 + 20)   # 114 880
+FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12     # 74.4 (148 SMs x 128 lanes x 2 x max clock)
+
+
+def peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.isfile(p):
+        try:
+            return float(json.load(open(p))['hbm_gbs']), 'measured'
+        except Exception:
+            pass
+    return 6650.0, 'fallback'
+
+
+def synth_pcm(n_streams, n_samples, seed, stream_offset=0):
+    """Gaussian sigma=3000 int16; 1 % silent, 1 % DC streams (the reference's own test signals)."""
+    rs = np.random.RandomState(seed)
+    x = rs.standard_normal((n_streams, n_samples)).astype(np.float32)
+    x *= 3000.0
+    pcm = np.clip(x, -32768, 32767).astype(np.int16)
+    ids = np.arange(n_streams) + stream_offset
+    pcm[ids % 100 == 17] = 0
+    pcm[ids % 100 == 53] = 32767
+    return pcm
+
+
+# ------------------------------------------------------------------------------------ CPU arm
+def _cpu_worker(args):
+    seed, n_streams, ticks, warm = args
+    os.environ['OMP_NUM_THREADS'] = '1'
+    from oracle.gru import GruWeights
+    from oracle.listener import OracleListener
+    from oracle.trigger import OracleTrigger
+    w = GruWeights.random(13, 20, seed=0, scale=0.1)
+    pcm = synth_pcm(n_streams, (ticks + warm) * CHUNK, seed)
+    lis = [OracleListener(w) for _ in range(n_streams)]
+    det = [OracleTrigger(2 * CHUNK) for _ in range(n_streams)]
+    fired = 0
+    t0 = None
+    for k in range(ticks + warm):
+        if k == warm:
+            t0 = time.perf_counter()
+        for s in range(n_streams):
+            c = pcm[s, k * CHUNK:(k + 1) * CHUNK].astype(np.float32) / 32768.0
+            fired += det[s].update(lis[s].update(c))
+    return n_streams * ticks, time.perf_counter() - t0, fired
+
+
+def cpu_port_rate(ticks=3000, warm=50, streams_per_proc=1, procs=None):
+    """The oracle port (numpy restatement of Listener.update + TriggerDetector.update) on the host
+    cores, one stream per worker process as in the reference (one Listener per process)."""
+    import multiprocessing as mp
+    procs = procs or os.cpu_count() or 1
+    ctx = mp.get_context('fork')
+    with ctx.Pool(procs) as pool:
+        res = pool.map(_cpu_worker, [(1000 + i, streams_per_proc, ticks, warm) for i in range(procs)])
+    updates = sum(r[0] for r in res)
+    wall = max(r[1] for r in res)
+    return updates / wall, procs, '%d worker processes x %d stream x %d ticks of 1024 samples (after %d warm-up ticks), numpy oracle port, OMP_NUM_THREADS=1' % (
+        procs, streams_per_proc, ticks, warm)
+
+
+def run_reference(args, rank):
+    """--impl reference: the reference's CPU path (oracle port; the TF/Keras/sonopy stack is not
+    installable on this image) on all host cores, bounded sample per step."""
+    if rank != 0:
+        return
+    t0 = time.perf_counter()
+    rates = []
+    for step in range(args.warmup + args.steps):
+        r, cores, sample = cpu_port_rate(ticks=40, warm=5)
+        if step >= args.warmup:
+            rates.append(r)
+    v = float(np.mean(rates))
+    line = {
+        'impl': 'reference', 'metric': 'stream-updates/s (16 kHz int16 PCM, 1024-sample chunk -> decoded confidence + trigger)',
+        'value': v, 'unit': 'stream-updates/s', 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': 1e3 * (time.perf_counter() - t0) / max(1, args.steps + args.warmup),
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64 MFCC / f32 GRU', 'data': 'synthetic',
+        'config': {'workload': 'default hey-mycroft parameters (n_fft 512, n_filt 20, n_mfcc 13, GRU 20), 1024-sample chunks; bounded CPU sample'},
+        'cpu_baseline': {'value': v, 'unit': 'stream-updates/s', 'cores': cores, 'kind': 'port', 'sample': sample + ' per step'},
+        'e2e': {'value': v, 'unit': 'stream-updates/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'realtime_streams': v / 15.625,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = 'index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,' \
+        'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile('w+', suffix='.csv', delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(['nvidia-smi', '-i', str(gpu_index), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits', '-lms', '100'],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.strip().split(', ') for r in open(self.f.name) if r.strip()]
+        os.unlink(self.f.name)
+        sm, mx, reasons = [], [], set()
+        for r in rows:
+            if len(r) < 9:
+                continue
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except ValueError:
+                continue
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[5:9]):
+                if v.strip().lower() == 'active':
+                    reasons.add(name)
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# ------------------------------------------------------------------------------------ GPU arm
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from mycroft_precise_b200 import GruModel, StreamBatch
+    from mycroft_precise_b200.core import pinned_empty, pinned_free
+    from mycroft_precise_b200.dist import init_from_env, DetectionCounter
+
+    cpu = None
+    if int(os.environ.get('WORLD_SIZE', '1')) == 1 and not args.no_cpu_baseline:
+        cpu = cpu_port_rate()                  # before CUDA is initialised in this process (fork safety)
+    rank, local, world = init_from_env()
+    if world != args.gpus and rank == 0:
+        print('note: WORLD_SIZE=%d, --gpus=%d' % (world, args.gpus), file=sys.stderr)
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    S = args.streams_per_gpu
+    K, W = args.steps, args.warmup
+    model = GruModel.random(13, 20, seed=0, scale=0.1)
+    sb = StreamBatch(model, S, chunk_samples=CHUNK, device=local)
+    core = sb.core
+
+    # ---- synthetic PCM: NT distinct ticks resident in HBM (each tick 2 KB x S > L2 at the default S)
+    NT = args.ticks_resident
+    host_ticks = [synth_pcm(S, CHUNK, seed=1234 + 17 * t, stream_offset=rank * S) for t in range(NT)]
+    dev_ticks = [torch.from_numpy(h).to(dev) for h in host_ticks]
+    counter = DetectionCounter(sb.count)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if S * CHUNK * 2 < (160 << 20) else None
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step(t):
+        if flush is not None:
+            flush.add_(1)                      # rewrite 256 MB: evicts L2 between iterations
+        sb.update(dev_ticks[t % NT])
+        if world > 1:
+            counter.all_reduce()
+
+    # ---- value: inputs resident in HBM
+    for t in range(W):
+        step(t)
+    barrier()
+    core.profile(True)
+    sampler = ClockSampler(local) if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    flush_ms = 0.0
+    if flush is not None:                       # cost of the flush alone, subtracted below
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for _ in range(K):
+            flush.add_(1)
+        f1.record(); torch.cuda.synchronize()
+        flush_ms = f0.elapsed_time(f1)
+        barrier()
+    e0.record()
+    for t in range(K):
+        step(W + t)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1) - flush_ms
+    kms, klaunch = core.profile_read()
+    core.profile(False)
+    clocks = sampler.stop() if sampler else None
+    tmax = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms_all = float(tmax.item())
+    value = S * world * K / (ms_all * 1e-3)
+    total_fired = int(counter.total.item()) if world > 1 else int(sb.count.item())
+
+    # ---- e2e: host buffers through pb_update_host (H2D of the PCM and D2H of the results inside)
+    pins = []
+    e2e = None
+    try:
+        hp = []
+        for t in range(min(NT, 2)):
+            a, p = pinned_empty((S, CHUNK), np.int16); a[:] = host_ticks[t]; hp.append(a); pins.append(p)
+        conf, p = pinned_empty((S,), np.float64); pins.append(p)
+        fired, p = pinned_empty((S,), np.uint8); pins.append(p)
+        for t in range(W):
+            sb.update_host(hp[t % len(hp)], conf, None, fired)
+        barrier()
+        t0 = time.perf_counter()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        cnt = 0
+        for t in range(K):
+            cnt += sb.update_host(hp[t % len(hp)], conf, None, fired)
+            if world > 1:
+                counter.all_reduce()
+        g1.record()
+        barrier()
+        wall_ms = (time.perf_counter() - t0) * 1e3
+        e_ms = g0.elapsed_time(g1)            # events bracket the blocking host calls: ~ wall time
+        if e_ms <= 0:
+            e_ms = wall_ms
+        te = torch.tensor([e_ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e = {'value': S * world * K / (float(te.item()) * 1e-3), 'unit': 'stream-updates/s',
+               'h2d_bytes_per_step': int(S * CHUNK * 2), 'd2h_bytes_per_step': int(S * (8 + 1) + 8),
+               'api': 'pb_update_host (StreamBatch.update_host), pinned host buffers', 'ms_per_step': float(te.item()) / K}
+    finally:
+        for p in pins:
+            pinned_free(p)
+
+    # ---- configs[1]: 1k streams, explicit L2 flush between steps
+    small = None
+    if rank == 0 and args.small_batch:
+        S2 = 1000
+        sb2 = StreamBatch(model, S2, chunk_samples=CHUNK, device=local)
+        tk = [torch.from_numpy(synth_pcm(S2, CHUNK, seed=99 + t)).to(dev) for t in range(4)]
+        fl = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+        evs = []
+        for t in range(W + K):
+            fl.add_(1)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); sb2.update(tk[t % 4]); b.record()
+            if t >= W:
+                evs.append((a, b))
+        torch.cuda.synchronize()
+        per = float(np.mean([a.elapsed_time(b) for a, b in evs]))
+        small = {'workload': 'configs[1]: 1000 streams, GRU 20, 1 GPU', 'ms_per_step': per, 'value': S2 / (per * 1e-3),
+                 'unit': 'stream-updates/s', 'l2': 'flushed (256 MB write) before every step'}
+        sb2.core.close()
+
+    if world > 1:
+        dist.barrier()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    hbm_peak, which = peaks()
+    k1_ms = kms[0] / max(1, klaunch[0])
+    k2_ms = kms[1] / max(1, klaunch[1])
+    k1_gbs = S * ALG_BYTES_PER_UPDATE / (k1_ms * 1e-3) / 1e9 if k1_ms > 0 else None
+    traffic = None
+    tp = os.path.join(ROOT, 'profiles', 'k1_traffic.json')
+    if os.path.isfile(tp):
+        try:
+            traffic = json.load(open(tp)).get('bytes_per_launch')
+        except Exception:
+            traffic = None
+    line = {
+        'metric': 'stream-updates/s (16 kHz int16 PCM, 1024-sample chunk -> decoded confidence + trigger)',
+        'value': value, 'unit': 'stream-updates/s', 'n_gpus': world, 'steps': K, 'warmup': W,
+        'ms_per_step': ms_all / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': 'per-GPU shard of configs[3]: %d streams/GPU x %d GPU, default hey-mycroft parameters '
+                               '(n_fft 512, hop 800, window 1600, n_filt 20, n_mfcc 13, GRU 20, 29-frame window), 1024-sample chunks' % (S, world),
+                   'streams_per_gpu': S, 'chunk_samples': CHUNK,
+                   'l2': ('inputs larger than L2: %d MB of PCM per tick, %d distinct ticks resident' % (S * CHUNK * 2 >> 20, NT))
+                         if flush is None else 'explicit 256 MB flush write between steps (its time measured separately and subtracted)',
+                   'parallelism': 'streams block-sharded over GPUs, NCCL all-reduce of the detection count per tick' if world > 1 else 'single GPU'},
+        'realtime_streams': value / 15.625,
+        'detections': total_fired,
+        'roofline': {'kernel': 'mfcc_stream_kernel (K1)', 'bound': 'hbm', 'achieved': k1_gbs, 'peak': hbm_peak, 'unit': 'GB/s',
+                     'frac': (k1_gbs / hbm_peak) if k1_gbs else None, 'of': which, 'traffic': traffic,
+                     'algorithmic_bytes_per_launch': S * ALG_BYTES_PER_UPDATE, 'ms_per_launch': k1_ms, 'launches': klaunch[0]},
+        'roofline_gru': {'kernel': 'gru_small_kernel<20,13> (K2+K3)', 'bound': 'fp32-fma', 'achieved': S * ALG_FLOP_PER_UPDATE_GRU / (k2_ms * 1e-3) / 1e12 if k2_ms > 0 else None,
+                         'peak': FP32_PEAK_TFLOPS, 'unit': 'TFLOP/s', 'frac': (S * ALG_FLOP_PER_UPDATE_GRU / (k2_ms * 1e-3) / 1e12 / FP32_PEAK_TFLOPS) if k2_ms > 0 else None,
+                         'of': 'nominal 148 SM x 128 lanes x 2 x 1.965 GHz', 'ms_per_launch': k2_ms, 'launches': klaunch[1]},
+        'e2e': e2e,
+        'gpu_launches': int(sum(klaunch)),
+        'cpu_baseline': ({'value': cpu[0], 'unit': 'stream-updates/s', 'cores': cpu[1], 'kind': 'port', 'sample': cpu[2]} if cpu else None),
+        'clocks': clocks,
+        'small_batch': small,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=50)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--streams-per-gpu', type=int, default=131072)
+    ap.add_argument('--ticks-resident', type=int, default=8)
+    ap.add_argument('--no-small-batch', dest='small_batch', action='store_false')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == 'reference':
+        run_reference(args, int(os.environ.get('RANK', '0')))
+        return
+    run_b200(args)
+
+
+if __name__ == '__main__':
+    main()

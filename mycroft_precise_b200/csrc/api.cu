@@ -1,0 +1,694 @@
+// api.cu -- C ABI of libprecise_b200.so (see include/precise_b200.h for the contract and the
+// reference interface each entry point replaces).  Host side: table construction (float64, then
+// rounded once), per-stream state allocation, launch configuration, the pinned/pipelined host
+// entry point and CUDA-event profiling.  No CPU compute path exists here by design.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <new>
+#include <vector>
+
+#include "../../include/precise_b200.h"
+#include "gru_kernels.cuh"
+#include "mfcc_kernels.cuh"
+
+using namespace pb;
+
+// ------------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CK(call)                                                                                  \
+    do {                                                                                          \
+        cudaError_t e_ = (call);                                                                  \
+        if (e_ != cudaSuccess)                                                                    \
+            return fail(PB_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+constexpr int N_PROFILE_SLOTS = 4;
+constexpr int PROFILE_POOL = 2048;
+constexpr int HOST_PIPE = 3;                 // internal streams of pb_update_host
+constexpr int64_t HOST_SUB_BATCH = 16384;    // streams per pipelined sub-batch (32 MiB of PCM at 1024 samples)
+
+struct ProfSlot {
+    std::vector<cudaEvent_t> ev;   // pairs
+    int used = 0;
+    double ms = 0.0;
+    uint64_t launches = 0;
+};
+
+struct pb_handle {
+    pb_config cfg;
+    int sm_count = 148;
+    // derived
+    int used = 0, n_bins = 0, n_out = 0, feat = 0, ring_rows = 0, row_stride = 0, tail_cap = 0, max_new = 0;
+    // host copies of tables
+    std::vector<double> fb;        // [n_filt][n_bins]
+    std::vector<double> cd;
+    int min_out = 0, max_out = 0;
+    // device tables
+    float *d_wrise = nullptr, *d_wfall = nullptr, *d_dct = nullptr;
+    int* d_grid = nullptr;
+    float2 *d_tw_stage = nullptr, *d_tw_post = nullptr;
+    double* d_cd = nullptr;
+    // state
+    StreamState st{};
+    // weights
+    bool have_weights = false;
+    bool small_path = false;
+    GruSmallW<20, 13> w_small;
+    float *d_wcat = nullptr, *d_bias = nullptr, *d_wd = nullptr;
+    float bd = 0.f;
+    // host pipeline
+    cudaStream_t pipe[HOST_PIPE] = {nullptr, nullptr, nullptr};
+    int16_t* d_stage_pcm[HOST_PIPE] = {nullptr, nullptr, nullptr};
+    int* d_stage_ids[HOST_PIPE] = {nullptr, nullptr, nullptr};
+    float* d_stage_raw[HOST_PIPE] = {nullptr, nullptr, nullptr};
+    double* d_stage_conf[HOST_PIPE] = {nullptr, nullptr, nullptr};
+    uint8_t* d_stage_fired[HOST_PIPE] = {nullptr, nullptr, nullptr};
+    unsigned long long* d_count = nullptr;
+    unsigned long long* h_count_pinned = nullptr;
+    // profiling
+    bool profiling = false;
+    ProfSlot prof[N_PROFILE_SLOTS];
+};
+
+// ------------------------------------------------------------------------------------------------
+// table construction (host, float64), restating sonopy.filterbanks as the reference calls it
+// (precise/vectorization.py:36-39): grid up to sample_rate, int() truncation, duplicate bins pushed
+// forward, np.linspace(endpoint=False) edge weights.
+static int build_mel(pb_handle* h, std::vector<float>& wrise, std::vector<float>& wfall, std::vector<int>& grid) {
+    const pb_config& c = h->cfg;
+    const int nb = h->n_bins, nf = c.n_filt;
+    const double top = 1127.0 * log(1.0 + (double)c.sample_rate / 700.0);
+    grid.assign(nf + 2, 0);
+    long long shift = 0, prev = -1;
+    for (int i = 0; i < nf + 2; ++i) {
+        // np.linspace(0, top, nf + 2): i * step, last element forced to stop
+        double m = (i == nf + 1) ? top : (double)i * (top / (double)(nf + 1));
+        double hz = 700.0 * (exp(m / 1127.0) - 1.0);
+        long long raw = (long long)(hz * (double)nb / (double)c.sample_rate);
+        if (i == 0) prev = raw - 1;
+        shift = std::max(0LL, shift + prev + 1 - raw);
+        grid[i] = (int)(raw + shift);
+        prev = raw;
+    }
+    if (grid[nf + 1] > nb)
+        return fail(PB_ERR_INVALID, "mel grid exceeds the spectrum (%d > %d bins): the reference's sonopy.filterbanks raises here", grid[nf + 1], nb);
+    h->fb.assign((size_t)nf * nb, 0.0);
+    wrise.assign(nb, 0.f);
+    wfall.assign(nb, 0.f);
+    for (int i = 0; i < nf; ++i) {
+        int lo = grid[i], mid = grid[i + 1], hi = grid[i + 2];
+        for (int k = lo; k < mid; ++k) h->fb[(size_t)i * nb + k] = (double)(k - lo) * (1.0 / (double)(mid - lo));
+        for (int k = mid; k < hi; ++k) h->fb[(size_t)i * nb + k] = (double)(k - mid) * (-1.0 / (double)(hi - mid)) + 1.0;
+        for (int k = lo; k < mid; ++k) wrise[k] = (float)h->fb[(size_t)i * nb + k];
+        for (int k = mid; k < hi; ++k) wfall[k] = (float)h->fb[(size_t)i * nb + k];
+    }
+    return PB_OK;
+}
+
+static void build_cdf(pb_handle* h) {
+    // precise/threshold_decoder.py:38-43, :68-70 and functions.pdf (:104-108)
+    const pb_config& c = h->cfg;
+    const int resolution = 200;
+    double lo = 0, hi = 0;
+    for (int i = 0; i < c.n_thresholds; ++i) {
+        double a = c.threshold_mu[i] + -4 * c.threshold_std[i], b = c.threshold_mu[i] + 4 * c.threshold_std[i];
+        if (i == 0 || a < lo) lo = a;
+        if (i == 0 || b > hi) hi = b;
+    }
+    h->min_out = (int)lo;
+    h->max_out = (int)hi;
+    const int range = h->max_out - h->min_out;
+    const int num = resolution * range;
+    h->cd.assign(std::max(num, 0), 0.0);
+    if (num <= 0) return;
+    const double step = num > 1 ? (double)(h->max_out - h->min_out) / (double)(num - 1) : 0.0;
+    double run = 0.0;
+    for (int j = 0; j < num; ++j) {
+        double x = (j == num - 1 && num > 1) ? (double)h->max_out : (double)j * step + (double)h->min_out;
+        double s = 0.0;
+        for (int i = 0; i < c.n_thresholds; ++i) {
+            double mu = c.threshold_mu[i], sd = c.threshold_std[i];
+            double p = sd == 0 ? 0.0 : (1.0 / (sd * sqrt(2 * M_PI))) * exp(-((x - mu) * (x - mu)) / (2 * (sd * sd)));
+            s = (i == 0) ? p : s + p;
+        }
+        run += s / (double)(resolution * c.n_thresholds);
+        h->cd[j] = run;
+    }
+}
+
+template <typename T>
+static cudaError_t upload(T** dst, const std::vector<T>& v) {
+    cudaError_t e = cudaMalloc((void**)dst, std::max<size_t>(v.size(), 1) * sizeof(T));
+    if (e != cudaSuccess) return e;
+    if (!v.empty()) e = cudaMemcpy(*dst, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
+    return e;
+}
+
+static bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+
+// ------------------------------------------------------------------------------------------------
+#define PB_API extern "C" __attribute__((visibility("default")))
+
+PB_API int pb_abi_version(void) { return PB_ABI_VERSION; }
+PB_API const char* pb_last_error(void) { return g_err; }
+PB_API const char* pb_build_info(void) { return "precise_b200 sm_100a " __DATE__ " " __TIME__; }
+
+PB_API int pb_config_default(pb_config* cfg) {
+    if (!cfg) return fail(PB_ERR_INVALID, "cfg is null");
+    memset(cfg, 0, sizeof(*cfg));
+    cfg->abi_version = PB_ABI_VERSION;
+    cfg->device = 0;
+    cfg->max_streams = 1;
+    cfg->chunk_samples = 1024;
+    cfg->sample_rate = 16000;
+    cfg->window_samples = 1600;
+    cfg->hop_samples = 800;
+    cfg->n_fft = 512;
+    cfg->n_filt = 20;
+    cfg->n_mfcc = 13;
+    cfg->n_features = 29;
+    cfg->use_delta = 0;
+    cfg->vectorizer = PB_VEC_MFCCS;
+    cfg->hidden = 20;
+    cfg->activation = PB_ACT_LINEAR;
+    cfg->recurrent_activation = PB_RACT_HARD_SIGMOID;
+    cfg->n_thresholds = 1;
+    cfg->threshold_mu[0] = 6.0;
+    cfg->threshold_std[0] = 4.0;
+    cfg->threshold_center = 0.2;
+    cfg->sensitivity = 0.5;
+    cfg->trigger_level = 3;
+    return PB_OK;
+}
+
+PB_API void pb_destroy(pb_handle* h) {
+    if (!h) return;
+    cudaSetDevice(h->cfg.device);
+    cudaFree(h->d_wrise); cudaFree(h->d_wfall); cudaFree(h->d_dct); cudaFree(h->d_grid);
+    cudaFree(h->d_tw_stage); cudaFree(h->d_tw_post); cudaFree(h->d_cd);
+    cudaFree(h->st.n_samples); cudaFree(h->st.tail); cudaFree(h->st.ring); cudaFree(h->st.trig);
+    cudaFree(h->d_wcat); cudaFree(h->d_bias); cudaFree(h->d_wd); cudaFree(h->d_count);
+    if (h->h_count_pinned) cudaFreeHost(h->h_count_pinned);
+    for (int i = 0; i < HOST_PIPE; ++i) {
+        cudaFree(h->d_stage_pcm[i]); cudaFree(h->d_stage_ids[i]); cudaFree(h->d_stage_raw[i]);
+        cudaFree(h->d_stage_conf[i]); cudaFree(h->d_stage_fired[i]);
+        if (h->pipe[i]) cudaStreamDestroy(h->pipe[i]);
+    }
+    for (auto& p : h->prof)
+        for (auto e : p.ev) cudaEventDestroy(e);
+    delete h;
+}
+
+PB_API int pb_create(const pb_config* cfg, pb_handle** out) {
+    if (!cfg || !out) return fail(PB_ERR_INVALID, "null argument");
+    *out = nullptr;
+    const pb_config& c = *cfg;
+    if (c.abi_version != PB_ABI_VERSION) return fail(PB_ERR_INVALID, "abi_version %d != %d", c.abi_version, PB_ABI_VERSION);
+    if (c.max_streams < 1) return fail(PB_ERR_INVALID, "max_streams must be >= 1");
+    if (c.chunk_samples < 1) return fail(PB_ERR_INVALID, "chunk_samples must be >= 1");
+    if (c.sample_rate < 1 || c.window_samples < 1 || c.hop_samples < 1 || c.n_features < 1 || c.hidden < 1)
+        return fail(PB_ERR_INVALID, "sample_rate, window_samples, hop_samples, n_features, hidden must be positive");
+    if (c.vectorizer == PB_VEC_SPEECHPY_MFCCS)
+        return fail(PB_ERR_UNSUPPORTED, "Vectorizer.speechpy_mfccs (legacy .params without 'vectorizer', precise/params.py:147) is not implemented");
+    if (c.vectorizer != PB_VEC_MFCCS && c.vectorizer != PB_VEC_MELS) return fail(PB_ERR_INVALID, "unknown vectorizer %d", c.vectorizer);
+    if (c.n_fft != 512) return fail(PB_ERR_UNSUPPORTED, "n_fft %d: only n_fft = 512 (the reference default) is implemented", c.n_fft);
+    if (!is_pow2(c.n_fft)) return fail(PB_ERR_INVALID, "n_fft must be a power of two");
+    if (c.n_filt < 1 || c.n_filt > 64 || c.n_mfcc < 1 || c.n_mfcc > 64) return fail(PB_ERR_UNSUPPORTED, "n_filt and n_mfcc must be in [1, 64]");
+    if (c.n_thresholds < 1 || c.n_thresholds > PB_MAX_THRESHOLDS) return fail(PB_ERR_INVALID, "n_thresholds must be in [1, %d]", PB_MAX_THRESHOLDS);
+    if (c.activation < 0 || c.activation > 1 || c.recurrent_activation < 0 || c.recurrent_activation > 1)
+        return fail(PB_ERR_UNSUPPORTED, "unsupported GRU activation");
+    int ndev = 0;
+    CK(cudaGetDeviceCount(&ndev));
+    if (c.device < 0 || c.device >= ndev) return fail(PB_ERR_CUDA, "device %d not available (%d visible)", c.device, ndev);
+    CK(cudaSetDevice(c.device));
+
+    pb_handle* h = new (std::nothrow) pb_handle();
+    if (!h) return fail(PB_ERR_CUDA, "out of host memory");
+    h->cfg = c;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, c.device) == cudaSuccess) h->sm_count = prop.multiProcessorCount;
+    h->used = std::min(c.n_fft, c.window_samples);
+    h->n_bins = c.n_fft / 2 + 1;
+    h->n_out = c.vectorizer == PB_VEC_MELS ? c.n_filt : std::min(c.n_filt, c.n_mfcc);
+    h->feat = h->n_out * (c.use_delta ? 2 : 1);
+    h->row_stride = (h->n_out + 3) & ~3;
+    h->ring_rows = c.n_features + (c.window_samples - h->used) / c.hop_samples + 2;
+    h->tail_cap = (h->used + 1) & ~1;
+    h->max_new = c.chunk_samples / c.hop_samples + 2;
+
+    std::vector<float> wrise, wfall;
+    std::vector<int> grid;
+    int rc = build_mel(h, wrise, wfall, grid);
+    if (rc != PB_OK) { delete h; return rc; }
+    // DCT-II, norm='ortho' (scipy.fftpack.dct as sonopy.mfcc_spec calls it), first n_out rows
+    std::vector<float> dct((size_t)h->n_out * c.n_filt);
+    for (int k = 0; k < h->n_out; ++k)
+        for (int n = 0; n < c.n_filt; ++n) {
+            double v = cos(M_PI * k * (2 * n + 1) / (2.0 * c.n_filt)) * sqrt(2.0 / c.n_filt);
+            if (k == 0) v *= sqrt(0.5);
+            dct[(size_t)k * c.n_filt + n] = (float)v;
+        }
+    std::vector<float2> tws(256), twp(16);
+    for (int n2 = 0; n2 < 16; ++n2)
+        for (int k1 = 0; k1 < 16; ++k1) {
+            double a = 2.0 * M_PI * (double)(n2 * k1) / 256.0;
+            tws[n2 * 16 + k1] = make_float2((float)cos(a), (float)-sin(a));
+        }
+    for (int k1 = 0; k1 < 16; ++k1) {
+        double a = 2.0 * M_PI * (double)k1 / 512.0;
+        twp[k1] = make_float2((float)cos(a), (float)sin(a));
+    }
+    build_cdf(h);
+
+#define CKH(call)                                                                                 \
+    do {                                                                                          \
+        cudaError_t e_ = (call);                                                                  \
+        if (e_ != cudaSuccess) {                                                                  \
+            pb_destroy(h);                                                                        \
+            return fail(PB_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_));             \
+        }                                                                                         \
+    } while (0)
+    CKH(upload(&h->d_wrise, wrise));
+    CKH(upload(&h->d_wfall, wfall));
+    CKH(upload(&h->d_grid, grid));
+    CKH(upload(&h->d_dct, dct));
+    CKH(upload(&h->d_tw_stage, tws));
+    CKH(upload(&h->d_tw_post, twp));
+    CKH(upload(&h->d_cd, h->cd));
+    const size_t S = (size_t)c.max_streams;
+    h->st.tail_cap = h->tail_cap; h->st.ring_rows = h->ring_rows; h->st.row_stride = h->row_stride;
+    CKH(cudaMalloc((void**)&h->st.n_samples, S * sizeof(long long)));
+    CKH(cudaMalloc((void**)&h->st.tail, S * h->tail_cap * sizeof(int16_t)));
+    CKH(cudaMalloc((void**)&h->st.ring, S * h->ring_rows * h->row_stride * sizeof(float)));
+    CKH(cudaMalloc((void**)&h->st.trig, S * sizeof(int)));
+    CKH(cudaMemset(h->st.n_samples, 0, S * sizeof(long long)));
+    CKH(cudaMemset(h->st.tail, 0, S * h->tail_cap * sizeof(int16_t)));
+    CKH(cudaMemset(h->st.ring, 0, S * h->ring_rows * h->row_stride * sizeof(float)));
+    CKH(cudaMemset(h->st.trig, 0, S * sizeof(int)));
+    CKH(cudaMalloc((void**)&h->d_count, sizeof(unsigned long long)));
+    CKH(cudaMemset(h->d_count, 0, sizeof(unsigned long long)));
+    CKH(cudaFuncSetAttribute(mfcc_batch_kernel<int16_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1Smem)));
+    CKH(cudaFuncSetAttribute(mfcc_batch_kernel<int16_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1Smem)));
+    CKH(cudaFuncSetAttribute(mfcc_batch_kernel<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1Smem)));
+    CKH(cudaFuncSetAttribute(mfcc_batch_kernel<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1Smem)));
+    CKH(cudaFuncSetAttribute(mfcc_stream_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1StreamSmem)));
+    CKH(cudaFuncSetAttribute(mfcc_stream_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1StreamSmem)));
+#undef CKH
+    *out = h;
+    return PB_OK;
+}
+
+PB_API int64_t pb_mfcc_frames(const pb_handle* h, int64_t n) {
+    if (!h) return 0;
+    return n < h->cfg.window_samples ? 0 : (n - h->cfg.window_samples) / h->cfg.hop_samples + 1;
+}
+PB_API int32_t pb_feature_size(const pb_handle* h) { return h ? h->feat : 0; }
+PB_API int32_t pb_mfcc_width(const pb_handle* h) { return h ? h->n_out : 0; }
+
+PB_API int pb_get_filterbank(const pb_handle* h, double* out) {
+    if (!h || !out) return fail(PB_ERR_INVALID, "null argument");
+    memcpy(out, h->fb.data(), h->fb.size() * sizeof(double));
+    return PB_OK;
+}
+
+PB_API int64_t pb_get_cdf(const pb_handle* h, double* out, int64_t capacity, int32_t* min_out, int32_t* max_out) {
+    if (!h) return fail(PB_ERR_INVALID, "null handle");
+    if (min_out) *min_out = h->min_out;
+    if (max_out) *max_out = h->max_out;
+    if (out) memcpy(out, h->cd.data(), std::min<int64_t>(capacity, (int64_t)h->cd.size()) * sizeof(double));
+    return (int64_t)h->cd.size();
+}
+
+PB_API int pb_set_cdf(pb_handle* h, const double* cd, int64_t len) {
+    if (!h || !cd) return fail(PB_ERR_INVALID, "null argument");
+    if (len != (int64_t)h->cd.size()) return fail(PB_ERR_INVALID, "cdf length %lld != %zu", (long long)len, h->cd.size());
+    CK(cudaSetDevice(h->cfg.device));
+    memcpy(h->cd.data(), cd, len * sizeof(double));
+    if (len) CK(cudaMemcpy(h->d_cd, cd, len * sizeof(double), cudaMemcpyHostToDevice));
+    return PB_OK;
+}
+
+PB_API int pb_load_weights(pb_handle* h, const float* kernel, const float* recurrent, const float* bias,
+                    const float* dense_w, float dense_b) {
+    if (!h || !kernel || !recurrent || !bias || !dense_w) return fail(PB_ERR_INVALID, "null argument");
+    CK(cudaSetDevice(h->cfg.device));
+    const int H = h->cfg.hidden, F = h->feat, H3 = 3 * H;
+    std::vector<float> wcat((size_t)(F + H) * H3);
+    memcpy(wcat.data(), kernel, (size_t)F * H3 * sizeof(float));
+    memcpy(wcat.data() + (size_t)F * H3, recurrent, (size_t)H * H3 * sizeof(float));
+    cudaFree(h->d_wcat); cudaFree(h->d_bias); cudaFree(h->d_wd);
+    h->d_wcat = h->d_bias = h->d_wd = nullptr;
+    CK(upload(&h->d_wcat, wcat));
+    CK(upload(&h->d_bias, std::vector<float>(bias, bias + H3)));
+    CK(upload(&h->d_wd, std::vector<float>(dense_w, dense_w + H)));
+    h->bd = dense_b;
+    h->small_path = (H == 20 && F == 13 && !h->cfg.use_delta && h->cfg.activation == PB_ACT_LINEAR &&
+                     h->cfg.recurrent_activation == PB_RACT_HARD_SIGMOID);
+    if (h->small_path) {
+        memcpy(h->w_small.W, kernel, sizeof(h->w_small.W));
+        memcpy(h->w_small.U, recurrent, sizeof(h->w_small.U));
+        memcpy(h->w_small.b, bias, sizeof(h->w_small.b));
+        memcpy(h->w_small.wd, dense_w, sizeof(h->w_small.wd));
+        h->w_small.bd = dense_b;
+    } else {
+        size_t smem = (size_t)(F + 3 * H) * K2_TILE_STREAMS * sizeof(float);
+        if (smem > 200 * 1024) return fail(PB_ERR_UNSUPPORTED, "feature_size + 3*hidden = %d is too large for the tiled GRU kernel", F + 3 * H);
+        CK(cudaFuncSetAttribute(gru_tiled_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CK(cudaFuncSetAttribute(gru_tiled_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
+    h->have_weights = true;
+    return PB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// profiling helpers
+struct ProfScope {
+    pb_handle* h; int slot; cudaStream_t s; int idx = -1;
+    ProfScope(pb_handle* h_, int slot_, cudaStream_t s_) : h(h_), slot(slot_), s(s_) {
+        if (!h->profiling) return;
+        ProfSlot& p = h->prof[slot];
+        if (p.used + 2 > (int)p.ev.size()) {
+            if ((int)p.ev.size() >= 2 * PROFILE_POOL) {          // pool full: fold what we have
+                for (int i = 0; i + 1 < p.used; i += 2) {
+                    cudaEventSynchronize(p.ev[i + 1]);
+                    float ms = 0; cudaEventElapsedTime(&ms, p.ev[i], p.ev[i + 1]); p.ms += ms;
+                }
+                p.used = 0;
+            } else {
+                cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b); p.ev.push_back(a); p.ev.push_back(b);
+            }
+        }
+        idx = p.used; p.used += 2; p.launches++;
+        cudaEventRecord(p.ev[idx], s);
+    }
+    ~ProfScope() { if (idx >= 0) cudaEventRecord(h->prof[slot].ev[idx + 1], s); }
+};
+
+PB_API int pb_profile_enable(pb_handle* h, int on) { if (!h) return fail(PB_ERR_INVALID, "null handle"); h->profiling = on != 0; return PB_OK; }
+
+PB_API int pb_profile_reset(pb_handle* h) {
+    if (!h) return fail(PB_ERR_INVALID, "null handle");
+    for (auto& p : h->prof) { p.used = 0; p.ms = 0; p.launches = 0; }
+    return PB_OK;
+}
+
+PB_API int pb_profile_read(pb_handle* h, double ms[4], uint64_t launches[4]) {
+    if (!h) return fail(PB_ERR_INVALID, "null handle");
+    CK(cudaSetDevice(h->cfg.device));
+    for (int s = 0; s < N_PROFILE_SLOTS; ++s) {
+        ProfSlot& p = h->prof[s];
+        for (int i = 0; i + 1 < p.used; i += 2) {
+            CK(cudaEventSynchronize(p.ev[i + 1]));
+            float t = 0; CK(cudaEventElapsedTime(&t, p.ev[i], p.ev[i + 1])); p.ms += t;
+        }
+        p.used = 0;
+        if (ms) ms[s] = p.ms;
+        if (launches) launches[s] = p.launches;
+    }
+    return PB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+static MelTables mel_tables(const pb_handle* h) {
+    MelTables t;
+    t.w_rise = h->d_wrise; t.w_fall = h->d_wfall; t.grid = h->d_grid; t.dct = h->d_dct;
+    t.tw_stage = h->d_tw_stage; t.tw_post = h->d_tw_post;
+    t.n_bins = h->n_bins; t.n_filt = h->cfg.n_filt; t.n_out = h->n_out;
+    t.mels_only = h->cfg.vectorizer == PB_VEC_MELS;
+    return t;
+}
+
+static DecodeParams decode_params(const pb_handle* h) {
+    DecodeParams d;
+    d.cd = h->d_cd; d.cd_len = (int)h->cd.size();
+    d.min_out = h->min_out; d.out_range = h->max_out - h->min_out;
+    d.center = h->cfg.threshold_center;
+    d.hot_threshold = 1.0 - h->cfg.sensitivity;
+    d.trigger_level = h->cfg.trigger_level;
+    const long long bytes = 2LL * h->cfg.chunk_samples;          // TriggerDetector.chunk_size is in bytes
+    long long q = -(8 * 2048) / bytes;                            // C truncates toward zero ...
+    if ((-(8 * 2048)) % bytes != 0) q -= 1;                       // ... python floors
+    d.trigger_reset = (int)q;
+    return d;
+}
+
+template <typename T>
+static int mfcc_impl(pb_handle* h, const T* d_in, int64_t n_streams, int64_t L, float* d_out, cudaStream_t s, float scale) {
+    if (!h) return fail(PB_ERR_INVALID, "null handle");
+    if (n_streams < 0 || L < 0) return fail(PB_ERR_INVALID, "negative size");
+    if (L == 0 && n_streams > 0) return fail(PB_ERR_INVALID, "Cannot vectorize empty audio!");   // vectorization.py:48-49
+    const int64_t nf = pb_mfcc_frames(h, L), total = nf * n_streams;
+    if (total == 0) return PB_OK;
+    if (!d_in || !d_out) return fail(PB_ERR_INVALID, "null buffer");
+    CK(cudaSetDevice(h->cfg.device));
+    const bool pairs = (L % 2 == 0) && (h->cfg.hop_samples % 2 == 0) && (h->used % 2 == 0) &&
+                       ((uintptr_t)d_in % (2 * sizeof(T)) == 0);
+    const int64_t tiles = (total + K1_TILE - 1) / K1_TILE;
+    const int grid = (int)std::min<int64_t>(tiles, (int64_t)h->sm_count * 4);
+    ProfScope ps(h, 0, s);
+    if (pairs)
+        mfcc_batch_kernel<T, true><<<grid, K1_THREADS, sizeof(K1Smem), s>>>(d_in, L, nf, total, h->cfg.hop_samples, h->used, scale, mel_tables(h), d_out);
+    else
+        mfcc_batch_kernel<T, false><<<grid, K1_THREADS, sizeof(K1Smem), s>>>(d_in, L, nf, total, h->cfg.hop_samples, h->used, scale, mel_tables(h), d_out);
+    CK(cudaGetLastError());
+    return PB_OK;
+}
+
+PB_API int pb_mfcc(pb_handle* h, const int16_t* d_pcm, int64_t n_streams, int64_t L, float* d_out, void* stream) {
+    if (!h) return fail(PB_ERR_INVALID, "null handle");
+    const float inv = 1.0f / 32768.0f;
+    return mfcc_impl<int16_t>(h, d_pcm, n_streams, L, d_out, (cudaStream_t)stream, inv * inv / (float)h->cfg.n_fft);
+}
+
+PB_API int pb_mfcc_f32(pb_handle* h, const float* d_audio, int64_t n_streams, int64_t L, float* d_out, void* stream) {
+    if (!h) return fail(PB_ERR_INVALID, "null handle");
+    return mfcc_impl<float>(h, d_audio, n_streams, L, d_out, (cudaStream_t)stream, 1.0f / (float)h->cfg.n_fft);
+}
+
+static int launch_gru(pb_handle* h, const K2In& in, bool ring, int64_t n, const DecodeParams& dp, const K2Out& o, cudaStream_t s) {
+    ProfScope ps(h, 1, s);
+    if (h->small_path) {
+        const int grid = (int)((n + K2_SMALL_THREADS - 1) / K2_SMALL_THREADS);
+        if (ring) gru_small_kernel<20, 13, true><<<grid, K2_SMALL_THREADS, 0, s>>>(h->w_small, in, n, dp, o);
+        else gru_small_kernel<20, 13, false><<<grid, K2_SMALL_THREADS, 0, s>>>(h->w_small, in, n, dp, o);
+    } else {
+        GruTiledW w;
+        w.wcat = h->d_wcat; w.bias = h->d_bias; w.wd = h->d_wd; w.bd = h->bd;
+        w.H = h->cfg.hidden; w.F_in = h->feat; w.act = h->cfg.activation; w.ract = h->cfg.recurrent_activation;
+        const size_t smem = (size_t)(w.F_in + 3 * w.H) * K2_TILE_STREAMS * sizeof(float);
+        const int grid = (int)((n + K2_TILE_STREAMS - 1) / K2_TILE_STREAMS);
+        if (ring) gru_tiled_kernel<true><<<grid, K2_TILE_THREADS, smem, s>>>(w, in, n, dp, o);
+        else gru_tiled_kernel<false><<<grid, K2_TILE_THREADS, smem, s>>>(w, in, n, dp, o);
+    }
+    CK(cudaGetLastError());
+    return PB_OK;
+}
+
+PB_API int pb_predict(pb_handle* h, const float* d_inputs, int64_t n, float* d_out, float* d_logit, void* stream) {
+    if (!h) return fail(PB_ERR_INVALID, "null handle");
+    if (!h->have_weights) return fail(PB_ERR_STATE, "pb_load_weights has not been called");
+    if (n < 0) return fail(PB_ERR_INVALID, "negative n");
+    if (n == 0) return PB_OK;
+    if (!d_inputs || !d_out) return fail(PB_ERR_INVALID, "null buffer");
+    CK(cudaSetDevice(h->cfg.device));
+    K2In in{};
+    in.inputs = d_inputs; in.T = h->cfg.n_features; in.F_base = h->n_out; in.use_delta = 0;
+    K2Out o{};
+    o.raw = d_out; o.logit = d_logit;
+    return launch_gru(h, in, false, n, decode_params(h), o, (cudaStream_t)stream);
+}
+
+PB_API int pb_decode(pb_handle* h, const float* d_raw, int64_t n, double* d_conf, void* stream) {
+    if (!h) return fail(PB_ERR_INVALID, "null handle");
+    if (n < 0) return fail(PB_ERR_INVALID, "negative n");
+    if (n == 0) return PB_OK;
+    if (!d_raw || !d_conf) return fail(PB_ERR_INVALID, "null buffer");
+    CK(cudaSetDevice(h->cfg.device));
+    cudaStream_t s = (cudaStream_t)stream;
+    ProfScope ps(h, 2, s);
+    decode_kernel<<<(int)((n + 255) / 256), 256, 0, s>>>(d_raw, n, decode_params(h), d_conf);
+    CK(cudaGetLastError());
+    return PB_OK;
+}
+
+static int check_tick(pb_handle* h, const void* pcm, int64_t n) {
+    if (!h) return fail(PB_ERR_INVALID, "null handle");
+    if (n < 0 || n > h->cfg.max_streams) return fail(PB_ERR_INVALID, "n = %lld outside [0, max_streams = %d]", (long long)n, h->cfg.max_streams);
+    if (n > 0 && !pcm) return fail(PB_ERR_INVALID, "null pcm");
+    if (h->max_new > 8) return fail(PB_ERR_UNSUPPORTED, "chunk_samples %d yields up to %d frames per tick (> 8): feed smaller chunks", h->cfg.chunk_samples, h->max_new);
+    return PB_OK;
+}
+
+static int launch_stream_mfcc(pb_handle* h, const int16_t* d_pcm, const int32_t* d_ids, int64_t n, cudaStream_t s) {
+    const bool pairs = (h->cfg.chunk_samples % 2 == 0) && (h->cfg.hop_samples % 2 == 0) && (h->used % 2 == 0) &&
+                       ((uintptr_t)d_pcm % 4 == 0);
+    const int64_t tiles = (n + K1_STREAMS_PER_CTA - 1) / K1_STREAMS_PER_CTA;
+    const int grid = (int)std::min<int64_t>(tiles, (int64_t)h->sm_count * 4);
+    const float inv = 1.0f / 32768.0f, scale = inv * inv / (float)h->cfg.n_fft;
+    ProfScope ps(h, 0, s);
+    if (pairs)
+        mfcc_stream_kernel<true><<<grid, K1_THREADS, sizeof(K1StreamSmem), s>>>(d_pcm, d_ids, (int)n, h->cfg.chunk_samples, h->cfg.hop_samples, h->used, h->max_new, scale, mel_tables(h), h->st);
+    else
+        mfcc_stream_kernel<false><<<grid, K1_THREADS, sizeof(K1StreamSmem), s>>>(d_pcm, d_ids, (int)n, h->cfg.chunk_samples, h->cfg.hop_samples, h->used, h->max_new, scale, mel_tables(h), h->st);
+    CK(cudaGetLastError());
+    return PB_OK;
+}
+
+PB_API int pb_update_vectors(pb_handle* h, const int16_t* d_pcm, const int32_t* d_ids, int64_t n, void* stream) {
+    int rc = check_tick(h, d_pcm, n);
+    if (rc != PB_OK || n == 0) return rc;
+    CK(cudaSetDevice(h->cfg.device));
+    return launch_stream_mfcc(h, d_pcm, d_ids, n, (cudaStream_t)stream);
+}
+
+PB_API int pb_update(pb_handle* h, const int16_t* d_pcm, const int32_t* d_ids, int64_t n, float* d_raw, double* d_conf,
+              uint8_t* d_fired, unsigned long long* d_count, void* stream) {
+    int rc = check_tick(h, d_pcm, n);
+    if (rc != PB_OK || n == 0) return rc;
+    if (!h->have_weights) return fail(PB_ERR_STATE, "pb_load_weights has not been called");
+    if (!d_conf) return fail(PB_ERR_INVALID, "null d_conf");
+    CK(cudaSetDevice(h->cfg.device));
+    cudaStream_t s = (cudaStream_t)stream;
+    rc = launch_stream_mfcc(h, d_pcm, d_ids, n, s);
+    if (rc != PB_OK) return rc;
+    K2In in{};
+    in.ring = h->st.ring; in.n_samples = h->st.n_samples; in.ids = d_ids;
+    in.ring_rows = h->ring_rows; in.row_stride = h->row_stride; in.window = h->cfg.window_samples; in.hop = h->cfg.hop_samples;
+    in.T = h->cfg.n_features; in.F_base = h->n_out; in.use_delta = h->cfg.use_delta;
+    K2Out o{};
+    o.raw = d_raw; o.conf = d_conf; o.fired = d_fired; o.count = d_count; o.trig = h->st.trig;
+    return launch_gru(h, in, true, n, decode_params(h), o, s);
+}
+
+__global__ void read_window_kernel(K2In in, const int* ids, long long n, float* out) {
+    // one thread per (item, row, column)
+    const int Fb = in.F_base;
+    long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long total = n * in.T * Fb;
+    if (e >= total) return;
+    int f = (int)(e % Fb);
+    long long q = e / Fb;
+    int t = (int)(q % in.T);
+    long long i = q / in.T;
+    int sid = ids ? ids[i] : (int)i;
+    long long ns = in.n_samples[sid];
+    long long rel = ns >= in.window ? (ns - in.window) / in.hop + 1 : 0;
+    const float* row = ring_row(in, sid, rel, t);
+    out[e] = row ? row[f] : 0.f;
+}
+
+PB_API int pb_read_window(pb_handle* h, const int32_t* d_ids, int64_t n, float* d_out, void* stream) {
+    if (!h) return fail(PB_ERR_INVALID, "null handle");
+    if (n < 0 || n > h->cfg.max_streams) return fail(PB_ERR_INVALID, "bad n");
+    if (n == 0) return PB_OK;
+    if (!d_out) return fail(PB_ERR_INVALID, "null buffer");
+    CK(cudaSetDevice(h->cfg.device));
+    K2In in{};
+    in.ring = h->st.ring; in.n_samples = h->st.n_samples; in.ids = d_ids;
+    in.ring_rows = h->ring_rows; in.row_stride = h->row_stride; in.window = h->cfg.window_samples; in.hop = h->cfg.hop_samples;
+    in.T = h->cfg.n_features; in.F_base = h->n_out;
+    long long total = n * in.T * in.F_base;
+    read_window_kernel<<<(int)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(in, d_ids, n, d_out);
+    CK(cudaGetLastError());
+    return PB_OK;
+}
+
+__global__ void clear_kernel(StreamState st, const int* ids, long long n) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int sid = ids ? ids[i] : (int)i;
+    st.n_samples[sid] = 0;
+    st.trig[sid] = 0;
+}
+
+PB_API int pb_clear(pb_handle* h, const int32_t* d_ids, int64_t n, void* stream) {
+    if (!h) return fail(PB_ERR_INVALID, "null handle");
+    if (n < 0 || n > h->cfg.max_streams) return fail(PB_ERR_INVALID, "bad n");
+    if (n == 0) return PB_OK;
+    CK(cudaSetDevice(h->cfg.device));
+    clear_kernel<<<(int)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(h->st, d_ids, n);
+    CK(cudaGetLastError());
+    return PB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+PB_API int pb_host_alloc(void** out, uint64_t bytes) {
+    if (!out) return fail(PB_ERR_INVALID, "null argument");
+    CK(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault));
+    return PB_OK;
+}
+
+PB_API int pb_host_free(void* p) {
+    if (p) CK(cudaFreeHost(p));
+    return PB_OK;
+}
+
+static int ensure_pipe(pb_handle* h) {
+    if (h->pipe[0]) return PB_OK;
+    const int64_t sb = std::min<int64_t>(HOST_SUB_BATCH, h->cfg.max_streams);
+    for (int i = 0; i < HOST_PIPE; ++i) {
+        CK(cudaStreamCreateWithFlags(&h->pipe[i], cudaStreamNonBlocking));
+        CK(cudaMalloc((void**)&h->d_stage_pcm[i], sb * h->cfg.chunk_samples * sizeof(int16_t)));
+        CK(cudaMalloc((void**)&h->d_stage_ids[i], sb * sizeof(int)));
+        CK(cudaMalloc((void**)&h->d_stage_raw[i], sb * sizeof(float)));
+        CK(cudaMalloc((void**)&h->d_stage_conf[i], sb * sizeof(double)));
+        CK(cudaMalloc((void**)&h->d_stage_fired[i], sb * sizeof(uint8_t)));
+    }
+    CK(cudaHostAlloc((void**)&h->h_count_pinned, sizeof(unsigned long long), cudaHostAllocDefault));
+    return PB_OK;
+}
+
+__global__ void iota_kernel(int* ids, int base, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) ids[i] = base + i;
+}
+
+PB_API int pb_update_host(pb_handle* h, const int16_t* h_pcm, const int32_t* h_ids, int64_t n, float* h_raw, double* h_conf,
+                   uint8_t* h_fired, unsigned long long* h_count) {
+    int rc = check_tick(h, h_pcm, n);
+    if (rc != PB_OK) return rc;
+    if (n == 0) { if (h_count) *h_count = 0; return PB_OK; }
+    if (!h->have_weights) return fail(PB_ERR_STATE, "pb_load_weights has not been called");
+    if (!h_conf) return fail(PB_ERR_INVALID, "null h_conf");
+    CK(cudaSetDevice(h->cfg.device));
+    rc = ensure_pipe(h);
+    if (rc != PB_OK) return rc;
+    const int64_t sb = std::min<int64_t>(HOST_SUB_BATCH, h->cfg.max_streams);
+    const int chunk = h->cfg.chunk_samples;
+    CK(cudaMemsetAsync(h->d_count, 0, sizeof(unsigned long long), h->pipe[0]));
+    CK(cudaStreamSynchronize(h->pipe[0]));
+    int p = 0;
+    for (int64_t off = 0; off < n; off += sb, p = (p + 1) % HOST_PIPE) {
+        const int64_t m = std::min(sb, n - off);
+        cudaStream_t s = h->pipe[p];
+        CK(cudaMemcpyAsync(h->d_stage_pcm[p], h_pcm + off * chunk, m * chunk * sizeof(int16_t), cudaMemcpyHostToDevice, s));
+        if (h_ids) CK(cudaMemcpyAsync(h->d_stage_ids[p], h_ids + off, m * sizeof(int), cudaMemcpyHostToDevice, s));
+        else { iota_kernel<<<(int)((m + 255) / 256), 256, 0, s>>>(h->d_stage_ids[p], (int)off, (int)m); CK(cudaGetLastError()); }
+        rc = pb_update(h, h->d_stage_pcm[p], h->d_stage_ids[p], m, h_raw ? h->d_stage_raw[p] : nullptr, h->d_stage_conf[p],
+                       h_fired ? h->d_stage_fired[p] : nullptr, h->d_count, s);
+        if (rc != PB_OK) return rc;
+        CK(cudaMemcpyAsync(h_conf + off, h->d_stage_conf[p], m * sizeof(double), cudaMemcpyDeviceToHost, s));
+        if (h_raw) CK(cudaMemcpyAsync(h_raw + off, h->d_stage_raw[p], m * sizeof(float), cudaMemcpyDeviceToHost, s));
+        if (h_fired) CK(cudaMemcpyAsync(h_fired + off, h->d_stage_fired[p], m * sizeof(uint8_t), cudaMemcpyDeviceToHost, s));
+    }
+    for (int i = 0; i < HOST_PIPE; ++i) CK(cudaStreamSynchronize(h->pipe[i]));
+    CK(cudaMemcpy(h->h_count_pinned, h->d_count, sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    if (h_count) *h_count = *h->h_count_pinned;
+    return PB_OK;
+}
+

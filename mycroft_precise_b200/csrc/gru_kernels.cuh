@@ -1,0 +1,363 @@
+// gru_kernels.cuh -- K2 (GRU window scan + Dense + sigmoid) fused with K3 (threshold decode,
+// trigger debounce, detection count).
+//
+// Network: precise/model.py:77-82 -- GRU(H, activation='linear', Keras default
+// recurrent_activation='hard_sigmoid', reset_after=False) + Dense(1,'sigmoid'), evaluated from
+// h0 = 0 over all T = n_features rows on every update (precise/network_runner.py:148-153).
+// Decode: precise/threshold_decoder.py:45-57.  Trigger: runner/precise_runner/runner.py:127-142.
+//
+// gru_small_kernel<H,F>: one thread per stream.  The whole weight set (8.2 KB at H=20, F=13) is a
+//   __grid_constant__ kernel parameter, i.e. it sits in the constant bank and every FFMA takes
+//   its weight as a constant operand: no weight loads at all, h/z/r stay in registers.
+// gru_tiled_kernel: any H, F.  A CTA owns 64 streams; per step two register-tiled SGEMM phases
+//   ([x,h] x [Wz|Wr], then [x,r*h] x Wh) with activations in shared memory and weights streamed
+//   through L1/L2.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace pb {
+
+struct DecodeParams {
+    const double* cd;        // cumulative distribution LUT
+    int cd_len;
+    int min_out, out_range;
+    double center;
+    double hot_threshold;    // 1.0 - sensitivity
+    int trigger_level;
+    int trigger_reset;       // -(8*2048) // chunk_bytes  (python floor division)
+};
+
+struct K2Out {
+    float* raw;                      // [n] or null
+    float* logit;                    // [n] or null
+    double* conf;                    // [n] or null
+    uint8_t* fired;                  // [n] or null
+    unsigned long long* count;       // [1] or null
+    int* trig;                       // [max_streams] or null => no trigger update
+};
+
+// Where row t of item i comes from.
+struct K2In {
+    const float* inputs;             // predict mode: [n][T][F_in] contiguous
+    const float* ring;               // stream mode: [max_streams][ring_rows][row_stride]
+    const long long* n_samples;      // stream mode: samples consumed (after this tick)
+    const int* ids;                  // stream mode: item -> stream id (null = identity)
+    int ring_rows, row_stride, window, hop;
+    int T, F_base;                   // F_base = MFCC width (without deltas)
+    int use_delta;
+};
+
+__device__ __forceinline__ float hard_sigmoid(float x) { return fminf(fmaxf(fmaf(0.2f, x, 0.5f), 0.f), 1.f); }
+__device__ __forceinline__ float sigmoid32(float x) { return 1.f / (1.f + expf(-x)); }
+
+template <int RACT>
+__device__ __forceinline__ float ract(float x) { return RACT == 0 ? hard_sigmoid(x) : sigmoid32(x); }
+template <int ACT>
+__device__ __forceinline__ float act(float x) { return ACT == 0 ? x : tanhf(x); }
+
+// ThresholdDecoder.decode on a float32 network output, in float64 like the reference.
+__device__ __forceinline__ double decode_one(float raw, const DecodeParams& d) {
+    const double r = (double)raw;
+    if (raw == 1.0f || raw == 0.0f) return r;
+    double cp;
+    if (d.out_range == 0) {
+        cp = r > (double)d.min_out ? 1.0 : 0.0;
+    } else {
+        double lg = -log(1.0 / r - 1.0);                               // functions.asigmoid
+        double ratio = (lg - (double)d.min_out) / (double)d.out_range;
+        ratio = fmin(fmax(ratio, 0.0), 1.0);
+        int idx = (int)__dadd_rn(__dmul_rn(ratio, (double)(d.cd_len - 1)), 0.5);
+        cp = d.cd[idx];
+    }
+    if (cp < d.center) return __dmul_rn(0.5, cp) / d.center;
+    return __dadd_rn(0.5, __dmul_rn(0.5, cp - d.center) / (1.0 - d.center));
+}
+
+// Sigmoid + decode + trigger + count for item i (stream sid).  Called by every thread of the
+// warp (valid = false for padding lanes) because the count is warp-aggregated.
+__device__ __forceinline__ void epilogue(float logit, bool valid, long long i, int sid,
+                                         const DecodeParams& d, const K2Out& o) {
+    bool fired = false;
+    if (valid) {
+        float raw = sigmoid32(logit);
+        if (o.logit) o.logit[i] = logit;
+        if (o.raw) o.raw[i] = raw;
+        if (o.conf || o.trig) {
+            double conf = decode_one(raw, d);
+            if (o.conf) o.conf[i] = conf;
+            if (o.trig) {
+                int a = o.trig[sid];
+                const bool hot = conf > d.hot_threshold;
+                if (hot || a < 0) {
+                    a += 1;
+                    fired = a > d.trigger_level;
+                    if (fired || (hot && a < 0)) a = d.trigger_reset;
+                } else if (a > 0) {
+                    a -= 1;
+                }
+                o.trig[sid] = a;
+                if (o.fired) o.fired[i] = fired ? 1 : 0;
+            }
+        }
+    }
+    if (o.count) {
+        unsigned m = __ballot_sync(0xffffffffu, fired);
+        if (m && (threadIdx.x & 31) == 0) atomicAdd(o.count, (unsigned long long)__popc(m));
+    }
+}
+
+// Row pointer of window row t for item i, or nullptr for an all-zero row
+// (rows before the stream's first frame: Listener.mfccs starts as zeros, network_runner.py:104).
+__device__ __forceinline__ const float* ring_row(const K2In& in, int sid, long long released, int t) {
+    long long k = released - in.T + t;
+    if (k < 0) return nullptr;
+    return in.ring + ((long long)sid * in.ring_rows + (int)(k % in.ring_rows)) * in.row_stride;
+}
+
+// ------------------------------------------------------------------------------------------------
+template <int H, int F>
+struct GruSmallW {
+    float W[F][3 * H];
+    float U[H][3 * H];
+    float b[3 * H];
+    float wd[H];
+    float bd;
+};
+
+constexpr int K2_SMALL_THREADS = 128;
+
+template <int H, int F, bool RING>
+__global__ void __launch_bounds__(K2_SMALL_THREADS)
+gru_small_kernel(const __grid_constant__ GruSmallW<H, F> P, K2In in, long long n, DecodeParams dp, K2Out out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = i < n;
+    int sid = 0;
+    long long released = 0;
+    float h[H];
+#pragma unroll
+    for (int j = 0; j < H; ++j) h[j] = 0.f;
+    if (valid) {
+        if (RING) {
+            sid = in.ids ? in.ids[i] : (int)i;
+            long long ns = in.n_samples[sid];
+            released = ns >= in.window ? (ns - in.window) / in.hop + 1 : 0;
+        }
+#pragma unroll 1
+        for (int t = 0; t < in.T; ++t) {
+            float x[F];
+            if (RING) {
+                const float* row = ring_row(in, sid, released, t);
+                if (row == nullptr) {
+#pragma unroll
+                    for (int f = 0; f < F; ++f) x[f] = 0.f;
+                } else {
+                    const float4* r4 = reinterpret_cast<const float4*>(row);   // rows are 16-byte aligned, padded to 4k floats
+#pragma unroll
+                    for (int q = 0; q < (F + 3) / 4; ++q) {
+                        float4 v = __ldg(r4 + q);
+                        if (4 * q + 0 < F) x[4 * q + 0] = v.x;
+                        if (4 * q + 1 < F) x[4 * q + 1] = v.y;
+                        if (4 * q + 2 < F) x[4 * q + 2] = v.z;
+                        if (4 * q + 3 < F) x[4 * q + 3] = v.w;
+                    }
+                }
+            } else {
+                const float* row = in.inputs + (i * in.T + t) * F;
+#pragma unroll
+                for (int f = 0; f < F; ++f) x[f] = __ldg(row + f);
+            }
+            float z[H], rh[H];
+#pragma unroll
+            for (int j = 0; j < H; ++j) {
+                float a = P.b[j];
+#pragma unroll
+                for (int f = 0; f < F; ++f) a = fmaf(x[f], P.W[f][j], a);
+#pragma unroll
+                for (int k = 0; k < H; ++k) a = fmaf(h[k], P.U[k][j], a);
+                z[j] = hard_sigmoid(a);
+            }
+#pragma unroll
+            for (int j = 0; j < H; ++j) {
+                float a = P.b[H + j];
+#pragma unroll
+                for (int f = 0; f < F; ++f) a = fmaf(x[f], P.W[f][H + j], a);
+#pragma unroll
+                for (int k = 0; k < H; ++k) a = fmaf(h[k], P.U[k][H + j], a);
+                rh[j] = hard_sigmoid(a) * h[j];
+            }
+#pragma unroll
+            for (int j = 0; j < H; ++j) {
+                float a = P.b[2 * H + j];
+#pragma unroll
+                for (int f = 0; f < F; ++f) a = fmaf(x[f], P.W[f][2 * H + j], a);
+#pragma unroll
+                for (int k = 0; k < H; ++k) a = fmaf(rh[k], P.U[k][2 * H + j], a);
+                z[j] = z[j] * h[j] + (1.f - z[j]) * a;         // linear candidate activation
+            }
+#pragma unroll
+            for (int j = 0; j < H; ++j) h[j] = z[j];
+        }
+    }
+    float logit = P.bd;
+#pragma unroll
+    for (int j = 0; j < H; ++j) logit = fmaf(h[j], P.wd[j], logit);
+    epilogue(logit, valid, i, sid, dp, out);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Generic tiled kernel.  wcat = [kernel; recurrent] as one [(F_in + H)][3H] row-major matrix.
+constexpr int K2_TILE_THREADS = 256;
+constexpr int K2_TILE_STREAMS = 64;     // 8 warps x 8 streams
+constexpr int K2_COLS_PER_THREAD = 8;   // columns tx + 32 c
+
+struct GruTiledW {
+    const float* wcat;   // [(F_in + H)][3H]
+    const float* bias;   // [3H]
+    const float* wd;     // [H]
+    float bd;
+    int H, F_in;
+    int act, ract;
+};
+
+__device__ __forceinline__ float apply_ract(float x, int kind) { return kind == 0 ? hard_sigmoid(x) : sigmoid32(x); }
+__device__ __forceinline__ float apply_act(float x, int kind) { return kind == 0 ? x : tanhf(x); }
+
+// acc[s][c] += sum_k A[k][8*warp + s] * Wcat[row0 + k][col(c)] for k in [0, K)
+__device__ __forceinline__ void tile_mac(float (&acc)[8][K2_COLS_PER_THREAD], const float* __restrict__ A,
+                                         const float* __restrict__ wrow, int ldw, int K, int col0, int ncols_total, int warp, int lane) {
+    for (int k = 0; k < K; ++k) {
+        const float4 a0 = *reinterpret_cast<const float4*>(A + k * K2_TILE_STREAMS + 8 * warp);
+        const float4 a1 = *reinterpret_cast<const float4*>(A + k * K2_TILE_STREAMS + 8 * warp + 4);
+        const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        const float* w = wrow + (long long)k * ldw;
+#pragma unroll
+        for (int c = 0; c < K2_COLS_PER_THREAD; ++c) {
+            int j = col0 + lane + 32 * c;
+            float wv = j < ncols_total ? __ldg(w + j) : 0.f;
+#pragma unroll
+            for (int s = 0; s < 8; ++s) acc[s][c] = fmaf(av[s], wv, acc[s][c]);
+        }
+    }
+}
+
+template <bool RING>
+__global__ void __launch_bounds__(K2_TILE_THREADS)
+gru_tiled_kernel(GruTiledW W, K2In in, long long n, DecodeParams dp, K2Out out) {
+    extern __shared__ __align__(16) float sm[];
+    const int H = W.H, F = W.F_in, H3 = 3 * W.H;
+    float* X = sm;                               // [F][64]
+    float* Hs = X + F * K2_TILE_STREAMS;         // [H][64]   (rows F.. of the [x,h] activation matrix)
+    float* RH = Hs + H * K2_TILE_STREAMS;        // [H][64]
+    float* Z = RH + H * K2_TILE_STREAMS;         // [H][64]
+    __shared__ int s_sid[K2_TILE_STREAMS];
+    __shared__ long long s_rel[K2_TILE_STREAMS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long base = (long long)blockIdx.x * K2_TILE_STREAMS;
+    if (threadIdx.x < K2_TILE_STREAMS) {
+        long long i = base + threadIdx.x;
+        int sid = 0; long long rel = 0;
+        if (RING && i < n) {
+            sid = in.ids ? in.ids[i] : (int)i;
+            long long ns = in.n_samples[sid];
+            rel = ns >= in.window ? (ns - in.window) / in.hop + 1 : 0;
+        }
+        s_sid[threadIdx.x] = sid; s_rel[threadIdx.x] = rel;
+    }
+    for (int e = threadIdx.x; e < H * K2_TILE_STREAMS; e += blockDim.x) Hs[e] = 0.f;
+    __syncthreads();
+    const int Fb = in.F_base;
+    for (int t = 0; t < in.T; ++t) {
+        // ---- stage x_t (and deltas) for the 64 streams: X[f][b]
+        for (int e = threadIdx.x; e < F * K2_TILE_STREAMS; e += blockDim.x) {
+            int f = e / K2_TILE_STREAMS, b = e - f * K2_TILE_STREAMS;   // conflict-free smem store; row reuse hits L1
+            long long i = base + b;
+            float v = 0.f;
+            if (i < n) {
+                if (RING) {
+                    int fb = f < Fb ? f : f - Fb;
+                    const float* row = ring_row(in, s_sid[b], s_rel[b], t);
+                    float cur = row ? row[fb] : 0.f;
+                    if (f < Fb) v = cur;
+                    else if (t > 0) {                      // add_deltas: delta[0] = 0
+                        const float* prow = ring_row(in, s_sid[b], s_rel[b], t - 1);
+                        v = cur - (prow ? prow[fb] : 0.f);
+                    }
+                } else {
+                    v = __ldg(in.inputs + (i * in.T + t) * F + f);
+                }
+            }
+            X[f * K2_TILE_STREAMS + b] = v;
+        }
+        __syncthreads();
+        // ---- phase 1: z, r  (columns [0, 2H))
+        for (int col0 = 0; col0 < 2 * H; col0 += 32 * K2_COLS_PER_THREAD) {
+            float acc[8][K2_COLS_PER_THREAD];
+#pragma unroll
+            for (int c = 0; c < K2_COLS_PER_THREAD; ++c) {
+                int j = col0 + lane + 32 * c;
+                float bj = j < 2 * H ? __ldg(W.bias + j) : 0.f;
+#pragma unroll
+                for (int s = 0; s < 8; ++s) acc[s][c] = bj;
+            }
+            tile_mac(acc, X, W.wcat, H3, F, col0, 2 * H, warp, lane);
+            tile_mac(acc, Hs, W.wcat + (long long)F * H3, H3, H, col0, 2 * H, warp, lane);
+#pragma unroll
+            for (int c = 0; c < K2_COLS_PER_THREAD; ++c) {
+                int j = col0 + lane + 32 * c;
+                if (j < 2 * H) {
+#pragma unroll
+                    for (int s = 0; s < 8; ++s) {
+                        float g = apply_ract(acc[s][c], W.ract);
+                        int b = 8 * warp + s;
+                        if (j < H) Z[j * K2_TILE_STREAMS + b] = g;
+                        else RH[(j - H) * K2_TILE_STREAMS + b] = g * Hs[(j - H) * K2_TILE_STREAMS + b];
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        // ---- phase 2: candidate + state update (columns [2H, 3H))
+        for (int col0 = 0; col0 < H; col0 += 32 * K2_COLS_PER_THREAD) {
+            float acc[8][K2_COLS_PER_THREAD];
+#pragma unroll
+            for (int c = 0; c < K2_COLS_PER_THREAD; ++c) {
+                int j = col0 + lane + 32 * c;
+                float bj = j < H ? __ldg(W.bias + 2 * H + j) : 0.f;
+#pragma unroll
+                for (int s = 0; s < 8; ++s) acc[s][c] = bj;
+            }
+            tile_mac(acc, X, W.wcat + 2 * H, H3, F, col0, H, warp, lane);
+            tile_mac(acc, RH, W.wcat + (long long)F * H3 + 2 * H, H3, H, col0, H, warp, lane);
+#pragma unroll
+            for (int c = 0; c < K2_COLS_PER_THREAD; ++c) {
+                int j = col0 + lane + 32 * c;
+                if (j < H) {
+#pragma unroll
+                    for (int s = 0; s < 8; ++s) {
+                        int b = 8 * warp + s;
+                        float z = Z[j * K2_TILE_STREAMS + b], hp = Hs[j * K2_TILE_STREAMS + b];
+                        Hs[j * K2_TILE_STREAMS + b] = z * hp + (1.f - z) * apply_act(acc[s][c], W.act);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+    // ---- Dense(1) + epilogue: warps 0,1 own the 64 streams
+    if (warp < 2) {
+        int b = threadIdx.x;
+        long long i = base + b;
+        float logit = W.bd;
+        for (int j = 0; j < H; ++j) logit = fmaf(Hs[j * K2_TILE_STREAMS + b], __ldg(W.wd + j), logit);
+        epilogue(logit, i < n, i, s_sid[b], dp, out);
+    }
+}
+
+// K3 alone (pb_decode)
+__global__ void decode_kernel(const float* __restrict__ raw, long long n, DecodeParams dp, double* __restrict__ conf) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) conf[i] = decode_one(raw[i], dp);
+}
+
+}  // namespace pb

@@ -1,0 +1,307 @@
+// mfcc_kernels.cuh -- K1: PCM -> power spectrum -> mel -> log -> DCT (MFCC).
+//
+// Two entry kernels share the device code:
+//   mfcc_batch_kernel   stateless: whole buffers [n_streams][L] -> [n_streams][n_frames][n_out]
+//                       (vectorize_raw, precise/vectorization.py:46-50)
+//   mfcc_stream_kernel  stateful tick: appends one chunk per stream, computes the frames that
+//                       became computable, writes them into the per-stream MFCC ring and keeps
+//                       the unconsumed PCM tail (Listener.update_vectors,
+//                       precise/network_runner.py:125-146)
+//
+// Phase A (FFT, fft512.cuh): a warp transforms two frames at a time (16 lanes per frame) and
+// leaves scaled power spectra in a shared-memory tile [<=32 frames][257].
+// Phase B (mel/log/DCT): one thread per frame walks the 257 bins once.  Bin k lies in exactly one
+// grid segment i = [g_i, g_i+1); it feeds the rising edge of filter i with weight w_rise[k] and
+// the falling edge of filter i-1 with weight w_fall[k] (sonopy.filterbanks), so
+// mel_j = rise(seg j) + fall(seg j+1).  Then log(max(.,eps)), the DCT-II(ortho) rows and the
+// c0 := log(sum power) replacement (sonopy.mfcc_spec).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "fft512.cuh"
+
+namespace pb {
+
+constexpr int K1_THREADS = 128;
+constexpr int K1_WARPS = K1_THREADS / 32;
+constexpr int K1_TILE = 32;              // frames per round
+constexpr int K1_PSTRIDE = 257;          // odd: thread-per-frame reads are bank-conflict free
+constexpr int K1_STREAMS_PER_CTA = 16;   // stream kernel: streams per tile
+constexpr float K1_EPS = 2.220446049250313e-16f;   // np.finfo(float).eps, sonopy.safe_log
+
+struct MelTables {
+    const float* w_rise;      // [n_bins]
+    const float* w_fall;      // [n_bins]
+    const int* grid;          // [n_filt + 2]
+    const float* dct;         // [n_out][n_filt]
+    const float2* tw_stage;   // [16][16]  (cos, -sin)(2 pi n2 k1 / 256)
+    const float2* tw_post;    // [16]      (cos, +sin)(2 pi k1 / 512)
+    int n_bins, n_filt, n_out;
+    int mels_only;            // Vectorizer.mels: emit log-mels, no DCT / c0
+};
+
+// Where the `used` samples of one frame live: sample i is p0[i] for i < len0, else p1[i - len0];
+// samples >= used are zero (window shorter than n_fft).
+template <typename T>
+struct FrameSrc {
+    const T* p0;
+    const T* p1;
+    int len0;
+    int used;
+};
+
+__device__ __forceinline__ float to_f(int16_t v) { return (float)v; }
+__device__ __forceinline__ float to_f(float v) { return v; }
+
+// packed complex element m = samples (2m, 2m+1)
+template <typename T, bool PAIRS>
+__device__ __forceinline__ cpx load_elem(const FrameSrc<T>& s, int m) {
+    cpx r;
+    int i = 2 * m;
+    if (PAIRS) {   // len0, used even and both pointers pair-aligned: a pair never straddles
+        if (i >= s.used) return {0.f, 0.f};
+        const T* p = (i < s.len0) ? s.p0 + i : s.p1 + (i - s.len0);
+        if (sizeof(T) == 2) {
+            int v = __ldg(reinterpret_cast<const int*>(p));
+            r.x = (float)(short)(v & 0xffff);
+            r.y = (float)(short)(v >> 16);
+        } else {
+            float2 v = __ldg(reinterpret_cast<const float2*>(p));
+            r.x = v.x; r.y = v.y;
+        }
+        return r;
+    }
+    r.x = (i < s.used) ? to_f(__ldg((i < s.len0) ? s.p0 + i : s.p1 + (i - s.len0))) : 0.f;
+    ++i;
+    r.y = (i < s.used) ? to_f(__ldg((i < s.len0) ? s.p0 + i : s.p1 + (i - s.len0))) : 0.f;
+    return r;
+}
+
+// Phase B for one frame: P = power row in shared memory (overwritten with log-mels), out = n_out floats.
+__device__ __forceinline__ void mel_log_dct(float* P, const MelTables& t, float* __restrict__ out) {
+    const int nb = t.n_bins;
+    float tot = 0.f;
+    int g0 = __ldg(t.grid);
+    for (int k = 0; k < g0 && k < nb; ++k) tot += P[k];
+    float rise_prev = 0.f;
+    for (int i = 0; i <= t.n_filt; ++i) {
+        int lo = __ldg(t.grid + i), hi = __ldg(t.grid + i + 1);
+        hi = hi < nb ? hi : nb;
+        float r0 = 0.f, f0 = 0.f, r1 = 0.f, f1 = 0.f, s0 = 0.f, s1 = 0.f;
+        int k = lo;
+        for (; k + 1 < hi; k += 2) {
+            float p0 = P[k], p1 = P[k + 1];
+            s0 += p0; s1 += p1;
+            r0 = fmaf(__ldg(t.w_rise + k), p0, r0);     r1 = fmaf(__ldg(t.w_rise + k + 1), p1, r1);
+            f0 = fmaf(__ldg(t.w_fall + k), p0, f0);     f1 = fmaf(__ldg(t.w_fall + k + 1), p1, f1);
+        }
+        if (k < hi) {
+            float p0 = P[k];
+            s0 += p0;
+            r0 = fmaf(__ldg(t.w_rise + k), p0, r0);
+            f0 = fmaf(__ldg(t.w_fall + k), p0, f0);
+        }
+        tot += s0 + s1;
+        if (i > 0) P[i - 1] = logf(fmaxf(rise_prev + (f0 + f1), K1_EPS));   // grid[i+1] >= i+1: slot is already consumed
+        rise_prev = r0 + r1;
+    }
+    for (int k = __ldg(t.grid + t.n_filt + 1); k < nb; ++k) tot += P[k];
+    if (t.mels_only) {
+        for (int j = 0; j < t.n_out; ++j) out[j] = P[j];
+        return;
+    }
+    out[0] = logf(fmaxf(tot, K1_EPS));
+    for (int c = 1; c < t.n_out; ++c) {
+        const float* d = t.dct + c * t.n_filt;
+        float a0 = 0.f, a1 = 0.f;
+        int j = 0;
+        for (; j + 1 < t.n_filt; j += 2) { a0 = fmaf(__ldg(d + j), P[j], a0); a1 = fmaf(__ldg(d + j + 1), P[j + 1], a1); }
+        if (j < t.n_filt) a0 = fmaf(__ldg(d + j), P[j], a0);
+        out[c] = a0 + a1;
+    }
+}
+
+struct K1Smem {
+    float power[K1_TILE * K1_PSTRIDE];
+    float2 xch[K1_WARPS * 2 * XCH_ELEMS];
+};
+
+// ------------------------------------------------------------------------------------------------
+// Stateless batch kernel.  Global frame g = stream * n_frames + f.
+template <typename T, bool PAIRS>
+__global__ void __launch_bounds__(K1_THREADS, 4)
+mfcc_batch_kernel(const T* __restrict__ pcm, long long samples_per_stream, long long n_frames_per_stream,
+                  long long total_frames, int hop, int used, float scale, MelTables tab,
+                  float* __restrict__ out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    K1Smem& sm = *reinterpret_cast<K1Smem*>(smem_raw);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, l16 = lane & 15, half = lane >> 4;
+    FftLaneConst lc;
+    load_lane_const(lc, tab.tw_stage, tab.tw_post, l16);
+    float2* xch = sm.xch + (warp * 2 + half) * XCH_ELEMS;
+    const long long n_tiles = (total_frames + K1_TILE - 1) / K1_TILE;
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const long long g_base = tile * K1_TILE;
+        // ---- phase A: 32 frames, 8 per pass over the 4 warps
+#pragma unroll 1
+        for (int pass = 0; pass < K1_TILE / (K1_WARPS * 2); ++pass) {
+            const int slot = pass * (K1_WARPS * 2) + warp * 2 + half;
+            const long long g = g_base + slot;
+            const bool active = g < total_frames;
+            cpx z[16];
+            if (active) {
+                long long s = g / n_frames_per_stream, f = g - s * n_frames_per_stream;
+                FrameSrc<T> src;
+                src.p0 = pcm + s * samples_per_stream + f * hop;
+                src.p1 = src.p0; src.len0 = used; src.used = used;
+#pragma unroll
+                for (int n1 = 0; n1 < 16; ++n1) z[n1] = load_elem<T, PAIRS>(src, 16 * n1 + l16);
+            } else {
+#pragma unroll
+                for (int n1 = 0; n1 < 16; ++n1) z[n1] = {0.f, 0.f};
+            }
+            fft512_power(z, lc, xch, sm.power + slot * K1_PSTRIDE, scale, l16, active);
+        }
+        __syncthreads();
+        // ---- phase B: thread per frame
+        if (threadIdx.x < K1_TILE) {
+            const long long g = g_base + threadIdx.x;
+            if (g < total_frames) mel_log_dct(sm.power + threadIdx.x * K1_PSTRIDE, tab, out + g * tab.n_out);
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Per-stream streaming state (device arrays owned by the handle).
+struct StreamState {
+    long long* n_samples;     // [max_streams] samples consumed so far
+    int16_t* tail;            // [max_streams][tail_cap] unconsumed samples a later frame still needs
+    float* ring;              // [max_streams][ring_rows][row_stride] MFCC rows, slot = frame index % ring_rows
+    int* trig;                // [max_streams] TriggerDetector.activation
+    int tail_cap, ring_rows, row_stride;
+};
+
+__host__ __device__ __forceinline__ long long frames_ready(long long n, int need, int hop) {
+    return n >= need ? (n - need) / hop + 1 : 0;
+}
+
+struct K1StreamSmem {
+    K1Smem k1;
+    // frame work list for this tile
+    int fr_stream[K1_STREAMS_PER_CTA * 8];    // local stream slot
+    long long fr_index[K1_STREAMS_PER_CTA * 8]; // absolute frame index k
+    int n_frames_tile;
+    int st_id[K1_STREAMS_PER_CTA];
+    long long st_n0[K1_STREAMS_PER_CTA];
+    long long st_ts0[K1_STREAMS_PER_CTA];
+    int st_cnt[K1_STREAMS_PER_CTA];
+    long long st_c0[K1_STREAMS_PER_CTA];
+};
+
+// One tick: stream ids[i] (or i) receives pcm[i][0..chunk).
+// max_new: upper bound of frames a stream can complete per tick (<= 8, host-checked).
+template <bool PAIRS>
+__global__ void __launch_bounds__(K1_THREADS, 4)
+mfcc_stream_kernel(const int16_t* __restrict__ pcm, const int* __restrict__ ids, int n, int chunk,
+                   int hop, int used, int max_new, float scale, MelTables tab, StreamState st) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    K1StreamSmem& sm = *reinterpret_cast<K1StreamSmem*>(smem_raw);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, l16 = lane & 15, half = lane >> 4;
+    FftLaneConst lc;
+    load_lane_const(lc, tab.tw_stage, tab.tw_post, l16);
+    float2* xch = sm.k1.xch + (warp * 2 + half) * XCH_ELEMS;
+    const int n_tiles = (n + K1_STREAMS_PER_CTA - 1) / K1_STREAMS_PER_CTA;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int base = tile * K1_STREAMS_PER_CTA;
+        // ---- bookkeeping: one thread per stream
+        if (threadIdx.x < K1_STREAMS_PER_CTA) {
+            int i = base + threadIdx.x, cnt = 0, sid = -1;
+            long long n0 = 0, c0 = 0, ts0 = 0;
+            if (i < n) {
+                sid = ids ? ids[i] : i;
+                n0 = st.n_samples[sid];
+                c0 = frames_ready(n0, used, hop);
+                long long c1 = frames_ready(n0 + chunk, used, hop);
+                cnt = (int)(c1 - c0);
+                ts0 = c0 * hop < n0 ? c0 * hop : n0;        // first absolute sample held in the tail
+            }
+            sm.st_id[threadIdx.x] = sid; sm.st_n0[threadIdx.x] = n0; sm.st_ts0[threadIdx.x] = ts0;
+            sm.st_cnt[threadIdx.x] = cnt; sm.st_c0[threadIdx.x] = c0;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int w = 0;
+            for (int t = 0; t < K1_STREAMS_PER_CTA; ++t)
+                for (int j = 0; j < sm.st_cnt[t]; ++j) { sm.fr_stream[w] = t; sm.fr_index[w] = sm.st_c0[t] + j; ++w; }
+            sm.n_frames_tile = w;
+        }
+        __syncthreads();
+        const int nf = sm.n_frames_tile;
+        for (int r0 = 0; r0 < nf; r0 += K1_TILE) {
+            const int nr = min(K1_TILE, nf - r0);
+            // ---- phase A
+#pragma unroll 1
+            for (int pass = 0; pass * (K1_WARPS * 2) < nr; ++pass) {
+                const int slot = pass * (K1_WARPS * 2) + warp * 2 + half;
+                const bool active = slot < nr;
+                cpx z[16];
+                if (active) {
+                    const int t = sm.fr_stream[r0 + slot];
+                    const long long a0 = sm.fr_index[r0 + slot] * hop;     // absolute first sample
+                    const long long n0 = sm.st_n0[t];
+                    const int sid = sm.st_id[t];
+                    const int16_t* chunk_p = pcm + (long long)(base + t) * chunk;
+                    FrameSrc<int16_t> src;
+                    src.used = used;
+                    if (a0 >= n0) { src.len0 = 0; src.p0 = chunk_p; src.p1 = chunk_p + (a0 - n0); }
+                    else {
+                        src.len0 = (int)min((long long)used, n0 - a0);
+                        src.p0 = st.tail + (long long)sid * st.tail_cap + (a0 - sm.st_ts0[t]);
+                        src.p1 = chunk_p;
+                    }
+#pragma unroll
+                    for (int n1 = 0; n1 < 16; ++n1) z[n1] = load_elem<int16_t, PAIRS>(src, 16 * n1 + l16);
+                } else {
+#pragma unroll
+                    for (int n1 = 0; n1 < 16; ++n1) z[n1] = {0.f, 0.f};
+                }
+                fft512_power(z, lc, xch, sm.k1.power + slot * K1_PSTRIDE, scale, l16, active);
+            }
+            __syncthreads();
+            // ---- phase B: rows go straight into the ring
+            if (threadIdx.x < nr) {
+                const int t = sm.fr_stream[r0 + threadIdx.x];
+                const long long k = sm.fr_index[r0 + threadIdx.x];
+                float* row = st.ring + ((long long)sm.st_id[t] * st.ring_rows + (int)(k % st.ring_rows)) * st.row_stride;
+                mel_log_dct(sm.k1.power + threadIdx.x * K1_PSTRIDE, tab, row);
+            }
+            __syncthreads();
+        }
+        // ---- tail + counter update: one warp per stream, reads complete before writes
+        for (int t = warp; t < K1_STREAMS_PER_CTA; t += K1_WARPS) {
+            const int sid = sm.st_id[t];
+            if (sid < 0) continue;
+            const long long n0 = sm.st_n0[t], n1 = n0 + chunk, ts0 = sm.st_ts0[t];
+            const long long c1 = frames_ready(n1, used, hop);
+            const long long ts1 = c1 * hop < n1 ? c1 * hop : n1;
+            const int len1 = (int)(n1 - ts1);
+            const int n_old = ts1 < n0 ? (int)(n0 - ts1) : 0;       // part that comes from the old tail
+            int16_t* tl = st.tail + (long long)sid * st.tail_cap;
+            const int16_t* chunk_p = pcm + (long long)(base + t) * chunk;
+            int16_t keep[64];                                        // tail_cap <= 2048 = 64 * 32
+            const int off = (int)(ts1 - ts0);
+#pragma unroll 1
+            for (int j = 0; j * 32 < n_old; ++j) { int i = j * 32 + lane; keep[j & 63] = i < n_old ? tl[off + i] : (int16_t)0; }
+            __syncwarp();
+#pragma unroll 1
+            for (int j = 0; j * 32 < n_old; ++j) { int i = j * 32 + lane; if (i < n_old) tl[i] = keep[j & 63]; }
+            const long long coff = (ts1 > n0 ? ts1 - n0 : 0);
+            for (int i = n_old + lane; i < len1; i += 32) tl[i] = chunk_p[coff + (i - n_old)];
+            if (lane == 0) st.n_samples[sid] = n1;
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace pb

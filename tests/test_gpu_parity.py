@@ -1,0 +1,413 @@
+"""-m gpu: CUDA path (through the C ABI) vs the oracle on the same seeded inputs.
+
+Tolerances
+  * MFCC rows: abs 2e-4 on realistic-amplitude audio (the kernel computes in fp32, the reference in
+    float64); exact -36.0437 / ln 512 rows on the reference's own all-zero / constant test signals.
+  * GRU output on identical inputs: abs 1e-5 (BASELINE.json north_star), vs the fp32 AND fp64 oracle.
+  * decode: bit-identical conf for the same raw, except that the LUT index may move by one bin
+    when CUDA's log() and libm's differ in the last ulp (rate reported, must be < 0.2 %).
+  * trigger / count: exact.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip('torch')
+
+from oracle import gru as og                      # noqa: E402
+from oracle import mfcc as om                     # noqa: E402
+from oracle.decoder import OracleDecoder          # noqa: E402
+from oracle.listener import run_streams, OracleListener   # noqa: E402
+from oracle.params import OracleParams            # noqa: E402
+from oracle.trigger import OracleTrigger          # noqa: E402
+
+
+def _mod():
+    import mycroft_precise_b200 as m
+    return m
+
+
+def cuda(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def noise(S, L, seed=0, sigma=3000):
+    rs = np.random.RandomState(seed)
+    return np.clip(rs.randn(S, L) * sigma, -32768, 32767).astype(np.int16)
+
+
+def oracle_pr(pr):
+    return OracleParams(**pr.to_dict())
+
+
+def oracle_mfcc(pcm_i16, pr):
+    return np.stack([om.vectorize_raw(r.astype(np.float32) / 32768.0, oracle_pr(pr)) for r in pcm_i16])
+
+
+@pytest.fixture(scope='module')
+def core():
+    m = _mod()
+    c = m.PreciseB200(max_streams=64)
+    yield c
+    c.close()
+
+
+# ------------------------------------------------------------------------------------------ tables
+def test_filterbank_bit_equal(core):
+    assert np.array_equal(core.filterbank(), om.filterbank(16000, 20, 257))
+
+
+def test_cdf_tables(core):
+    d = OracleDecoder(((6, 4),), 0.2)
+    cd, lo, hi = core.cdf()
+    assert (lo, hi) == (d.min_out, d.max_out) and len(cd) == 6400
+    assert np.array_equal(cd, d.cd)                # numpy-built table uploaded by the host
+    m = _mod()
+    import ctypes as C
+    from mycroft_precise_b200.core import make_config, get_lib, check
+    cfg = make_config(m.ListenerParams())
+    h = C.c_void_p()
+    check(get_lib().pb_create(C.byref(cfg), C.byref(h)))
+    raw = np.zeros(6400)
+    get_lib().pb_get_cdf(h, raw.ctypes.data_as(C.c_void_p), 6400, None, None)
+    get_lib().pb_destroy(h)
+    assert np.max(np.abs(raw - d.cd)) < 1e-14      # libm-built table inside the library
+
+
+# ------------------------------------------------------------------------------------------ K1
+def test_mfcc_batch_noise(core):
+    pcm = noise(37, 24000, seed=1)
+    got = core.mfcc(cuda(pcm)).cpu().numpy()
+    want = oracle_mfcc(pcm, core.params)
+    assert got.shape == want.shape == (37, 29, 13)
+    err = np.max(np.abs(got - want))
+    print('mfcc max abs err', err)
+    assert err < 2e-4
+
+
+def test_mfcc_lengths_and_ragged_tail(core):
+    for L in (1600, 1601, 2399, 2400, 3333, 9999):
+        pcm = noise(3, L, seed=L)
+        got = core.mfcc(cuda(pcm)).cpu().numpy()
+        want = oracle_mfcc(pcm, core.params)
+        assert got.shape == want.shape
+        assert np.max(np.abs(got - want)) < 2e-4
+    assert core.mfcc(cuda(noise(2, 1599))).shape == (2, 0, 13)
+    with pytest.raises(ValueError):
+        core.mfcc(torch.zeros((1, 0), dtype=torch.int16, device='cuda'))
+
+
+def test_mfcc_reference_test_signals(core):
+    z = core.mfcc(torch.zeros((1, 1600), dtype=torch.int16, device='cuda')).cpu().numpy()[0, 0]
+    assert abs(z[0] - (-36.04365338911715)) < 1e-5 and np.all(np.abs(z[1:]) < 1e-5)
+    ones = torch.ones((1, 1600), dtype=torch.float32, device='cuda')          # the reference's 1.0 signal
+    o = core.mfcc(ones).cpu().numpy()[0, 0]
+    assert abs(o[0] - np.log(512.0)) < 1e-5 and np.all(np.abs(o[1:]) < 1e-5)
+    dc = torch.full((1, 1600), 32767, dtype=torch.int16, device='cuda')
+    d = core.mfcc(dc).cpu().numpy()[0, 0]
+    want = om.mfcc_spec(np.full(1600, 32767 / 32768.0), 16000, 1600, 800, 512, 20, 13)[0]
+    assert np.max(np.abs(d - want)) < 1e-5
+
+
+def test_mfcc_tone_and_quiet(core):
+    t = np.arange(24000)
+    tone = (12000 * np.sin(2 * np.pi * 440.0 * t / 16000)).astype(np.int16)[None]
+    quiet = noise(1, 24000, seed=5, sigma=20)
+    for pcm, tol in ((tone, 5e-3), (quiet, 2e-4)):
+        got = core.mfcc(cuda(pcm)).cpu().numpy()
+        want = oracle_mfcc(pcm, core.params)
+        err = np.max(np.abs(got - want))
+        print('err', err)
+        assert err < tol
+
+
+def test_mfcc_f32_input(core):
+    rs = np.random.RandomState(2)
+    a = (rs.randn(5, 8000) * 0.1).astype(np.float32)
+    got = core.mfcc(cuda(a)).cpu().numpy()
+    want = np.stack([om.vectorize_raw(r, oracle_pr(core.params)) for r in a])
+    assert np.max(np.abs(got - want)) < 2e-4
+    odd = a[:, 1:7000]                                   # misaligned rows: scalar load path
+    got = core.mfcc(cuda(odd)).cpu().numpy()
+    want = np.stack([om.vectorize_raw(r, oracle_pr(core.params)) for r in odd])
+    assert np.max(np.abs(got - want)) < 2e-4
+
+
+def test_mfcc_linearity_property_large(core):
+    """Full-size property check: scaling the PCM by 2 adds ln 4 to c0 and leaves c1.. unchanged."""
+    pcm = noise(4096, 8000, seed=7, sigma=2000)
+    a = core.mfcc(cuda(pcm))
+    b = core.mfcc(cuda((pcm.astype(np.int32) * 2).astype(np.int16)))
+    d = (b - a).cpu().numpy()
+    assert np.max(np.abs(d[..., 0] - np.log(4.0))) < 1e-4
+    assert np.max(np.abs(d[..., 1:])) < 1e-4
+
+
+# ------------------------------------------------------------------------------------------ K2
+@pytest.mark.parametrize('scale', [0.1, 0.3])
+def test_predict_small_path(core, scale):
+    w = og.GruWeights.random(13, 20, seed=3, scale=scale)
+    core.load_weights(w.kernel, w.recurrent, w.bias, w.dense_w, w.dense_b)
+    x = (np.random.RandomState(4).randn(1000, 29, 13) * 3).astype(np.float32)
+    p, lg = core.predict(cuda(x), want_logit=True)
+    p, lg = p.cpu().numpy(), lg.cpu().numpy()
+    p32, l32 = og.gru_forward(w, x, np.float32)
+    p64, l64 = og.gru_forward(w, x, np.float64)
+    print('prob err vs f32 %.3g vs f64 %.3g ; logit rel err %.3g' % (
+        np.max(np.abs(p - p32)), np.max(np.abs(p - p64)), np.max(np.abs(lg - l64) / (1 + np.abs(l64)))))
+    assert np.max(np.abs(p - p32)) < 1e-5 and np.max(np.abs(p - p64)) < 1e-5
+    assert np.max(np.abs(lg - l64) / (1 + np.abs(l64))) < 1e-4
+
+
+def _generic_case(pr_kw, H, act='linear', ract='hard_sigmoid', N=200, seed=5):
+    m = _mod()
+    pr = m.ListenerParams(**pr_kw)
+    c = m.PreciseB200(pr, hidden=H, max_streams=8, activation=act, recurrent_activation=ract)
+    F = c.feature_size
+    w = og.GruWeights.random(F, H, seed=seed, scale=0.3 / np.sqrt(H / 20.0))
+    w.activation, w.recurrent_activation = act, ract
+    c.load_weights(w.kernel, w.recurrent, w.bias, w.dense_w, w.dense_b)
+    x = (np.random.RandomState(seed).randn(N, pr.n_features, F) * 2).astype(np.float32)
+    p = c.predict(cuda(x)).cpu().numpy()
+    p64 = og.gru_forward(w, x, np.float64)[0]
+    c.close()
+    return np.max(np.abs(p - p64))
+
+
+@pytest.mark.parametrize('H,kw,act,ract', [
+    (32, {}, 'linear', 'hard_sigmoid'),
+    (128, dict(n_filt=40, n_mfcc=40), 'linear', 'hard_sigmoid'),     # BASELINE config 3
+    (20, dict(use_delta=True), 'linear', 'hard_sigmoid'),
+    (20, {}, 'tanh', 'sigmoid'),
+    (7, dict(n_mfcc=5), 'tanh', 'hard_sigmoid'),
+])
+def test_predict_tiled_path(H, kw, act, ract):
+    err = _generic_case(kw, H, act, ract)
+    print('tiled GRU err', err)
+    assert err < 1e-5
+
+
+def test_predict_edge_sizes(core):
+    w = og.GruWeights.random(13, 20, seed=3, scale=0.1)
+    core.load_weights(w.kernel, w.recurrent, w.bias, w.dense_w, w.dense_b)
+    assert core.predict(torch.zeros((0, 29, 13), device='cuda')).shape == (0,)
+    for N in (1, 127, 129):
+        x = (np.random.RandomState(N).randn(N, 29, 13)).astype(np.float32)
+        p = core.predict(cuda(x)).cpu().numpy()
+        assert np.max(np.abs(p - og.gru_forward(w, x, np.float64)[0])) < 1e-5
+    with pytest.raises(ValueError):
+        core.predict(torch.zeros((2, 28, 13), device='cuda'))
+
+
+# ------------------------------------------------------------------------------------------ K3
+def test_decode_vs_reference_golden(core, golden_dir):
+    import os
+    g = np.load(os.path.join(golden_dir, 'decoder_golden.npz'))
+    raws = g['raws']
+    got = core.decode(cuda(raws)).cpu().numpy()
+    want = g['dec_0']                                     # produced by the reference class itself
+    d = OracleDecoder(((6, 4),), 0.2)
+    exact = got == want
+    print('decode: %d / %d bit-identical' % (exact.sum(), len(raws)))
+    assert exact.mean() > 0.998
+    for r, a in zip(raws[~exact], got[~exact]):           # the rest: neighbouring LUT bin
+        i = d.index(float(r))
+        cands = []
+        for j in (i - 1, i + 1):
+            if 0 <= j < len(d.cd):
+                cp = d.cd[j]
+                cands.append(0.5 * cp / d.center if cp < d.center else 0.5 + 0.5 * (cp - d.center) / (1 - d.center))
+        assert any(a == c for c in cands)
+
+
+# ------------------------------------------------------------------------------------------ stateful
+def _run_gpu_streams(m, model, pcm, chunk, pr=None, sens=0.5, lvl=3, host=False):
+    S = pcm.shape[0]
+    K = pcm.shape[1] // chunk
+    sb = m.StreamBatch(model, S, params=pr, chunk_samples=chunk, sensitivity=sens, trigger_level=lvl)
+    raw = np.zeros((S, K), np.float32)
+    conf = np.zeros((S, K))
+    fired = np.zeros((S, K), bool)
+    wins = []
+    counts = 0
+    for k in range(K):
+        c = np.ascontiguousarray(pcm[:, k * chunk:(k + 1) * chunk])
+        if host:
+            r = np.zeros(S, np.float32); cf = np.zeros(S); f = np.zeros(S, np.uint8)
+            counts += sb.update_host(c, cf, r, f)
+            raw[:, k], conf[:, k], fired[:, k] = r, cf, f.astype(bool)
+        else:
+            out = sb.update(cuda(c))
+            raw[:, k] = out['raw'].cpu().numpy()
+            conf[:, k] = out['conf'].cpu().numpy()
+            fired[:, k] = out['fired'].cpu().numpy().astype(bool)
+        wins.append(sb.core.read_window(S).cpu().numpy())
+    if not host:
+        counts = int(sb.count.item())
+    sb.core.close()
+    return raw, conf, fired, np.array(wins), counts
+
+
+def _oracle_windows(pcm, chunk, pr):
+    S, K = pcm.shape[0], pcm.shape[1] // chunk
+    w = og.GruWeights.random(pr.n_mfcc if not hasattr(pr, 'feature_size') else 13, 20)
+    wins = np.zeros((K, S, pr.n_features, pr.n_mfcc))
+    for s in range(S):
+        lis = OracleListener(w, pr)
+        for k in range(K):
+            wins[k, s] = lis.update_vectors(pcm[s, k * chunk:(k + 1) * chunk].astype(np.float32) / 32768.0)
+    return wins
+
+
+@pytest.mark.parametrize('chunk', [1024, 512, 800, 2000, 334, 333])
+def test_stream_state_machine(chunk):
+    """Window contents, raw, conf, fired after every tick vs S independent oracle Listeners."""
+    m = _mod()
+    S, K = 7, max(12, 30000 // chunk)
+    pcm = noise(S, K * chunk, seed=chunk)
+    pcm[5] = 0
+    pcm[6] = 32767
+    model = m.GruModel.random(13, 20, seed=0, scale=0.1)
+    raw, conf, fired, wins, count = _run_gpu_streams(m, model, pcm, chunk, sens=0.8, lvl=1)
+    opr = OracleParams()
+    owins = _oracle_windows(pcm, chunk, opr)
+    werr = np.max(np.abs(wins - owins))
+    print('window err', werr)
+    assert werr < 2e-4
+    w = og.GruWeights(model.kernel, model.recurrent, model.bias, model.dense_w, model.dense_b)
+    # GRU on the GPU's own windows: identical inputs -> 1e-5
+    p64 = og.gru_forward(w, wins.reshape(-1, 29, 13), np.float64)[0].reshape(K, S).T
+    assert np.max(np.abs(raw - p64)) < 1e-5
+    # end to end vs oracle listeners
+    oraw, oconf, ofired = run_streams(w, pcm, chunk, sensitivity=0.8, trigger_level=1)
+    assert np.max(np.abs(raw - oraw)) < 1e-4
+    # decode of the GPU raw: exact up to a neighbouring bin
+    d = OracleDecoder(opr.threshold_config, opr.threshold_center)
+    dconf = np.vectorize(lambda r: d.decode(float(r)))(raw)
+    neq = conf != dconf
+    assert neq.mean() < 0.01
+    step = np.max(np.abs(np.diff(d.cd))) * 2.5
+    assert np.max(np.abs(conf - dconf)) <= step
+    # trigger on the GPU conf: exact
+    for s in range(S):
+        det = OracleTrigger(chunk * 2, 0.8, 1)
+        assert [det.update(c) for c in conf[s]] == list(fired[s])
+    assert count == fired.sum()
+    assert fired.sum() > 0
+
+
+def test_stream_host_path_equals_device_path():
+    m = _mod()
+    S, K, chunk = 50, 14, 1024
+    pcm = noise(S, K * chunk, seed=9)
+    model = m.GruModel.random(13, 20, seed=1, scale=0.1)
+    a = _run_gpu_streams(m, model, pcm, chunk)
+    b = _run_gpu_streams(m, model, pcm, chunk, host=True)
+    for x, y in zip(a[:4], b[:4]):
+        assert np.array_equal(x, y)
+    assert a[4] == b[4]
+
+
+def test_stream_ids_subset_and_clear():
+    m = _mod()
+    S, chunk = 16, 1024
+    model = m.GruModel.random(13, 20, seed=2, scale=0.1)
+    pcm = noise(S, 20 * chunk, seed=11)
+    sb = m.StreamBatch(model, S, chunk_samples=chunk)
+    ids = torch.tensor([3, 9, 4, 15], dtype=torch.int32, device='cuda')
+    ref = m.StreamBatch(model, 4, chunk_samples=chunk)
+    for k in range(10):
+        c = pcm[:, k * chunk:(k + 1) * chunk]
+        a = sb.update(cuda(c[[3, 9, 4, 15]]), ids)
+        b = ref.update(cuda(c[[3, 9, 4, 15]]))
+        assert torch.equal(a['conf'], b['conf']) and torch.equal(a['raw'], b['raw'])
+    # untouched streams are still in their initial state
+    assert float(sb.core.read_window(S)[0].abs().max()) == 0.0
+    # clear two of them: they behave like fresh streams afterwards
+    cl = torch.tensor([9, 15], dtype=torch.int32, device='cuda')
+    sb.clear(cl)
+    fresh = m.StreamBatch(model, 2, chunk_samples=chunk)
+    for k in range(10, 16):
+        c = pcm[:, k * chunk:(k + 1) * chunk]
+        a = sb.update(cuda(c[[9, 15]]), cl)
+        b = fresh.update(cuda(c[[9, 15]]))
+        assert torch.equal(a['conf'], b['conf'])
+    for x in (sb, ref, fresh):
+        x.core.close()
+
+
+def test_stream_config3_and_delta_and_mels():
+    m = _mod()
+    chunk, S, K = 1024, 5, 40
+    pcm = noise(S, K * chunk, seed=13)
+    for kw, H in ((dict(n_filt=40, n_mfcc=40), 128), (dict(use_delta=True), 20)):
+        pr = m.ListenerParams(**kw)
+        F = pr.feature_size
+        model = m.GruModel.random(F, H, seed=3, scale=0.1 / np.sqrt(H / 20.0))
+        raw, conf, fired, wins, count = _run_gpu_streams(m, model, pcm, chunk, pr=pr)
+        w = og.GruWeights(model.kernel, model.recurrent, model.bias, model.dense_w, model.dense_b)
+        oraw, oconf, ofired = run_streams(w, pcm, chunk, pr=OracleParams(**pr.to_dict()))
+        print(kw, 'raw err', np.max(np.abs(raw - oraw)))
+        assert np.max(np.abs(raw - oraw)) < 1e-4
+
+
+def test_mels_vectorizer():
+    m = _mod()
+    pr = m.ListenerParams(vectorizer=m.Vectorizer.mels)
+    c = m.PreciseB200(pr)
+    pcm = noise(3, 8000, seed=17)
+    got = c.mfcc(cuda(pcm)).cpu().numpy()
+    want = np.stack([om.mel_spec(r.astype(np.float32) / 32768.0, 16000, 1600, 800, 512, 20) for r in pcm])
+    assert got.shape == want.shape and np.max(np.abs(got - want)) < 2e-4
+    c.close()
+
+
+def test_unsupported_and_errors():
+    m = _mod()
+    with pytest.raises(NotImplementedError):
+        m.PreciseB200(m.ListenerParams(vectorizer=m.Vectorizer.speechpy_mfccs))
+    c = m.PreciseB200(max_streams=4)
+    with pytest.raises(m.PBError):
+        c.predict(torch.zeros((1, 29, 13), device='cuda'))           # weights not loaded
+    with pytest.raises(ValueError):
+        c.update(torch.zeros((5, 1024), dtype=torch.int16, device='cuda'))   # n > max_streams
+    c.close()
+
+
+# ------------------------------------------------------------------------------------------ mirrors
+def test_listener_and_engine_mirrors_vs_reference_listener(golden_dir):
+    """B200Listener / B200Engine on the PCM of the golden fixture that the reference's real Listener produced."""
+    import os
+    m = _mod()
+    g = np.load(os.path.join(golden_dir, 'listener_golden.npz'))
+    model = m.GruModel(g['kernel'], g['recurrent'], g['bias'], g['dense_w'], g['dense_b'])
+    d = OracleDecoder(((6, 4),), 0.2)
+    step = np.max(np.abs(np.diff(d.cd))) * 2.5
+    for i, chunk in ((0, 1024), (3, 3000), (4, 333)):
+        pcm = g['pcm_%d' % i]
+        want = g['conf_%d' % i]
+        lis = m.B200Listener(model, chunk * 2)
+        got = np.array([lis.update(pcm[k * chunk:(k + 1) * chunk].tobytes()) for k in range(len(want))])
+        # golden weights (scale 0.3) saturate quickly; compare where the oracle is not pinned at 0/1
+        assert np.max(np.abs(got - want)) < 5e-3, (i, np.max(np.abs(got - want)))
+        with pytest.raises(EOFError):
+            lis.update(b'')
+    pcm, want = g['pcm_0'], g['conf_0']
+    eng = m.B200Engine(model, 2048)
+    eng.start()
+    got = np.array([eng.get_prediction(pcm[k * 1024:(k + 1) * 1024].tobytes()) for k in range(len(want))])
+    with pytest.raises(ValueError):
+        eng.get_prediction(b'\0' * 100)
+    eng.stop()
+    assert np.max(np.abs(got - want)) < 5e-3
+
+
+def test_runner_plugin_predict_shape():
+    m = _mod()
+    model = m.GruModel.random(13, 20, seed=4, scale=0.1)
+    r = m.B200Runner(model)
+    x = np.random.RandomState(0).randn(9, 29, 13)
+    p = r.predict(x)
+    assert p.shape == (9, 1) and p.dtype == np.float32
+    assert abs(r.run(x[2]) - p[2, 0]) < 1e-7
