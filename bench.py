@@ -65,7 +65,11 @@ def synth_pcm(n_streams, n_samples, seed, stream_offset=0):
 # ------------------------------------------------------------------------------------ CPU arm
 def _cpu_worker(args):
     seed, n_streams, ticks, warm = args
-    os.environ['OMP_NUM_THREADS'] = '1'
+    try:                                        # one BLAS/OpenMP thread per worker: one core each
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(1)
+    except Exception:
+        pass
     from oracle.gru import GruWeights
     from oracle.listener import OracleListener
     from oracle.trigger import OracleTrigger
@@ -94,7 +98,7 @@ def cpu_port_rate(ticks=3000, warm=50, streams_per_proc=1, procs=None):
         res = pool.map(_cpu_worker, [(1000 + i, streams_per_proc, ticks, warm) for i in range(procs)])
     updates = sum(r[0] for r in res)
     wall = max(r[1] for r in res)
-    return updates / wall, procs, '%d worker processes x %d stream x %d ticks of 1024 samples (after %d warm-up ticks), numpy oracle port, OMP_NUM_THREADS=1' % (
+    return updates / wall, procs, '%d worker processes x %d stream x %d ticks of 1024 samples (after %d warm-up ticks), numpy oracle port, 1 BLAS thread per worker' % (
         procs, streams_per_proc, ticks, warm)
 
 

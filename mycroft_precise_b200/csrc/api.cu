@@ -54,6 +54,7 @@ struct pb_handle {
     int sm_count = 148;
     // derived
     int used = 0, n_bins = 0, n_out = 0, feat = 0, ring_rows = 0, row_stride = 0, tail_cap = 0, max_new = 0;
+    size_t k1_batch_smem = 0, k1_stream_smem = 0;
     // host copies of tables
     std::vector<double> fb;        // [n_filt][n_bins]
     std::vector<double> cd;
@@ -248,9 +249,11 @@ PB_API int pb_create(const pb_config* cfg, pb_handle** out) {
     h->feat = h->n_out * (c.use_delta ? 2 : 1);
     h->row_stride = (h->n_out + 3) & ~3;
     h->ring_rows = c.n_features + (c.window_samples - h->used) / c.hop_samples + 2;
-    h->tail_cap = (h->used + 1) & ~1;
+    h->tail_cap = (h->used + 7) & ~7;            // rows stay 16-byte aligned
     h->max_new = c.chunk_samples / c.hop_samples + 2;
 
+    h->k1_batch_smem = sizeof(K1Smem) + (size_t)h->n_out * c.n_filt * sizeof(float);
+    h->k1_stream_smem = sizeof(K1StreamSmem) + (size_t)h->n_out * c.n_filt * sizeof(float);
     std::vector<float> wrise, wfall;
     std::vector<int> grid;
     int rc = build_mel(h, wrise, wfall, grid);
@@ -302,12 +305,12 @@ PB_API int pb_create(const pb_config* cfg, pb_handle** out) {
     CKH(cudaMemset(h->st.trig, 0, S * sizeof(int)));
     CKH(cudaMalloc((void**)&h->d_count, sizeof(unsigned long long)));
     CKH(cudaMemset(h->d_count, 0, sizeof(unsigned long long)));
-    CKH(cudaFuncSetAttribute(mfcc_batch_kernel<int16_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1Smem)));
-    CKH(cudaFuncSetAttribute(mfcc_batch_kernel<int16_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1Smem)));
-    CKH(cudaFuncSetAttribute(mfcc_batch_kernel<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1Smem)));
-    CKH(cudaFuncSetAttribute(mfcc_batch_kernel<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1Smem)));
-    CKH(cudaFuncSetAttribute(mfcc_stream_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1StreamSmem)));
-    CKH(cudaFuncSetAttribute(mfcc_stream_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1StreamSmem)));
+    CKH(cudaFuncSetAttribute(mfcc_batch_kernel<int16_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->k1_batch_smem));
+    CKH(cudaFuncSetAttribute(mfcc_batch_kernel<int16_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->k1_batch_smem));
+    CKH(cudaFuncSetAttribute(mfcc_batch_kernel<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->k1_batch_smem));
+    CKH(cudaFuncSetAttribute(mfcc_batch_kernel<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->k1_batch_smem));
+    CKH(cudaFuncSetAttribute(mfcc_stream_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->k1_stream_smem));
+    CKH(cudaFuncSetAttribute(mfcc_stream_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->k1_stream_smem));
 #undef CKH
     *out = h;
     return PB_OK;
@@ -462,9 +465,9 @@ static int mfcc_impl(pb_handle* h, const T* d_in, int64_t n_streams, int64_t L, 
     const int grid = (int)std::min<int64_t>(tiles, (int64_t)h->sm_count * 4);
     ProfScope ps(h, 0, s);
     if (pairs)
-        mfcc_batch_kernel<T, true><<<grid, K1_THREADS, sizeof(K1Smem), s>>>(d_in, L, nf, total, h->cfg.hop_samples, h->used, scale, mel_tables(h), d_out);
+        mfcc_batch_kernel<T, true><<<grid, K1_THREADS, h->k1_batch_smem, s>>>(d_in, L, nf, total, h->cfg.hop_samples, h->used, scale, mel_tables(h), d_out);
     else
-        mfcc_batch_kernel<T, false><<<grid, K1_THREADS, sizeof(K1Smem), s>>>(d_in, L, nf, total, h->cfg.hop_samples, h->used, scale, mel_tables(h), d_out);
+        mfcc_batch_kernel<T, false><<<grid, K1_THREADS, h->k1_batch_smem, s>>>(d_in, L, nf, total, h->cfg.hop_samples, h->used, scale, mel_tables(h), d_out);
     CK(cudaGetLastError());
     return PB_OK;
 }
@@ -483,7 +486,8 @@ PB_API int pb_mfcc_f32(pb_handle* h, const float* d_audio, int64_t n_streams, in
 static int launch_gru(pb_handle* h, const K2In& in, bool ring, int64_t n, const DecodeParams& dp, const K2Out& o, cudaStream_t s) {
     ProfScope ps(h, 1, s);
     if (h->small_path) {
-        const int grid = (int)((n + K2_SMALL_THREADS - 1) / K2_SMALL_THREADS);
+        const int per_cta = K2_SMALL_THREADS * K2_NS;
+        const int grid = (int)((n + per_cta - 1) / per_cta);
         if (ring) gru_small_kernel<20, 13, true><<<grid, K2_SMALL_THREADS, 0, s>>>(h->w_small, in, n, dp, o);
         else gru_small_kernel<20, 13, false><<<grid, K2_SMALL_THREADS, 0, s>>>(h->w_small, in, n, dp, o);
     } else {
@@ -542,9 +546,9 @@ static int launch_stream_mfcc(pb_handle* h, const int16_t* d_pcm, const int32_t*
     const float inv = 1.0f / 32768.0f, scale = inv * inv / (float)h->cfg.n_fft;
     ProfScope ps(h, 0, s);
     if (pairs)
-        mfcc_stream_kernel<true><<<grid, K1_THREADS, sizeof(K1StreamSmem), s>>>(d_pcm, d_ids, (int)n, h->cfg.chunk_samples, h->cfg.hop_samples, h->used, h->max_new, scale, mel_tables(h), h->st);
+        mfcc_stream_kernel<true><<<grid, K1_THREADS, h->k1_stream_smem, s>>>(d_pcm, d_ids, (int)n, h->cfg.chunk_samples, h->cfg.hop_samples, h->used, scale, mel_tables(h), h->st);
     else
-        mfcc_stream_kernel<false><<<grid, K1_THREADS, sizeof(K1StreamSmem), s>>>(d_pcm, d_ids, (int)n, h->cfg.chunk_samples, h->cfg.hop_samples, h->used, h->max_new, scale, mel_tables(h), h->st);
+        mfcc_stream_kernel<false><<<grid, K1_THREADS, h->k1_stream_smem, s>>>(d_pcm, d_ids, (int)n, h->cfg.chunk_samples, h->cfg.hop_samples, h->used, scale, mel_tables(h), h->st);
     CK(cudaGetLastError());
     return PB_OK;
 }

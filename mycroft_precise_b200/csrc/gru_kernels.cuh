@@ -126,83 +126,126 @@ struct GruSmallW {
 };
 
 constexpr int K2_SMALL_THREADS = 128;
+constexpr int K2_NS = 2;                       // streams per thread: every weight fetched feeds 2 FMAs
 
-template <int H, int F, bool RING>
-__global__ void __launch_bounds__(K2_SMALL_THREADS)
-gru_small_kernel(const __grid_constant__ GruSmallW<H, F> P, K2In in, long long n, DecodeParams dp, K2Out out) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool valid = i < n;
-    int sid = 0;
-    long long released = 0;
-    float h[H];
+// dot product of column j of [W;U] (shared memory, transposed: Wt[j][0..K)) with [x | hv], for the
+// K2_NS streams of this thread.  Weight loads are warp-uniform 16-byte broadcasts.
+template <int H, int F, int KP>
+__device__ __forceinline__ void gate_dot(const float (*Wt)[KP], int j, float bias, const float (&x)[K2_NS][F],
+                                         const float (&hv)[K2_NS][H], float (&a)[K2_NS]) {
 #pragma unroll
-    for (int j = 0; j < H; ++j) h[j] = 0.f;
-    if (valid) {
-        if (RING) {
-            sid = in.ids ? in.ids[i] : (int)i;
-            long long ns = in.n_samples[sid];
-            released = ns >= in.window ? (ns - in.window) / in.hop + 1 : 0;
-        }
-#pragma unroll 1
-        for (int t = 0; t < in.T; ++t) {
-            float x[F];
-            if (RING) {
-                const float* row = ring_row(in, sid, released, t);
-                if (row == nullptr) {
+    for (int s = 0; s < K2_NS; ++s) a[s] = bias;
 #pragma unroll
-                    for (int f = 0; f < F; ++f) x[f] = 0.f;
-                } else {
-                    const float4* r4 = reinterpret_cast<const float4*>(row);   // rows are 16-byte aligned, padded to 4k floats
+    for (int q = 0; q < KP / 4; ++q) {
+        const float4 w = *reinterpret_cast<const float4*>(&Wt[j][4 * q]);
+        const float wv[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
-                    for (int q = 0; q < (F + 3) / 4; ++q) {
-                        float4 v = __ldg(r4 + q);
-                        if (4 * q + 0 < F) x[4 * q + 0] = v.x;
-                        if (4 * q + 1 < F) x[4 * q + 1] = v.y;
-                        if (4 * q + 2 < F) x[4 * q + 2] = v.z;
-                        if (4 * q + 3 < F) x[4 * q + 3] = v.w;
-                    }
-                }
-            } else {
-                const float* row = in.inputs + (i * in.T + t) * F;
+        for (int e = 0; e < 4; ++e) {
+            const int k = 4 * q + e;
+            if (k < F + H) {
 #pragma unroll
-                for (int f = 0; f < F; ++f) x[f] = __ldg(row + f);
+                for (int s = 0; s < K2_NS; ++s) a[s] = fmaf(k < F ? x[s][k < F ? k : 0] : hv[s][k >= F ? k - F : 0], wv[e], a[s]);
             }
-            float z[H], rh[H];
-#pragma unroll
-            for (int j = 0; j < H; ++j) {
-                float a = P.b[j];
-#pragma unroll
-                for (int f = 0; f < F; ++f) a = fmaf(x[f], P.W[f][j], a);
-#pragma unroll
-                for (int k = 0; k < H; ++k) a = fmaf(h[k], P.U[k][j], a);
-                z[j] = hard_sigmoid(a);
-            }
-#pragma unroll
-            for (int j = 0; j < H; ++j) {
-                float a = P.b[H + j];
-#pragma unroll
-                for (int f = 0; f < F; ++f) a = fmaf(x[f], P.W[f][H + j], a);
-#pragma unroll
-                for (int k = 0; k < H; ++k) a = fmaf(h[k], P.U[k][H + j], a);
-                rh[j] = hard_sigmoid(a) * h[j];
-            }
-#pragma unroll
-            for (int j = 0; j < H; ++j) {
-                float a = P.b[2 * H + j];
-#pragma unroll
-                for (int f = 0; f < F; ++f) a = fmaf(x[f], P.W[f][2 * H + j], a);
-#pragma unroll
-                for (int k = 0; k < H; ++k) a = fmaf(rh[k], P.U[k][2 * H + j], a);
-                z[j] = z[j] * h[j] + (1.f - z[j]) * a;         // linear candidate activation
-            }
-#pragma unroll
-            for (int j = 0; j < H; ++j) h[j] = z[j];
         }
     }
-    float logit = P.bd;
+}
+
+// One thread owns K2_NS adjacent streams; h, z, r*h live in registers.  The weights sit in shared
+// memory transposed -- column j of [W;U] is one contiguous row of KP = roundup4(F + H) floats -- and are
+// fetched with warp-uniform (broadcast) 16-byte loads.  sm_100a has no constant-operand FFMA (ptxas
+// turns __grid_constant__/__constant__ weights into one LDCU per FFMA: measured 2008 LDCU for 2073
+// FFMA per step), so shared-memory broadcast with 2-way register blocking is the cheapest weight path:
+// 9 LDS.128 per 66 FFMA.
+template <int H, int F, bool RING>
+__global__ void __launch_bounds__(K2_SMALL_THREADS, 3)
+gru_small_kernel(const __grid_constant__ GruSmallW<H, F> P, K2In in, long long n, DecodeParams dp, K2Out out) {
+    constexpr int K = F + H, KP = (K + 3) & ~3;
+    __shared__ __align__(16) float Wt[3 * H][KP];
+    __shared__ float bs[3 * H];
+    for (int e = threadIdx.x; e < 3 * H * KP; e += blockDim.x) {
+        const int j = e / KP, k = e - j * KP;
+        Wt[j][k] = k < F ? P.W[k][j] : (k < K ? P.U[k - F][j] : 0.f);
+    }
+    for (int e = threadIdx.x; e < 3 * H; e += blockDim.x) bs[e] = P.b[e];
+    __syncthreads();
+
+    const long long i0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * K2_NS;
+    bool valid[K2_NS];
+    int sid[K2_NS];
+    long long released[K2_NS];
+    float h[K2_NS][H];
 #pragma unroll
-    for (int j = 0; j < H; ++j) logit = fmaf(h[j], P.wd[j], logit);
-    epilogue(logit, valid, i, sid, dp, out);
+    for (int s = 0; s < K2_NS; ++s) {
+        valid[s] = i0 + s < n;
+        sid[s] = 0; released[s] = 0;
+#pragma unroll
+        for (int j = 0; j < H; ++j) h[s][j] = 0.f;
+        if (RING && valid[s]) {
+            sid[s] = in.ids ? in.ids[i0 + s] : (int)(i0 + s);
+            const long long ns = in.n_samples[sid[s]];
+            released[s] = ns >= in.window ? (ns - in.window) / in.hop + 1 : 0;
+        }
+    }
+    if (valid[0]) {
+#pragma unroll 1
+        for (int t = 0; t < in.T; ++t) {
+            float x[K2_NS][F];
+#pragma unroll
+            for (int s = 0; s < K2_NS; ++s) {
+#pragma unroll
+                for (int f = 0; f < F; ++f) x[s][f] = 0.f;
+                if (!valid[s]) continue;
+                if (RING) {
+                    const float* row = ring_row(in, sid[s], released[s], t);
+                    if (row != nullptr) {
+                        const float4* r4 = reinterpret_cast<const float4*>(row);   // rows: 16-byte aligned, padded to 4k floats
+#pragma unroll
+                        for (int q = 0; q < (F + 3) / 4; ++q) {
+                            const float4 u = __ldg(r4 + q);
+                            if (4 * q + 0 < F) x[s][4 * q + 0] = u.x;
+                            if (4 * q + 1 < F) x[s][4 * q + 1] = u.y;
+                            if (4 * q + 2 < F) x[s][4 * q + 2] = u.z;
+                            if (4 * q + 3 < F) x[s][4 * q + 3] = u.w;
+                        }
+                    }
+                } else {
+                    const float* row = in.inputs + ((i0 + s) * in.T + t) * F;
+#pragma unroll
+                    for (int f = 0; f < F; ++f) x[s][f] = __ldg(row + f);
+                }
+            }
+            float z[K2_NS][H], rh[K2_NS][H], a[K2_NS];
+#pragma unroll
+            for (int j = 0; j < H; ++j) {
+                gate_dot<H, F, KP>(Wt, j, bs[j], x, h, a);
+#pragma unroll
+                for (int s = 0; s < K2_NS; ++s) z[s][j] = hard_sigmoid(a[s]);
+            }
+#pragma unroll
+            for (int j = 0; j < H; ++j) {
+                gate_dot<H, F, KP>(Wt, H + j, bs[H + j], x, h, a);
+#pragma unroll
+                for (int s = 0; s < K2_NS; ++s) rh[s][j] = hard_sigmoid(a[s]) * h[s][j];
+            }
+#pragma unroll
+            for (int j = 0; j < H; ++j) {
+                gate_dot<H, F, KP>(Wt, 2 * H + j, bs[2 * H + j], x, rh, a);
+#pragma unroll
+                for (int s = 0; s < K2_NS; ++s) z[s][j] = z[s][j] * h[s][j] + (1.f - z[s][j]) * a[s];   // linear candidate
+            }
+#pragma unroll
+            for (int s = 0; s < K2_NS; ++s)
+#pragma unroll
+                for (int j = 0; j < H; ++j) h[s][j] = z[s][j];
+        }
+    }
+#pragma unroll
+    for (int s = 0; s < K2_NS; ++s) {
+        float logit = P.bd;
+#pragma unroll
+        for (int j = 0; j < H; ++j) logit = fmaf(h[s][j], P.wd[j], logit);
+        epilogue(logit, valid[s], i0 + s, sid[s], dp, out);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -26,7 +26,7 @@ constexpr int K1_THREADS = 128;
 constexpr int K1_WARPS = K1_THREADS / 32;
 constexpr int K1_TILE = 32;              // frames per round
 constexpr int K1_PSTRIDE = 257;          // odd: thread-per-frame reads are bank-conflict free
-constexpr int K1_STREAMS_PER_CTA = 16;   // stream kernel: streams per tile
+constexpr int K1_STREAMS_PER_CTA = 32;   // stream kernel: streams per tile
 constexpr float K1_EPS = 2.220446049250313e-16f;   // np.finfo(float).eps, sonopy.safe_log
 
 struct MelTables {
@@ -77,53 +77,94 @@ __device__ __forceinline__ cpx load_elem(const FrameSrc<T>& s, int m) {
     return r;
 }
 
-// Phase B for one frame: P = power row in shared memory (overwritten with log-mels), out = n_out floats.
-__device__ __forceinline__ void mel_log_dct(float* P, const MelTables& t, float* __restrict__ out) {
+// Per-CTA copy of the small tables (broadcast reads in phase B).
+constexpr int K1_MAX_BINS = 257;
+constexpr int K1_MAX_FILT = 64;
+struct K1Tables {
+    float2 w[K1_MAX_BINS + 3];                 // (w_rise, w_fall) per bin
+    int grid[K1_MAX_FILT + 2];
+    float* dct;                                // [n_out][n_filt], in the dynamic tail of the CTA's shared memory
+};
+
+__device__ __forceinline__ void load_tables(K1Tables& s, const MelTables& t, float* dct_smem) {
+    if (threadIdx.x == 0) s.dct = dct_smem;
+    for (int k = threadIdx.x; k < t.n_bins; k += blockDim.x) s.w[k] = make_float2(__ldg(t.w_rise + k), __ldg(t.w_fall + k));
+    for (int k = threadIdx.x; k < t.n_filt + 2; k += blockDim.x) s.grid[k] = __ldg(t.grid + k);
+    if (!t.mels_only)
+        for (int k = threadIdx.x; k < t.n_out * t.n_filt; k += blockDim.x) dct_smem[k] = __ldg(t.dct + k);
+}
+
+// Phase B for one frame: P = power row in shared memory (its head is overwritten with the log-mels),
+// out = n_out floats (row_pad floats are written when PADDED: the destination row is 16-byte aligned
+// and padded to a multiple of 4 floats).
+template <bool PADDED>
+__device__ __forceinline__ void mel_log_dct(float* P, const K1Tables& tb, const MelTables& t, float* __restrict__ out) {
     const int nb = t.n_bins;
-    float tot = 0.f;
-    int g0 = __ldg(t.grid);
-    for (int k = 0; k < g0 && k < nb; ++k) tot += P[k];
+    const float* dct = tb.dct;
+    float tot0 = 0.f, tot1 = 0.f;
+    const int g0 = tb.grid[0];
+    for (int k = 0; k < g0 && k < nb; ++k) tot0 += P[k];
     float rise_prev = 0.f;
     for (int i = 0; i <= t.n_filt; ++i) {
-        int lo = __ldg(t.grid + i), hi = __ldg(t.grid + i + 1);
+        const int lo = tb.grid[i];
+        int hi = tb.grid[i + 1];
         hi = hi < nb ? hi : nb;
-        float r0 = 0.f, f0 = 0.f, r1 = 0.f, f1 = 0.f, s0 = 0.f, s1 = 0.f;
+        float r0 = 0.f, f0 = 0.f, r1 = 0.f, f1 = 0.f, r2 = 0.f, f2 = 0.f, r3 = 0.f, f3 = 0.f;
         int k = lo;
-        for (; k + 1 < hi; k += 2) {
-            float p0 = P[k], p1 = P[k + 1];
-            s0 += p0; s1 += p1;
-            r0 = fmaf(__ldg(t.w_rise + k), p0, r0);     r1 = fmaf(__ldg(t.w_rise + k + 1), p1, r1);
-            f0 = fmaf(__ldg(t.w_fall + k), p0, f0);     f1 = fmaf(__ldg(t.w_fall + k + 1), p1, f1);
+        for (; k + 3 < hi; k += 4) {
+            const float p0 = P[k], p1 = P[k + 1], p2 = P[k + 2], p3 = P[k + 3];
+            const float2 w0 = tb.w[k], w1 = tb.w[k + 1], w2 = tb.w[k + 2], w3 = tb.w[k + 3];
+            tot0 += p0 + p2; tot1 += p1 + p3;
+            r0 = fmaf(w0.x, p0, r0); f0 = fmaf(w0.y, p0, f0);
+            r1 = fmaf(w1.x, p1, r1); f1 = fmaf(w1.y, p1, f1);
+            r2 = fmaf(w2.x, p2, r2); f2 = fmaf(w2.y, p2, f2);
+            r3 = fmaf(w3.x, p3, r3); f3 = fmaf(w3.y, p3, f3);
         }
-        if (k < hi) {
-            float p0 = P[k];
-            s0 += p0;
-            r0 = fmaf(__ldg(t.w_rise + k), p0, r0);
-            f0 = fmaf(__ldg(t.w_fall + k), p0, f0);
+        for (; k < hi; ++k) {
+            const float p0 = P[k];
+            const float2 w0 = tb.w[k];
+            tot0 += p0;
+            r0 = fmaf(w0.x, p0, r0); f0 = fmaf(w0.y, p0, f0);
         }
-        tot += s0 + s1;
-        if (i > 0) P[i - 1] = logf(fmaxf(rise_prev + (f0 + f1), K1_EPS));   // grid[i+1] >= i+1: slot is already consumed
-        rise_prev = r0 + r1;
+        if (i > 0) P[i - 1] = logf(fmaxf(rise_prev + ((f0 + f1) + (f2 + f3)), K1_EPS));   // grid[i+1] >= i+1: slot already consumed
+        rise_prev = (r0 + r1) + (r2 + r3);
     }
-    for (int k = __ldg(t.grid + t.n_filt + 1); k < nb; ++k) tot += P[k];
+    for (int k = tb.grid[t.n_filt + 1]; k < nb; ++k) tot0 += P[k];
     if (t.mels_only) {
         for (int j = 0; j < t.n_out; ++j) out[j] = P[j];
         return;
     }
-    out[0] = logf(fmaxf(tot, K1_EPS));
-    for (int c = 1; c < t.n_out; ++c) {
-        const float* d = t.dct + c * t.n_filt;
-        float a0 = 0.f, a1 = 0.f;
-        int j = 0;
-        for (; j + 1 < t.n_filt; j += 2) { a0 = fmaf(__ldg(d + j), P[j], a0); a1 = fmaf(__ldg(d + j + 1), P[j + 1], a1); }
-        if (j < t.n_filt) a0 = fmaf(__ldg(d + j), P[j], a0);
-        out[c] = a0 + a1;
+    const float c0 = logf(fmaxf(tot0 + tot1, K1_EPS));
+    if (PADDED) {
+        // rows of 4 outputs, stored as float4
+        for (int c4 = 0; c4 < t.n_out; c4 += 4) {
+            float a[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int j = 0; j < t.n_filt; ++j) {
+                const float m = P[j];
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if (c4 + q < t.n_out) a[q] = fmaf(dct[(c4 + q) * t.n_filt + j], m, a[q]);
+            }
+            if (c4 == 0) a[0] = c0;
+            *reinterpret_cast<float4*>(out + c4) = make_float4(a[0], a[1], a[2], a[3]);
+        }
+    } else {
+        out[0] = c0;
+        for (int c = 1; c < t.n_out; ++c) {
+            const float* d = dct + c * t.n_filt;
+            float a0 = 0.f, a1 = 0.f;
+            int j = 0;
+            for (; j + 1 < t.n_filt; j += 2) { a0 = fmaf(d[j], P[j], a0); a1 = fmaf(d[j + 1], P[j + 1], a1); }
+            if (j < t.n_filt) a0 = fmaf(d[j], P[j], a0);
+            out[c] = a0 + a1;
+        }
     }
 }
 
 struct K1Smem {
     float power[K1_TILE * K1_PSTRIDE];
     float2 xch[K1_WARPS * 2 * XCH_ELEMS];
+    K1Tables tab;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -139,6 +180,8 @@ mfcc_batch_kernel(const T* __restrict__ pcm, long long samples_per_stream, long 
     FftLaneConst lc;
     load_lane_const(lc, tab.tw_stage, tab.tw_post, l16);
     float2* xch = sm.xch + (warp * 2 + half) * XCH_ELEMS;
+    load_tables(sm.tab, tab, reinterpret_cast<float*>(smem_raw + sizeof(K1Smem)));
+    __syncthreads();
     const long long n_tiles = (total_frames + K1_TILE - 1) / K1_TILE;
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const long long g_base = tile * K1_TILE;
@@ -166,7 +209,7 @@ mfcc_batch_kernel(const T* __restrict__ pcm, long long samples_per_stream, long 
         // ---- phase B: thread per frame
         if (threadIdx.x < K1_TILE) {
             const long long g = g_base + threadIdx.x;
-            if (g < total_frames) mel_log_dct(sm.power + threadIdx.x * K1_PSTRIDE, tab, out + g * tab.n_out);
+            if (g < total_frames) mel_log_dct<false>(sm.power + threadIdx.x * K1_PSTRIDE, sm.tab, tab, out + g * tab.n_out);
         }
         __syncthreads();
     }
@@ -189,52 +232,51 @@ __host__ __device__ __forceinline__ long long frames_ready(long long n, int need
 struct K1StreamSmem {
     K1Smem k1;
     // frame work list for this tile
-    int fr_stream[K1_STREAMS_PER_CTA * 8];    // local stream slot
-    long long fr_index[K1_STREAMS_PER_CTA * 8]; // absolute frame index k
+    short fr_stream[K1_STREAMS_PER_CTA * 8];     // local stream slot
+    short fr_sub[K1_STREAMS_PER_CTA * 8];        // j-th new frame of that stream
     int n_frames_tile;
     int st_id[K1_STREAMS_PER_CTA];
+    int st_cnt[K1_STREAMS_PER_CTA];
     long long st_n0[K1_STREAMS_PER_CTA];
     long long st_ts0[K1_STREAMS_PER_CTA];
-    int st_cnt[K1_STREAMS_PER_CTA];
     long long st_c0[K1_STREAMS_PER_CTA];
 };
 
-// One tick: stream ids[i] (or i) receives pcm[i][0..chunk).
-// max_new: upper bound of frames a stream can complete per tick (<= 8, host-checked).
+// One tick: stream ids[i] (or i) receives pcm[i][0..chunk).  A stream completes at most 8 frames
+// per tick (host-checked).
 template <bool PAIRS>
 __global__ void __launch_bounds__(K1_THREADS, 4)
 mfcc_stream_kernel(const int16_t* __restrict__ pcm, const int* __restrict__ ids, int n, int chunk,
-                   int hop, int used, int max_new, float scale, MelTables tab, StreamState st) {
+                   int hop, int used, float scale, MelTables tab, StreamState st) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     K1StreamSmem& sm = *reinterpret_cast<K1StreamSmem*>(smem_raw);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, l16 = lane & 15, half = lane >> 4;
     FftLaneConst lc;
     load_lane_const(lc, tab.tw_stage, tab.tw_post, l16);
     float2* xch = sm.k1.xch + (warp * 2 + half) * XCH_ELEMS;
+    load_tables(sm.k1.tab, tab, reinterpret_cast<float*>(smem_raw + sizeof(K1StreamSmem)));
     const int n_tiles = (n + K1_STREAMS_PER_CTA - 1) / K1_STREAMS_PER_CTA;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int base = tile * K1_STREAMS_PER_CTA;
-        // ---- bookkeeping: one thread per stream
-        if (threadIdx.x < K1_STREAMS_PER_CTA) {
-            int i = base + threadIdx.x, cnt = 0, sid = -1;
+        // ---- bookkeeping: warp 0, one lane per stream; frame list by warp prefix sum
+        if (warp == 0) {
+            const int i = base + lane;
+            int cnt = 0, sid = -1;
             long long n0 = 0, c0 = 0, ts0 = 0;
             if (i < n) {
                 sid = ids ? ids[i] : i;
                 n0 = st.n_samples[sid];
                 c0 = frames_ready(n0, used, hop);
-                long long c1 = frames_ready(n0 + chunk, used, hop);
-                cnt = (int)(c1 - c0);
+                cnt = (int)(frames_ready(n0 + chunk, used, hop) - c0);
                 ts0 = c0 * hop < n0 ? c0 * hop : n0;        // first absolute sample held in the tail
             }
-            sm.st_id[threadIdx.x] = sid; sm.st_n0[threadIdx.x] = n0; sm.st_ts0[threadIdx.x] = ts0;
-            sm.st_cnt[threadIdx.x] = cnt; sm.st_c0[threadIdx.x] = c0;
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            int w = 0;
-            for (int t = 0; t < K1_STREAMS_PER_CTA; ++t)
-                for (int j = 0; j < sm.st_cnt[t]; ++j) { sm.fr_stream[w] = t; sm.fr_index[w] = sm.st_c0[t] + j; ++w; }
-            sm.n_frames_tile = w;
+            sm.st_id[lane] = sid; sm.st_n0[lane] = n0; sm.st_ts0[lane] = ts0; sm.st_cnt[lane] = cnt; sm.st_c0[lane] = c0;
+            int incl = cnt;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { int v = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += v; }
+            const int off = incl - cnt;
+            for (int j = 0; j < cnt; ++j) { sm.fr_stream[off + j] = (short)lane; sm.fr_sub[off + j] = (short)j; }
+            if (lane == 31) sm.n_frames_tile = incl;
         }
         __syncthreads();
         const int nf = sm.n_frames_tile;
@@ -248,16 +290,15 @@ mfcc_stream_kernel(const int16_t* __restrict__ pcm, const int* __restrict__ ids,
                 cpx z[16];
                 if (active) {
                     const int t = sm.fr_stream[r0 + slot];
-                    const long long a0 = sm.fr_index[r0 + slot] * hop;     // absolute first sample
+                    const long long a0 = (sm.st_c0[t] + sm.fr_sub[r0 + slot]) * hop;     // absolute first sample
                     const long long n0 = sm.st_n0[t];
-                    const int sid = sm.st_id[t];
                     const int16_t* chunk_p = pcm + (long long)(base + t) * chunk;
                     FrameSrc<int16_t> src;
                     src.used = used;
                     if (a0 >= n0) { src.len0 = 0; src.p0 = chunk_p; src.p1 = chunk_p + (a0 - n0); }
                     else {
                         src.len0 = (int)min((long long)used, n0 - a0);
-                        src.p0 = st.tail + (long long)sid * st.tail_cap + (a0 - sm.st_ts0[t]);
+                        src.p0 = st.tail + (long long)sm.st_id[t] * st.tail_cap + (a0 - sm.st_ts0[t]);
                         src.p1 = chunk_p;
                     }
 #pragma unroll
@@ -269,35 +310,46 @@ mfcc_stream_kernel(const int16_t* __restrict__ pcm, const int* __restrict__ ids,
                 fft512_power(z, lc, xch, sm.k1.power + slot * K1_PSTRIDE, scale, l16, active);
             }
             __syncthreads();
-            // ---- phase B: rows go straight into the ring
+            // ---- phase B: rows go straight into the ring (rows are 16-byte aligned and padded)
             if (threadIdx.x < nr) {
                 const int t = sm.fr_stream[r0 + threadIdx.x];
-                const long long k = sm.fr_index[r0 + threadIdx.x];
+                const long long k = sm.st_c0[t] + sm.fr_sub[r0 + threadIdx.x];
                 float* row = st.ring + ((long long)sm.st_id[t] * st.ring_rows + (int)(k % st.ring_rows)) * st.row_stride;
-                mel_log_dct(sm.k1.power + threadIdx.x * K1_PSTRIDE, tab, row);
+                mel_log_dct<true>(sm.k1.power + threadIdx.x * K1_PSTRIDE, sm.k1.tab, tab, row);
             }
             __syncthreads();
         }
-        // ---- tail + counter update: one warp per stream, reads complete before writes
+        // ---- tail + counter update: one warp per stream, all reads of the old tail precede the writes
         for (int t = warp; t < K1_STREAMS_PER_CTA; t += K1_WARPS) {
             const int sid = sm.st_id[t];
             if (sid < 0) continue;
             const long long n0 = sm.st_n0[t], n1 = n0 + chunk, ts0 = sm.st_ts0[t];
-            const long long c1 = frames_ready(n1, used, hop);
+            const long long c1 = sm.st_c0[t] + sm.st_cnt[t];
             const long long ts1 = c1 * hop < n1 ? c1 * hop : n1;
             const int len1 = (int)(n1 - ts1);
             const int n_old = ts1 < n0 ? (int)(n0 - ts1) : 0;       // part that comes from the old tail
             int16_t* tl = st.tail + (long long)sid * st.tail_cap;
             const int16_t* chunk_p = pcm + (long long)(base + t) * chunk;
-            int16_t keep[64];                                        // tail_cap <= 2048 = 64 * 32
-            const int off = (int)(ts1 - ts0);
+            if (n_old > 0) {
+                int16_t keep[64];                                    // tail_cap <= 2048 = 64 * 32
+                const int off = (int)(ts1 - ts0);
 #pragma unroll 1
-            for (int j = 0; j * 32 < n_old; ++j) { int i = j * 32 + lane; keep[j & 63] = i < n_old ? tl[off + i] : (int16_t)0; }
-            __syncwarp();
+                for (int j = 0; j * 32 < n_old; ++j) { int i = j * 32 + lane; keep[j & 63] = i < n_old ? tl[off + i] : (int16_t)0; }
+                __syncwarp();
 #pragma unroll 1
-            for (int j = 0; j * 32 < n_old; ++j) { int i = j * 32 + lane; if (i < n_old) tl[i] = keep[j & 63]; }
-            const long long coff = (ts1 > n0 ? ts1 - n0 : 0);
-            for (int i = n_old + lane; i < len1; i += 32) tl[i] = chunk_p[coff + (i - n_old)];
+                for (int j = 0; j * 32 < n_old; ++j) { int i = j * 32 + lane; if (i < n_old) tl[i] = keep[j & 63]; }
+            }
+            const int16_t* srcp = chunk_p + (ts1 > n0 ? ts1 - n0 : 0);
+            int16_t* dstp = tl + n_old;
+            const int m = len1 - n_old;                              // samples copied from the chunk
+            int done = 0;
+            if ((((uintptr_t)srcp | (uintptr_t)dstp) & 15) == 0) {   // 16-byte vectors (default geometry)
+                const int nv = m >> 3;
+                for (int v = lane; v < nv; v += 32)
+                    reinterpret_cast<int4*>(dstp)[v] = __ldg(reinterpret_cast<const int4*>(srcp) + v);
+                done = nv << 3;
+            }
+            for (int i = done + lane; i < m; i += 32) dstp[i] = srcp[i];
             if (lane == 0) st.n_samples[sid] = n1;
         }
         __syncthreads();
