@@ -188,6 +188,10 @@ int64_t pb_get_cdf(const pb_handle* h, double* h_out, int64_t capacity, int32_t*
  * from numpy's SIMD exp by at most an ulp per entry. */
 int pb_set_cdf(pb_handle* h, const double* h_cd, int64_t len);
 
+/* Test hook: route the aligned default geometry through the generic (any-alignment) MFCC kernels
+ * instead of the warp-autonomous fast kernels, so both implementations are covered by parity tests. */
+int pb_debug_force_generic(pb_handle* h, int on);
+
 const char* pb_last_error(void);
 int pb_abi_version(void);
 const char* pb_build_info(void);

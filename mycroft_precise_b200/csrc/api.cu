@@ -16,6 +16,7 @@
 #include "../../include/precise_b200.h"
 #include "gru_kernels.cuh"
 #include "mfcc_kernels.cuh"
+#include "mfcc_fast.cuh"
 
 using namespace pb;
 
@@ -54,7 +55,11 @@ struct pb_handle {
     int sm_count = 148;
     // derived
     int used = 0, n_bins = 0, n_out = 0, feat = 0, ring_rows = 0, row_stride = 0, tail_cap = 0, max_new = 0;
-    size_t k1_batch_smem = 0, k1_stream_smem = 0;
+    size_t k1_batch_smem = 0, k1_stream_smem = 0, k1_fast_smem = 0;
+    bool force_generic = false;      // tests: exercise the generic kernels on the aligned geometry
+    bool fast_ok = false;            // aligned geometry: warp-autonomous kernels (mfcc_fast.cuh)
+    int n_pieces = 0;
+    int *d_piece = nullptr, *d_seg_first = nullptr;
     // host copies of tables
     std::vector<double> fb;        // [n_filt][n_bins]
     std::vector<double> cd;
@@ -201,7 +206,7 @@ PB_API void pb_destroy(pb_handle* h) {
     if (!h) return;
     cudaSetDevice(h->cfg.device);
     cudaFree(h->d_wrise); cudaFree(h->d_wfall); cudaFree(h->d_dct); cudaFree(h->d_grid);
-    cudaFree(h->d_tw_stage); cudaFree(h->d_tw_post); cudaFree(h->d_cd);
+    cudaFree(h->d_tw_stage); cudaFree(h->d_tw_post); cudaFree(h->d_cd); cudaFree(h->d_piece); cudaFree(h->d_seg_first);
     cudaFree(h->st.n_samples); cudaFree(h->st.tail); cudaFree(h->st.ring); cudaFree(h->st.trig);
     cudaFree(h->d_wcat); cudaFree(h->d_bias); cudaFree(h->d_wd); cudaFree(h->d_count);
     if (h->h_count_pinned) cudaFreeHost(h->h_count_pinned);
@@ -258,6 +263,23 @@ PB_API int pb_create(const pb_config* cfg, pb_handle** out) {
     std::vector<int> grid;
     int rc = build_mel(h, wrise, wfall, grid);
     if (rc != PB_OK) { delete h; return rc; }
+    // piece schedule of the 16-lane mel stage (mfcc_fast.cuh): <= 8 bins each, never across a grid point
+    std::vector<int> pieces, seg_first(c.n_filt + 2, 0);
+    {
+        auto add_range = [&](int lo, int hi) {
+            for (int k = lo; k < hi; k += K1F_PIECE_LEN) pieces.push_back(k | (std::min(K1F_PIECE_LEN, hi - k) << 16));
+        };
+        for (int i = 0; i <= c.n_filt; ++i) {
+            seg_first[i] = (int)pieces.size();
+            add_range(grid[i], std::min(grid[i + 1], h->n_bins));
+        }
+        seg_first[c.n_filt + 1] = (int)pieces.size();
+        add_range(0, std::min(grid[0], h->n_bins));                       // bins outside the grid: total power only
+        add_range(grid[c.n_filt + 1], h->n_bins);
+        h->n_pieces = (int)pieces.size();
+    }
+    h->fast_ok = c.n_fft == 512 && h->used == 512 && c.hop_samples % 8 == 0 && h->n_pieces <= K1F_MAX_PIECES;
+    h->k1_fast_smem = sizeof(K1FShared) + K1F_WARPS * sizeof(K1FWarp) + (size_t)h->n_out * c.n_filt * sizeof(float);
     // DCT-II, norm='ortho' (scipy.fftpack.dct as sonopy.mfcc_spec calls it), first n_out rows
     std::vector<float> dct((size_t)h->n_out * c.n_filt);
     for (int k = 0; k < h->n_out; ++k)
@@ -293,6 +315,8 @@ PB_API int pb_create(const pb_config* cfg, pb_handle** out) {
     CKH(upload(&h->d_tw_stage, tws));
     CKH(upload(&h->d_tw_post, twp));
     CKH(upload(&h->d_cd, h->cd));
+    CKH(upload(&h->d_piece, pieces));
+    CKH(upload(&h->d_seg_first, seg_first));
     const size_t S = (size_t)c.max_streams;
     h->st.tail_cap = h->tail_cap; h->st.ring_rows = h->ring_rows; h->st.row_stride = h->row_stride;
     CKH(cudaMalloc((void**)&h->st.n_samples, S * sizeof(long long)));
@@ -309,6 +333,8 @@ PB_API int pb_create(const pb_config* cfg, pb_handle** out) {
     CKH(cudaFuncSetAttribute(mfcc_batch_kernel<int16_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->k1_batch_smem));
     CKH(cudaFuncSetAttribute(mfcc_batch_kernel<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->k1_batch_smem));
     CKH(cudaFuncSetAttribute(mfcc_batch_kernel<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->k1_batch_smem));
+    CKH(cudaFuncSetAttribute(mfcc_fast_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->k1_fast_smem));
+    CKH(cudaFuncSetAttribute(mfcc_fast_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->k1_fast_smem));
     CKH(cudaFuncSetAttribute(mfcc_stream_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->k1_stream_smem));
     CKH(cudaFuncSetAttribute(mfcc_stream_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->k1_stream_smem));
 #undef CKH
@@ -402,6 +428,8 @@ struct ProfScope {
     ~ProfScope() { if (idx >= 0) cudaEventRecord(h->prof[slot].ev[idx + 1], s); }
 };
 
+PB_API int pb_debug_force_generic(pb_handle* h, int on) { if (!h) return fail(PB_ERR_INVALID, "null handle"); h->force_generic = on != 0; return PB_OK; }
+
 PB_API int pb_profile_enable(pb_handle* h, int on) { if (!h) return fail(PB_ERR_INVALID, "null handle"); h->profiling = on != 0; return PB_OK; }
 
 PB_API int pb_profile_reset(pb_handle* h) {
@@ -436,6 +464,12 @@ static MelTables mel_tables(const pb_handle* h) {
     return t;
 }
 
+static FastTables fast_tables(const pb_handle* h) {
+    FastTables f;
+    f.piece = h->d_piece; f.seg_first = h->d_seg_first; f.n_pieces = h->n_pieces;
+    return f;
+}
+
 static DecodeParams decode_params(const pb_handle* h) {
     DecodeParams d;
     d.cd = h->d_cd; d.cd_len = (int)h->cd.size();
@@ -464,7 +498,12 @@ static int mfcc_impl(pb_handle* h, const T* d_in, int64_t n_streams, int64_t L, 
     const int64_t tiles = (total + K1_TILE - 1) / K1_TILE;
     const int grid = (int)std::min<int64_t>(tiles, (int64_t)h->sm_count * 4);
     ProfScope ps(h, 0, s);
-    if (pairs)
+    if (sizeof(T) == 2 && h->fast_ok && L % 8 == 0 && (uintptr_t)d_in % 16 == 0 && !h->force_generic) {
+        const int64_t pairs2 = (total + 1) / 2;
+        const int gridf = (int)std::min<int64_t>((pairs2 + K1F_WARPS - 1) / K1F_WARPS, (int64_t)h->sm_count * 4);
+        mfcc_fast_batch_kernel<<<gridf, K1F_THREADS, h->k1_fast_smem, s>>>((const int16_t*)d_in, L, nf, total, h->cfg.hop_samples, scale,
+                                                                           mel_tables(h), fast_tables(h), d_out);
+    } else if (pairs)
         mfcc_batch_kernel<T, true><<<grid, K1_THREADS, h->k1_batch_smem, s>>>(d_in, L, nf, total, h->cfg.hop_samples, h->used, scale, mel_tables(h), d_out);
     else
         mfcc_batch_kernel<T, false><<<grid, K1_THREADS, h->k1_batch_smem, s>>>(d_in, L, nf, total, h->cfg.hop_samples, h->used, scale, mel_tables(h), d_out);
@@ -545,7 +584,12 @@ static int launch_stream_mfcc(pb_handle* h, const int16_t* d_pcm, const int32_t*
     const int grid = (int)std::min<int64_t>(tiles, (int64_t)h->sm_count * 4);
     const float inv = 1.0f / 32768.0f, scale = inv * inv / (float)h->cfg.n_fft;
     ProfScope ps(h, 0, s);
-    if (pairs)
+    if (h->fast_ok && h->cfg.chunk_samples % 8 == 0 && (uintptr_t)d_pcm % 16 == 0 && !h->force_generic) {
+        const int64_t tilesf = (n + K1F_STREAMS_PER_WARP - 1) / K1F_STREAMS_PER_WARP;
+        const int gridf = (int)std::min<int64_t>((tilesf + K1F_WARPS - 1) / K1F_WARPS, (int64_t)h->sm_count * 4);
+        mfcc_fast_stream_kernel<<<gridf, K1F_THREADS, h->k1_fast_smem, s>>>(d_pcm, d_ids, (int)n, h->cfg.chunk_samples, h->cfg.hop_samples, scale,
+                                                                            mel_tables(h), fast_tables(h), h->st);
+    } else if (pairs)
         mfcc_stream_kernel<true><<<grid, K1_THREADS, h->k1_stream_smem, s>>>(d_pcm, d_ids, (int)n, h->cfg.chunk_samples, h->cfg.hop_samples, h->used, scale, mel_tables(h), h->st);
     else
         mfcc_stream_kernel<false><<<grid, K1_THREADS, h->k1_stream_smem, s>>>(d_pcm, d_ids, (int)n, h->cfg.chunk_samples, h->cfg.hop_samples, h->used, scale, mel_tables(h), h->st);

@@ -133,8 +133,10 @@ constexpr int K2_NS = 2;                       // streams per thread: every weig
 template <int H, int F, int KP>
 __device__ __forceinline__ void gate_dot(const float (*Wt)[KP], int j, float bias, const float (&x)[K2_NS][F],
                                          const float (&hv)[K2_NS][H], float (&a)[K2_NS]) {
+    // two partial sums per stream (even / odd k) double the number of independent FMA chains
+    float a0[K2_NS], a1[K2_NS];
 #pragma unroll
-    for (int s = 0; s < K2_NS; ++s) a[s] = bias;
+    for (int s = 0; s < K2_NS; ++s) { a0[s] = bias; a1[s] = 0.f; }
 #pragma unroll
     for (int q = 0; q < KP / 4; ++q) {
         const float4 w = *reinterpret_cast<const float4*>(&Wt[j][4 * q]);
@@ -144,10 +146,16 @@ __device__ __forceinline__ void gate_dot(const float (*Wt)[KP], int j, float bia
             const int k = 4 * q + e;
             if (k < F + H) {
 #pragma unroll
-                for (int s = 0; s < K2_NS; ++s) a[s] = fmaf(k < F ? x[s][k < F ? k : 0] : hv[s][k >= F ? k - F : 0], wv[e], a[s]);
+                for (int s = 0; s < K2_NS; ++s) {
+                    const float vin = k < F ? x[s][k < F ? k : 0] : hv[s][k >= F ? k - F : 0];
+                    if (e & 1) a1[s] = fmaf(vin, wv[e], a1[s]);
+                    else a0[s] = fmaf(vin, wv[e], a0[s]);
+                }
             }
         }
     }
+#pragma unroll
+    for (int s = 0; s < K2_NS; ++s) a[s] = a0[s] + a1[s];
 }
 
 // One thread owns K2_NS adjacent streams; h, z, r*h live in registers.  The weights sit in shared

@@ -1,0 +1,315 @@
+// mfcc_fast.cuh -- K1 fast path: warp-autonomous MFCC pipeline for the 16-byte-aligned geometry
+// (n_fft = window-crop = 512 samples; hop, chunk and buffer length multiples of 8 samples -- true for
+// the reference defaults, precise/params.py:140-144, and the 1024-sample runner chunk).
+//
+// Every warp is its own pipeline, there is no block-level barrier after start-up:
+//
+//   pass p:  [bulk copy of pass p+1's two frames -> staging buffer (p+1)&1, cp.async.bulk + mbarrier]
+//            wait for buffer p&1 -> 16 x LDS.32 per lane -> FFT-512 (fft512.cuh; the same buffer is
+//            reused as the transpose scratch and then holds the 257 power bins) -> mel/log/DCT by the
+//            16 lanes of the half-warp -> one coalesced store of the MFCC row
+//
+// Mel stage on 16 lanes.  The spectrum is cut into "pieces" (<= 8 bins, never crossing a mel-grid
+// point; built on the host).  Lane l accumulates pieces l, l+16, ...: rise/fall partial sums
+// (w_rise[k] P[k], w_fall[k] P[k]) and its share of the total power.  Filter j then adds the rise
+// partials of grid segment j and the fall partials of segment j+1 (sonopy.filterbanks geometry, see
+// mfcc_kernels.cuh), takes log(max(., eps)), and lane c forms DCT row c.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "fft512.cuh"
+#include "mfcc_kernels.cuh"
+
+namespace pb {
+
+// ------------------------------------------------------------------------------------------------
+// PTX: mbarrier + 1-D bulk async copy (TMA engine, SASS UBLKCP)
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+
+// ------------------------------------------------------------------------------------------------
+constexpr int K1F_THREADS = 128;
+constexpr int K1F_WARPS = K1F_THREADS / 32;
+constexpr int K1F_MAX_PIECES = 128;
+constexpr int K1F_PIECE_LEN = 8;
+constexpr int K1F_STREAMS_PER_WARP = 16;
+constexpr int K1F_MAX_NEW = 8;
+
+struct FastTables {            // device copies built by the host (api.cu: build_pieces)
+    const int* piece;          // [n_pieces] start | (len << 16)
+    const int* seg_first;      // [n_filt + 2] first piece id of grid segment i; [n_filt + 1] = end
+    int n_pieces;
+};
+
+struct K1FShared {             // per CTA
+    float2 w[K1_MAX_BINS + 3];
+    int piece[K1F_MAX_PIECES];
+    int seg_first[K1_MAX_FILT + 4];
+};
+
+struct K1FWarp {               // per warp
+    float2 buf[2][2][XCH_ELEMS];               // [stage][half]: input staging -> transpose scratch -> power bins
+    float pr[2][K1F_MAX_PIECES];
+    float pf[2][K1F_MAX_PIECES];
+    float mel[2][K1_MAX_FILT];
+    unsigned long long bar[2];
+    // stream mode bookkeeping for the warp's tile of streams
+    long long st_n0[K1F_STREAMS_PER_WARP], st_ts0[K1F_STREAMS_PER_WARP], st_c0[K1F_STREAMS_PER_WARP];
+    int st_id[K1F_STREAMS_PER_WARP], st_cnt[K1F_STREAMS_PER_WARP];
+    short fr_stream[K1F_STREAMS_PER_WARP * K1F_MAX_NEW], fr_sub[K1F_STREAMS_PER_WARP * K1F_MAX_NEW];
+};
+
+__device__ __forceinline__ void load_fast_tables(K1FShared& s, const MelTables& t, const FastTables& ft, float* dct_smem) {
+    for (int k = threadIdx.x; k < t.n_bins; k += blockDim.x) s.w[k] = make_float2(__ldg(t.w_rise + k), __ldg(t.w_fall + k));
+    for (int k = threadIdx.x; k < ft.n_pieces; k += blockDim.x) s.piece[k] = __ldg(ft.piece + k);
+    for (int k = threadIdx.x; k < t.n_filt + 2; k += blockDim.x) s.seg_first[k] = __ldg(ft.seg_first + k);
+    if (!t.mels_only)
+        for (int k = threadIdx.x; k < t.n_out * t.n_filt; k += blockDim.x) dct_smem[k] = __ldg(t.dct + k);
+}
+
+// mel / log / DCT for one frame by its 16 lanes.  P: 257 power bins (shared).  out: n_out floats.
+// All 32 lanes of the warp call this (the other half works on its own frame); `active` only gates
+// the final store.
+__device__ __forceinline__ void mel16(const float* P, const K1FShared& ts, const float* dct, const MelTables& t, int n_pieces,
+                                      float* pr, float* pf, float* mel, int l16, bool active, float* __restrict__ out) {
+    float tot = 0.f;
+    for (int p = l16; p < n_pieces; p += 16) {
+        const int pc = ts.piece[p];
+        const int start = pc & 0xffff, len = pc >> 16;
+        float r = 0.f, f = 0.f;
+#pragma unroll
+        for (int i = 0; i < K1F_PIECE_LEN; ++i) {
+            if (i < len) {
+                const float pw = P[start + i];
+                const float2 w = ts.w[start + i];
+                tot += pw;
+                r = fmaf(w.x, pw, r);
+                f = fmaf(w.y, pw, f);
+            }
+        }
+        pr[p] = r; pf[p] = f;
+    }
+    // total power over the 16 lanes of this half-warp
+#pragma unroll
+    for (int d = 8; d >= 1; d >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, d);
+    __syncwarp();
+    for (int j = l16; j < t.n_filt; j += 16) {
+        const int a = ts.seg_first[j], b = ts.seg_first[j + 1], c = ts.seg_first[j + 2];
+        float m = 0.f;
+        for (int p = a; p < b; ++p) m += pr[p];
+        for (int p = b; p < c; ++p) m += pf[p];
+        mel[j] = logf(fmaxf(m, K1_EPS));
+    }
+    __syncwarp();
+    if (t.mels_only) {
+        for (int j = l16; j < t.n_out; j += 16)
+            if (active) out[j] = mel[j];
+    } else {
+        for (int c = l16; c < t.n_out; c += 16) {
+            float a0 = 0.f, a1 = 0.f;
+            const float* d = dct + c * t.n_filt;
+            int j = 0;
+            for (; j + 1 < t.n_filt; j += 2) { a0 = fmaf(d[j], mel[j], a0); a1 = fmaf(d[j + 1], mel[j + 1], a1); }
+            if (j < t.n_filt) a0 = fmaf(d[j], mel[j], a0);
+            const float v = c == 0 ? logf(fmaxf(tot, K1_EPS)) : a0 + a1;
+            if (active) out[c] = v;
+        }
+    }
+    __syncwarp();
+}
+
+// One FFT + mel pass for the warp's two frames whose 1 KB inputs have landed in ws.buf[stage].
+__device__ __forceinline__ void fast_pass(K1FWarp& ws, int stage, uint32_t parity, const FftLaneConst& lc, const K1FShared& ts,
+                                          const float* dct, const MelTables& t, int n_pieces, float scale, int l16, int half,
+                                          bool active, float* __restrict__ out) {
+    mbar_wait(&ws.bar[stage], parity);
+    const int* in = reinterpret_cast<const int*>(ws.buf[stage][half]);
+    cpx z[16];
+#pragma unroll
+    for (int n1 = 0; n1 < 16; ++n1) {
+        const int v = active ? in[16 * n1 + l16] : 0;
+        z[n1].x = (float)(short)(v & 0xffff);
+        z[n1].y = (float)(short)(v >> 16);
+    }
+    __syncwarp();                                  // all lanes have read the staged samples: the buffer becomes scratch
+    float* P = reinterpret_cast<float*>(ws.buf[stage][half]);
+    fft512_power(z, lc, ws.buf[stage][half], P, scale, l16, active);   // P aliases the scratch: written after the last scratch read
+    __syncwarp();
+    mel16(P, ts, dct, t, n_pieces, ws.pr[half], ws.pf[half], ws.mel[half], l16, active, out);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Stateless batch kernel (pb_mfcc on the aligned geometry).  Global frame g = stream * n_frames + f.
+__global__ void __launch_bounds__(K1F_THREADS, 4)
+mfcc_fast_batch_kernel(const int16_t* __restrict__ pcm, long long samples_per_stream, long long n_frames_per_stream,
+                       long long total_frames, int hop, float scale, MelTables tab, FastTables ft, float* __restrict__ out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    K1FShared& ts = *reinterpret_cast<K1FShared*>(smem_raw);
+    K1FWarp* wsm = reinterpret_cast<K1FWarp*>(smem_raw + sizeof(K1FShared));
+    float* dct = reinterpret_cast<float*>(smem_raw + sizeof(K1FShared) + K1F_WARPS * sizeof(K1FWarp));
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, l16 = lane & 15, half = lane >> 4;
+    K1FWarp& ws = wsm[warp];
+    load_fast_tables(ts, tab, ft, dct);
+    if (lane == 0) { mbar_init(&ws.bar[0], 1); mbar_init(&ws.bar[1], 1); fence_mbar_init(); }
+    FftLaneConst lc;
+    load_lane_const(lc, tab.tw_stage, tab.tw_post, l16);
+    __syncthreads();
+
+    const long long n_pairs = (total_frames + 1) / 2;
+    const long long gwarp = (long long)blockIdx.x * K1F_WARPS + warp, nwarps = (long long)gridDim.x * K1F_WARPS;
+    auto issue = [&](long long pair, int stage) {            // lane 0: bulk copies for both frames of `pair`
+        const long long g0 = 2 * pair;
+        const int nfr = (g0 + 1 < total_frames) ? 2 : 1;
+        fence_proxy_async();
+        mbar_expect_tx(&ws.bar[stage], 1024u * nfr);
+        for (int hf = 0; hf < nfr; ++hf) {
+            const long long g = g0 + hf, s = g / n_frames_per_stream, f = g - s * n_frames_per_stream;
+            bulk_g2s(ws.buf[stage][hf], pcm + s * samples_per_stream + f * hop, 1024u, &ws.bar[stage]);
+        }
+    };
+    long long pair = gwarp;
+    int it = 0;
+    if (pair < n_pairs && lane == 0) issue(pair, 0);
+    for (; pair < n_pairs; pair += nwarps, ++it) {
+        const int stage = it & 1;
+        const long long next = pair + nwarps;
+        if (next < n_pairs && lane == 0) issue(next, stage ^ 1);
+        const long long g = 2 * pair + half;
+        const bool active = g < total_frames;
+        fast_pass(ws, stage, (uint32_t)((it >> 1) & 1), lc, ts, dct, tab, ft.n_pieces, scale, l16, half, active,
+                  out + (active ? g : 0) * tab.n_out);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Stateful tick (pb_update / pb_update_vectors on the aligned geometry): a warp owns 16 streams.
+__global__ void __launch_bounds__(K1F_THREADS, 4)
+mfcc_fast_stream_kernel(const int16_t* __restrict__ pcm, const int* __restrict__ ids, int n, int chunk, int hop,
+                        float scale, MelTables tab, FastTables ft, StreamState st) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    K1FShared& ts = *reinterpret_cast<K1FShared*>(smem_raw);
+    K1FWarp* wsm = reinterpret_cast<K1FWarp*>(smem_raw + sizeof(K1FShared));
+    float* dct = reinterpret_cast<float*>(smem_raw + sizeof(K1FShared) + K1F_WARPS * sizeof(K1FWarp));
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, l16 = lane & 15, half = lane >> 4;
+    K1FWarp& ws = wsm[warp];
+    load_fast_tables(ts, tab, ft, dct);
+    if (lane == 0) { mbar_init(&ws.bar[0], 1); mbar_init(&ws.bar[1], 1); fence_mbar_init(); }
+    FftLaneConst lc;
+    load_lane_const(lc, tab.tw_stage, tab.tw_post, l16);
+    __syncthreads();
+
+    constexpr int used = 512;
+    const int n_tiles = (n + K1F_STREAMS_PER_WARP - 1) / K1F_STREAMS_PER_WARP;
+    const int gwarp = blockIdx.x * K1F_WARPS + warp, nwarps = gridDim.x * K1F_WARPS;
+    uint32_t uses0 = 0, uses1 = 0;                          // completed uses of each staging buffer (mbarrier phase)
+    for (int tile = gwarp; tile < n_tiles; tile += nwarps) {
+        const int base = tile * K1F_STREAMS_PER_WARP;
+        // ---- bookkeeping: lane i < 16 <-> stream base + i
+        int cnt = 0;
+        {
+            const int i = base + lane;
+            int sid = -1;
+            long long n0 = 0, c0 = 0, ts0 = 0;
+            if (lane < K1F_STREAMS_PER_WARP && i < n) {
+                sid = ids ? ids[i] : i;
+                n0 = st.n_samples[sid];
+                c0 = frames_ready(n0, used, hop);
+                cnt = (int)(frames_ready(n0 + chunk, used, hop) - c0);
+                ts0 = c0 * hop < n0 ? c0 * hop : n0;
+            }
+            if (lane < K1F_STREAMS_PER_WARP) {
+                ws.st_id[lane] = sid; ws.st_n0[lane] = n0; ws.st_ts0[lane] = ts0; ws.st_cnt[lane] = cnt; ws.st_c0[lane] = c0;
+            }
+        }
+        int incl = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { int v = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += v; }
+        const int nf = __shfl_sync(0xffffffffu, incl, 31);
+        for (int j = 0; j < cnt; ++j) { ws.fr_stream[incl - cnt + j] = (short)lane; ws.fr_sub[incl - cnt + j] = (short)j; }
+        __syncwarp();
+
+        auto issue = [&](int f0, int stage) {               // lane 0: bulk copies for frames f0, f0+1 of the list
+            const int nfr = min(2, nf - f0);
+            fence_proxy_async();
+            mbar_expect_tx(&ws.bar[stage], 1024u * nfr);
+            for (int hf = 0; hf < nfr; ++hf) {
+                const int t = ws.fr_stream[f0 + hf];
+                const long long a0 = (ws.st_c0[t] + ws.fr_sub[f0 + hf]) * hop, n0 = ws.st_n0[t];
+                const int16_t* chunk_p = pcm + (long long)(base + t) * chunk;
+                char* dst = reinterpret_cast<char*>(ws.buf[stage][hf]);
+                if (a0 >= n0) {
+                    bulk_g2s(dst, chunk_p + (a0 - n0), 1024u, &ws.bar[stage]);
+                } else {
+                    const int len0 = (int)min((long long)used, n0 - a0);
+                    bulk_g2s(dst, st.tail + (long long)ws.st_id[t] * st.tail_cap + (a0 - ws.st_ts0[t]), 2u * len0, &ws.bar[stage]);
+                    if (len0 < used) bulk_g2s(dst + 2 * len0, chunk_p, 2u * (used - len0), &ws.bar[stage]);
+                }
+            }
+        };
+        int stage = 0;
+        if (nf > 0 && lane == 0) issue(0, 0);
+        for (int f0 = 0; f0 < nf; f0 += 2, stage ^= 1) {
+            if (f0 + 2 < nf && lane == 0) issue(f0 + 2, stage ^ 1);
+            const bool active = f0 + half < nf;
+            float* row = st.ring;
+            if (active) {
+                const int t = ws.fr_stream[f0 + half];
+                const long long k = ws.st_c0[t] + ws.fr_sub[f0 + half];
+                row = st.ring + ((long long)ws.st_id[t] * st.ring_rows + (int)(k % st.ring_rows)) * st.row_stride;
+            }
+            const uint32_t parity = (stage == 0 ? uses0 : uses1) & 1;
+            fast_pass(ws, stage, parity, lc, ts, dct, tab, ft.n_pieces, scale, l16, half, active, row);
+            if (stage == 0) ++uses0; else ++uses1;
+        }
+        // ---- tail + sample counter: the warp walks its streams; every old-tail read of this tile is complete
+        // (the bulk copies that read it were waited for above)
+        for (int t = 0; t < K1F_STREAMS_PER_WARP; ++t) {
+            const int sid = ws.st_id[t];
+            if (sid < 0) continue;
+            const long long n0 = ws.st_n0[t], n1 = n0 + chunk, ts0 = ws.st_ts0[t];
+            const long long c1 = ws.st_c0[t] + ws.st_cnt[t];
+            const long long ts1 = c1 * hop < n1 ? c1 * hop : n1;
+            const int len1 = (int)(n1 - ts1);
+            const int n_old = ts1 < n0 ? (int)(n0 - ts1) : 0;
+            int16_t* tl = st.tail + (long long)sid * st.tail_cap;
+            const int16_t* chunk_p = pcm + (long long)(base + t) * chunk;
+            if (n_old > 0) {                                  // shift inside the tail (chunk shorter than the FFT window)
+                int4 keep[2];                                 // n_old < 512 samples = 64 int4 = 2 per lane
+                const int4* srcv = reinterpret_cast<const int4*>(tl + (ts1 - ts0));
+                const int nv = n_old >> 3;
+#pragma unroll
+                for (int j = 0; j < 2; ++j) if (j * 32 + lane < nv) keep[j] = srcv[j * 32 + lane];
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < 2; ++j) if (j * 32 + lane < nv) reinterpret_cast<int4*>(tl)[j * 32 + lane] = keep[j];
+            }
+            const int4* srcv = reinterpret_cast<const int4*>(chunk_p + (ts1 > n0 ? ts1 - n0 : 0));
+            int4* dstv = reinterpret_cast<int4*>(tl + n_old);
+            const int nv = (len1 - n_old) >> 3;
+            for (int v = lane; v < nv; v += 32) dstv[v] = __ldg(srcv + v);
+            if (lane == 0) st.n_samples[sid] = n1;
+        }
+        __syncwarp();
+    }
+}
+
+}  // namespace pb

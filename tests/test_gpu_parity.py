@@ -86,6 +86,28 @@ def test_mfcc_batch_noise(core):
     assert err < 2e-4
 
 
+def test_generic_kernels_on_default_geometry():
+    """The any-alignment kernels (mfcc_kernels.cuh) must agree with the warp-autonomous fast kernels
+    (mfcc_fast.cuh) that normally serve the default geometry."""
+    m = _mod()
+    pcm = noise(21, 24000, seed=31)
+    a = m.PreciseB200(max_streams=32)
+    b = m.PreciseB200(max_streams=32)
+    b.force_generic(True)
+    ma, mb = a.mfcc(cuda(pcm)).cpu().numpy(), b.mfcc(cuda(pcm)).cpu().numpy()
+    want = oracle_mfcc(pcm, a.params)
+    assert np.max(np.abs(ma - want)) < 2e-4 and np.max(np.abs(mb - want)) < 2e-4
+    assert np.max(np.abs(ma - mb)) < 1e-4
+    for k in range(23):
+        c = cuda(pcm[:, k * 1024:(k + 1) * 1024])
+        a.update_vectors(c)
+        b.update_vectors(c)
+        wa, wb = a.read_window(21).cpu().numpy(), b.read_window(21).cpu().numpy()
+        assert np.max(np.abs(wa - wb)) < 1e-4
+    assert np.abs(wa).max() > 1
+    a.close(); b.close()
+
+
 def test_mfcc_lengths_and_ragged_tail(core):
     for L in (1600, 1601, 2399, 2400, 3333, 9999):
         pcm = noise(3, L, seed=L)
