@@ -53,6 +53,7 @@ constexpr int K1F_MAX_PIECES = 128;
 constexpr int K1F_PIECE_LEN = 8;
 constexpr int K1F_STREAMS_PER_WARP = 16;
 constexpr int K1F_MAX_NEW = 8;
+constexpr int K1F_BUF_ELEMS = XCH_ELEMS + 8;   // +64 B: the two half-warps of a warp hit disjoint bank halves on 32-bit accesses
 
 struct FastTables {            // device copies built by the host (api.cu: build_pieces)
     const int* piece;          // [n_pieces] start | (len << 16)
@@ -67,7 +68,7 @@ struct K1FShared {             // per CTA
 };
 
 struct K1FWarp {               // per warp
-    float2 buf[2][2][XCH_ELEMS];               // [stage][half]: input staging -> transpose scratch -> power bins
+    float2 buf[2][2][K1F_BUF_ELEMS];           // [stage][half]: input staging -> transpose scratch -> power bins
     float pr[2][K1F_MAX_PIECES];
     float pf[2][K1F_MAX_PIECES];
     float mel[2][K1_MAX_FILT];
@@ -92,12 +93,16 @@ __device__ __forceinline__ void load_fast_tables(K1FShared& s, const MelTables& 
 __device__ __forceinline__ void mel16(const float* P, const K1FShared& ts, const float* dct, const MelTables& t, int n_pieces,
                                       float* pr, float* pf, float* mel, int l16, bool active, float* __restrict__ out) {
     float tot = 0.f;
+    // consecutive lanes own consecutive 8-bin pieces (stride 8 words = 4 bank groups): rotating the walk
+    // by (lane / 4) inside a piece, and by 4 more in the second half-warp, keeps 32 lanes on 32 banks
+    const int rot = ((l16 >> 2) + ((threadIdx.x & 16) >> 2)) & 7;
     for (int p = l16; p < n_pieces; p += 16) {
         const int pc = ts.piece[p];
         const int start = pc & 0xffff, len = pc >> 16;
         float r = 0.f, f = 0.f;
 #pragma unroll
-        for (int i = 0; i < K1F_PIECE_LEN; ++i) {
+        for (int i0 = 0; i0 < K1F_PIECE_LEN; ++i0) {
+            const int i = (i0 + rot) & 7;
             if (i < len) {
                 const float pw = P[start + i];
                 const float2 w = ts.w[start + i];
