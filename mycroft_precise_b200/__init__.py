@@ -16,5 +16,6 @@ from .core import PreciseB200, PBError, lib_path                 # noqa: F401
 from .runner import B200Runner, B200Listener, B200Engine, Engine, TriggerDetector  # noqa: F401
 from .batch import StreamBatch                                    # noqa: F401
 from .model_io import load_weights, save_weights, GruModel        # noqa: F401
+from . import offline                                             # noqa: F401
 
 __version__ = '0.1.0'

@@ -44,5 +44,8 @@ def load_weights(path: str) -> GruModel:
         return GruModel(z['kernel'], z['recurrent'], z['bias'], z['dense_w'], z['dense_b'],
                         str(z['activation']) if 'activation' in z else 'linear',
                         str(z['recurrent_activation']) if 'recurrent_activation' in z else 'hard_sigmoid')
-    raise ValueError('File extension of ' + path + " must be: ['.npz'] "
-                     '(.net / .pb import is not implemented yet)')
+    if path.endswith('.pb'):
+        from .pb_import import load_pb
+        return load_pb(path)
+    raise ValueError('File extension of ' + path + " must be: ['.npz', '.pb'] "
+                     '(Keras .net / HDF5 import is not implemented: convert with precise-convert)')

@@ -68,8 +68,8 @@ def _resolve_model(model):
     if isinstance(model, GruModel):
         return model, None
     ext = splitext(model)[-1]
-    if ext not in ('.npz',):
-        raise ValueError('File extension of ' + model + " must be: ['.npz']")
+    if ext not in ('.npz', '.pb'):
+        raise ValueError('File extension of ' + model + " must be: ['.npz', '.pb']")
     return load_weights(model), load_params(model)
 
 

@@ -1,0 +1,72 @@
+"""CPU: weight containers and the TensorFlow-free GraphDef (.pb) importer."""
+import json
+import os
+import struct
+
+import numpy as np
+import pytest
+
+from mycroft_precise_b200 import GruModel, ListenerParams, Vectorizer, load_params, load_weights, save_weights
+from mycroft_precise_b200.params import save_params
+
+
+def _vi(n):
+    out = b''
+    while True:
+        b = n & 0x7f
+        n >>= 7
+        out += bytes([b | (0x80 if n else 0)])
+        if not n:
+            return out
+
+
+def _ld(fno, payload):
+    return _vi(fno << 3 | 2) + _vi(len(payload)) + payload
+
+
+def _const_node(name, arr, as_content=True):
+    shape = b''.join(_ld(2, _vi(1 << 3) + _vi(d)) for d in arr.shape)
+    tensor = _vi(1 << 3) + _vi(1) + _ld(2, shape)
+    if as_content:
+        tensor += _ld(4, arr.astype('<f4').tobytes())
+    else:
+        tensor += _ld(5, arr.astype('<f4').tobytes())          # packed float_val
+    attr_val = _ld(8, tensor)
+    attr = _ld(1, b'value') + _ld(2, attr_val)
+    dtype_attr = _ld(1, b'dtype') + _ld(2, _vi(6 << 3) + _vi(1))
+    return _ld(1, _ld(1, name.encode()) + _ld(2, b'Const') + _ld(5, dtype_attr) + _ld(5, attr))
+
+
+def test_pb_import_roundtrip(tmp_path):
+    m = GruModel.random(13, 20, seed=5, scale=0.2)
+    other = _ld(1, _ld(1, b'import/net_input') + _ld(2, b'Placeholder'))
+    blob = (other + _const_node('net/kernel', m.kernel) + _const_node('net/recurrent_kernel', m.recurrent, as_content=False)
+            + _const_node('net/bias', m.bias) + _const_node('dense_1/kernel', m.dense_w.reshape(20, 1))
+            + _const_node('dense_1/bias', np.float32([m.dense_b]))
+            + _ld(1, _ld(1, b'net/while/add/y') + _ld(2, b'Const')))
+    p = tmp_path / 'model.pb'
+    p.write_bytes(blob)
+    g = load_weights(str(p))
+    assert g.hidden == 20 and g.feature_size == 13
+    for a, b in ((g.kernel, m.kernel), (g.recurrent, m.recurrent), (g.bias, m.bias), (g.dense_w, m.dense_w)):
+        assert np.array_equal(a, b)
+    assert g.dense_b == pytest.approx(m.dense_b)
+
+
+def test_npz_roundtrip_and_params_file(tmp_path):
+    m = GruModel.random(26, 32, seed=1)
+    path = str(tmp_path / 'w.npz')
+    save_weights(path, m)
+    g = load_weights(path)
+    assert np.array_equal(g.recurrent, m.recurrent) and g.activation == 'linear'
+    pr = ListenerParams(n_mfcc=13, use_delta=True, threshold_config=((5, 3),), threshold_center=0.3)
+    save_params(path, pr)
+    q = load_params(path)
+    assert q.to_dict() == pr.to_dict() and q.feature_size == 26
+    # a .params file written before the 'vectorizer' field existed selects speechpy (params.py:147)
+    d = pr.to_dict(); d.pop('vectorizer')
+    json.dump(d, open(path + '.params', 'w'))
+    assert load_params(path).vectorizer == Vectorizer.speechpy_mfccs
+    assert load_params(str(tmp_path / 'missing.npz')).to_dict() == ListenerParams().to_dict()
+    with pytest.raises(ValueError):
+        load_weights(str(tmp_path / 'model.net'))
