@@ -88,11 +88,29 @@ def _cpu_worker(args):
     return n_streams * ticks, time.perf_counter() - t0, fired
 
 
+def usable_cores():
+    """Host cores this process may actually use: affinity mask capped by the cgroup CPU quota."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1)
+    try:
+        q, per = open('/sys/fs/cgroup/cpu.max').read().split()
+        if q != 'max':
+            n = max(1, min(n, int(float(q) / float(per) + 0.5)))
+    except Exception:
+        try:
+            q = int(open('/sys/fs/cgroup/cpu/cpu.cfs_quota_us').read())
+            per = int(open('/sys/fs/cgroup/cpu/cpu.cfs_period_us').read())
+            if q > 0:
+                n = max(1, min(n, int(q / per + 0.5)))
+        except Exception:
+            pass
+    return n
+
+
 def cpu_port_rate(ticks=3000, warm=50, streams_per_proc=1, procs=None):
     """The oracle port (numpy restatement of Listener.update + TriggerDetector.update) on the host
     cores, one stream per worker process as in the reference (one Listener per process)."""
     import multiprocessing as mp
-    procs = procs or os.cpu_count() or 1
+    procs = procs or usable_cores()
     ctx = mp.get_context('fork')
     with ctx.Pool(procs) as pool:
         res = pool.map(_cpu_worker, [(1000 + i, streams_per_proc, ticks, warm) for i in range(procs)])
@@ -100,6 +118,24 @@ def cpu_port_rate(ticks=3000, warm=50, streams_per_proc=1, procs=None):
     wall = max(r[1] for r in res)
     return updates / wall, procs, '%d worker processes x %d stream x %d ticks of 1024 samples (after %d warm-up ticks), numpy oracle port, 1 BLAS thread per worker' % (
         procs, streams_per_proc, ticks, warm)
+
+
+def cpu_latency(calls=600, warm=50):
+    """p50/p99 of one oracle Listener.update + TriggerDetector.update (batch 1, one core), microseconds."""
+    from oracle.gru import GruWeights
+    from oracle.listener import OracleListener
+    from oracle.trigger import OracleTrigger
+    w = GruWeights.random(13, 20, seed=0, scale=0.1)
+    pcm = synth_pcm(1, (calls + warm) * CHUNK, 4321)
+    lis, det = OracleListener(w), OracleTrigger(2 * CHUNK)
+    ts = []
+    for k in range(calls + warm):
+        c = pcm[0, k * CHUNK:(k + 1) * CHUNK].astype(np.float32) / 32768.0
+        t0 = time.perf_counter()
+        det.update(lis.update(c))
+        ts.append(time.perf_counter() - t0)
+    ts = np.array(ts[warm:]) * 1e6
+    return float(np.percentile(ts, 50)), float(np.percentile(ts, 99))
 
 
 def run_reference(args, rank):
@@ -136,7 +172,7 @@ class ClockSampler:
         self.f = tempfile.NamedTemporaryFile('w+', suffix='.csv', delete=False)
         self.p = None
         try:
-            self.p = subprocess.Popen(['nvidia-smi', '-i', str(gpu_index), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits', '-lms', '100'],
+            self.p = subprocess.Popen(['nvidia-smi', '-i', str(gpu_index), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits', '-lms', '20'],
                                       stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
@@ -178,8 +214,10 @@ def run_b200(args):
     from mycroft_precise_b200.dist import init_from_env, DetectionCounter
 
     cpu = None
+    cpu_lat = None
     if int(os.environ.get('WORLD_SIZE', '1')) == 1 and not args.no_cpu_baseline:
         cpu = cpu_port_rate()                  # before CUDA is initialised in this process (fork safety)
+        cpu_lat = cpu_latency() if args.latency else None
     rank, local, world = init_from_env()
     if world != args.gpus and rank == 0:
         print('note: WORLD_SIZE=%d, --gpus=%d' % (world, args.gpus), file=sys.stderr)
@@ -211,11 +249,11 @@ def run_b200(args):
             counter.all_reduce()
 
     # ---- value: inputs resident in HBM
+    sampler = ClockSampler(local) if rank == 0 else None     # samples from here to the end of the e2e loop
     for t in range(W):
         step(t)
     barrier()
     core.profile(True)
-    sampler = ClockSampler(local) if rank == 0 else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     flush_ms = 0.0
     if flush is not None:                       # cost of the flush alone, subtracted below
@@ -234,7 +272,6 @@ def run_b200(args):
     ms = e0.elapsed_time(e1) - flush_ms
     kms, klaunch = core.profile_read()
     core.profile(False)
-    clocks = sampler.stop() if sampler else None
     tmax = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -277,6 +314,7 @@ def run_b200(args):
     finally:
         for p in pins:
             pinned_free(p)
+    clocks = sampler.stop() if sampler else None
 
     # ---- configs[1]: 1k streams, explicit L2 flush between steps
     small = None
@@ -297,6 +335,27 @@ def run_b200(args):
         small = {'workload': 'configs[1]: 1000 streams, GRU 20, 1 GPU', 'ms_per_step': per, 'value': S2 / (per * 1e-3),
                  'unit': 'stream-updates/s', 'l2': 'flushed (256 MB write) before every step'}
         sb2.core.close()
+
+    # ---- configs[4]: latency mode, batch = 1: one Engine.get_prediction-sized call at a time
+    lat = None
+    if rank == 0 and args.latency:
+        sb1 = StreamBatch(model, 1, chunk_samples=CHUNK, device=local)
+        one, p1 = pinned_empty((1, CHUNK), np.int16)
+        c1, p2 = pinned_empty((1,), np.float64)
+        src = synth_pcm(1, CHUNK * 64, 777)
+        ts = []
+        for k in range(2200):
+            one[0] = src[0, (k % 64) * CHUNK:(k % 64 + 1) * CHUNK]
+            t0 = time.perf_counter()
+            sb1.update_host(one, c1)                        # H2D 2 KB -> K1 -> K2/K3 -> D2H 8 B, host-synchronous
+            ts.append(time.perf_counter() - t0)
+        ts = np.array(ts[200:]) * 1e6
+        lat = {'workload': 'configs[4]: batch 1, window->decision through pb_update_host (pinned 2 KB in, 8 B out)',
+               'p50_us': float(np.percentile(ts, 50)), 'p99_us': float(np.percentile(ts, 99)), 'calls': int(len(ts))}
+        if cpu_lat:
+            lat.update(cpu_p50_us=cpu_lat[0], cpu_p99_us=cpu_lat[1], cpu='oracle port, 1 core')
+        pinned_free(p1); pinned_free(p2)
+        sb1.core.close()
 
     if world > 1:
         dist.barrier()
@@ -340,6 +399,7 @@ def run_b200(args):
         'cpu_baseline': ({'value': cpu[0], 'unit': 'stream-updates/s', 'cores': cpu[1], 'kind': 'port', 'sample': cpu[2]} if cpu else None),
         'clocks': clocks,
         'small_batch': small,
+        'latency': lat,
     }
     print(json.dumps(line))
     if world > 1:
@@ -356,6 +416,7 @@ def main():
     ap.add_argument('--ticks-resident', type=int, default=8)
     ap.add_argument('--no-small-batch', dest='small_batch', action='store_false')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-latency', dest='latency', action='store_false')
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

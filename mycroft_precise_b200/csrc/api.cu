@@ -40,6 +40,7 @@ static int fail(int code, const char* fmt, ...) {
 
 constexpr int N_PROFILE_SLOTS = 4;
 constexpr int PROFILE_POOL = 2048;
+constexpr int K2_WARP_PATH_MAX = 8192;       // streams: below this the warp-per-stream GRU kernel wins (latency-bound regime)
 constexpr int HOST_PIPE = 3;                 // internal streams of pb_update_host
 constexpr int64_t HOST_SUB_BATCH = 16384;    // streams per pipelined sub-batch (32 MiB of PCM at 1024 samples)
 
@@ -79,6 +80,7 @@ struct pb_handle {
     float bd = 0.f;
     // host pipeline
     cudaStream_t pipe[HOST_PIPE] = {nullptr, nullptr, nullptr};
+    cudaEvent_t pipe_ev[HOST_PIPE] = {nullptr, nullptr, nullptr};
     int16_t* d_stage_pcm[HOST_PIPE] = {nullptr, nullptr, nullptr};
     int* d_stage_ids[HOST_PIPE] = {nullptr, nullptr, nullptr};
     float* d_stage_raw[HOST_PIPE] = {nullptr, nullptr, nullptr};
@@ -214,6 +216,7 @@ PB_API void pb_destroy(pb_handle* h) {
         cudaFree(h->d_stage_pcm[i]); cudaFree(h->d_stage_ids[i]); cudaFree(h->d_stage_raw[i]);
         cudaFree(h->d_stage_conf[i]); cudaFree(h->d_stage_fired[i]);
         if (h->pipe[i]) cudaStreamDestroy(h->pipe[i]);
+        if (h->pipe_ev[i]) cudaEventDestroy(h->pipe_ev[i]);
     }
     for (auto& p : h->prof)
         for (auto e : p.ev) cudaEventDestroy(e);
@@ -524,7 +527,11 @@ PB_API int pb_mfcc_f32(pb_handle* h, const float* d_audio, int64_t n_streams, in
 
 static int launch_gru(pb_handle* h, const K2In& in, bool ring, int64_t n, const DecodeParams& dp, const K2Out& o, cudaStream_t s) {
     ProfScope ps(h, 1, s);
-    if (h->small_path) {
+    if (h->small_path && n <= K2_WARP_PATH_MAX) {                 // latency path: a warp per stream
+        const int grid = (int)((n + 3) / 4);
+        if (ring) gru_warp_kernel<20, 13, true><<<grid, 128, 0, s>>>(h->w_small, in, n, dp, o);
+        else gru_warp_kernel<20, 13, false><<<grid, 128, 0, s>>>(h->w_small, in, n, dp, o);
+    } else if (h->small_path) {
         const int per_cta = K2_SMALL_THREADS * K2_NS;
         const int grid = (int)((n + per_cta - 1) / per_cta);
         if (ring) gru_small_kernel<20, 13, true><<<grid, K2_SMALL_THREADS, 0, s>>>(h->w_small, in, n, dp, o);
@@ -585,9 +592,12 @@ static int launch_stream_mfcc(pb_handle* h, const int16_t* d_pcm, const int32_t*
     const float inv = 1.0f / 32768.0f, scale = inv * inv / (float)h->cfg.n_fft;
     ProfScope ps(h, 0, s);
     if (h->fast_ok && h->cfg.chunk_samples % 8 == 0 && (uintptr_t)d_pcm % 16 == 0 && !h->force_generic) {
-        const int64_t tilesf = (n + K1F_STREAMS_PER_WARP - 1) / K1F_STREAMS_PER_WARP;
+        // streams per warp tile: 16 at scale; fewer when the batch cannot fill the machine's warps
+        const int64_t warps_total = (int64_t)h->sm_count * 4 * K1F_WARPS;
+        const int spw = (int)std::max<int64_t>(1, std::min<int64_t>(K1F_STREAMS_PER_WARP, (n + warps_total - 1) / warps_total));
+        const int64_t tilesf = (n + spw - 1) / spw;
         const int gridf = (int)std::min<int64_t>((tilesf + K1F_WARPS - 1) / K1F_WARPS, (int64_t)h->sm_count * 4);
-        mfcc_fast_stream_kernel<<<gridf, K1F_THREADS, h->k1_fast_smem, s>>>(d_pcm, d_ids, (int)n, h->cfg.chunk_samples, h->cfg.hop_samples, scale,
+        mfcc_fast_stream_kernel<<<gridf, K1F_THREADS, h->k1_fast_smem, s>>>(d_pcm, d_ids, (int)n, h->cfg.chunk_samples, h->cfg.hop_samples, spw, scale,
                                                                             mel_tables(h), fast_tables(h), h->st);
     } else if (pairs)
         mfcc_stream_kernel<true><<<grid, K1_THREADS, h->k1_stream_smem, s>>>(d_pcm, d_ids, (int)n, h->cfg.chunk_samples, h->cfg.hop_samples, h->used, scale, mel_tables(h), h->st);
@@ -691,6 +701,7 @@ static int ensure_pipe(pb_handle* h) {
     const int64_t sb = std::min<int64_t>(HOST_SUB_BATCH, h->cfg.max_streams);
     for (int i = 0; i < HOST_PIPE; ++i) {
         CK(cudaStreamCreateWithFlags(&h->pipe[i], cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&h->pipe_ev[i], cudaEventDisableTiming));
         CK(cudaMalloc((void**)&h->d_stage_pcm[i], sb * h->cfg.chunk_samples * sizeof(int16_t)));
         CK(cudaMalloc((void**)&h->d_stage_ids[i], sb * sizeof(int)));
         CK(cudaMalloc((void**)&h->d_stage_raw[i], sb * sizeof(float)));
@@ -718,8 +729,14 @@ PB_API int pb_update_host(pb_handle* h, const int16_t* h_pcm, const int32_t* h_i
     if (rc != PB_OK) return rc;
     const int64_t sb = std::min<int64_t>(HOST_SUB_BATCH, h->cfg.max_streams);
     const int chunk = h->cfg.chunk_samples;
+    // the counter is zeroed on pipe 0; the other pipes wait for that, pipe 0 waits for them at the end,
+    // so the whole tick costs one host synchronisation
     CK(cudaMemsetAsync(h->d_count, 0, sizeof(unsigned long long), h->pipe[0]));
-    CK(cudaStreamSynchronize(h->pipe[0]));
+    const int used_pipes = (int)std::min<int64_t>(HOST_PIPE, (n + sb - 1) / sb);
+    if (used_pipes > 1) {
+        CK(cudaEventRecord(h->pipe_ev[0], h->pipe[0]));
+        for (int i = 1; i < used_pipes; ++i) CK(cudaStreamWaitEvent(h->pipe[i], h->pipe_ev[0], 0));
+    }
     int p = 0;
     for (int64_t off = 0; off < n; off += sb, p = (p + 1) % HOST_PIPE) {
         const int64_t m = std::min(sb, n - off);
@@ -734,8 +751,12 @@ PB_API int pb_update_host(pb_handle* h, const int16_t* h_pcm, const int32_t* h_i
         if (h_raw) CK(cudaMemcpyAsync(h_raw + off, h->d_stage_raw[p], m * sizeof(float), cudaMemcpyDeviceToHost, s));
         if (h_fired) CK(cudaMemcpyAsync(h_fired + off, h->d_stage_fired[p], m * sizeof(uint8_t), cudaMemcpyDeviceToHost, s));
     }
-    for (int i = 0; i < HOST_PIPE; ++i) CK(cudaStreamSynchronize(h->pipe[i]));
-    CK(cudaMemcpy(h->h_count_pinned, h->d_count, sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    for (int i = 1; i < used_pipes; ++i) {
+        CK(cudaEventRecord(h->pipe_ev[i], h->pipe[i]));
+        CK(cudaStreamWaitEvent(h->pipe[0], h->pipe_ev[i], 0));
+    }
+    CK(cudaMemcpyAsync(h->h_count_pinned, h->d_count, sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->pipe[0]));
+    CK(cudaStreamSynchronize(h->pipe[0]));
     if (h_count) *h_count = *h->h_count_pinned;
     return PB_OK;
 }

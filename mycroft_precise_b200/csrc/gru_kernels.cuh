@@ -257,6 +257,69 @@ gru_small_kernel(const __grid_constant__ GruSmallW<H, F> P, K2In in, long long n
 }
 
 // ------------------------------------------------------------------------------------------------
+// Latency variant for small batches (BASELINE configs[1] and [4]): one WARP per stream.  Lane l < H owns
+// hidden unit l for all three gates with its 3 x (F + H) weights in registers; h and r*h are exchanged
+// with warp shuffles, so a step is ~2 x (H shuffles + a (F+H)-long FMA chain split 4 ways) instead of a
+// thread walking all 3H x (F+H) products serially.
+template <int H, int F, bool RING>
+__global__ void __launch_bounds__(128)
+gru_warp_kernel(const __grid_constant__ GruSmallW<H, F> P, K2In in, long long n, DecodeParams dp, K2Out out) {
+    static_assert(H <= 32, "one lane per hidden unit");
+    const int lane = threadIdx.x & 31;
+    const long long i = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (i >= n) return;                                   // whole warp exits together
+    const int u = lane < H ? lane : 0;
+    float wz[F + H], wr[F + H], wh[F + H];
+#pragma unroll
+    for (int k = 0; k < F; ++k) { wz[k] = P.W[k][u]; wr[k] = P.W[k][H + u]; wh[k] = P.W[k][2 * H + u]; }
+#pragma unroll
+    for (int k = 0; k < H; ++k) { wz[F + k] = P.U[k][u]; wr[F + k] = P.U[k][H + u]; wh[F + k] = P.U[k][2 * H + u]; }
+    const float bz = P.b[u], br = P.b[H + u], bh = P.b[2 * H + u];
+    int sid = 0;
+    long long released = 0;
+    if (RING) {
+        sid = in.ids ? in.ids[i] : (int)i;
+        const long long ns = in.n_samples[sid];
+        released = ns >= in.window ? (ns - in.window) / in.hop + 1 : 0;
+    }
+    float h = 0.f;
+#pragma unroll 1
+    for (int t = 0; t < in.T; ++t) {
+        float x[F];
+        const float* row = RING ? ring_row(in, sid, released, t) : in.inputs + (i * in.T + t) * F;
+#pragma unroll
+        for (int f = 0; f < F; ++f) x[f] = row ? __ldg(row + f) : 0.f;          // same address in every lane: broadcast
+        float az[4] = {bz, 0.f, 0.f, 0.f}, ar[4] = {br, 0.f, 0.f, 0.f}, ah[4] = {bh, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int f = 0; f < F; ++f) {
+            az[f & 3] = fmaf(x[f], wz[f], az[f & 3]);
+            ar[f & 3] = fmaf(x[f], wr[f], ar[f & 3]);
+            ah[f & 3] = fmaf(x[f], wh[f], ah[f & 3]);
+        }
+#pragma unroll
+        for (int k = 0; k < H; ++k) {
+            const float hk = __shfl_sync(0xffffffffu, h, k);
+            az[k & 3] = fmaf(hk, wz[F + k], az[k & 3]);
+            ar[k & 3] = fmaf(hk, wr[F + k], ar[k & 3]);
+        }
+        const float z = hard_sigmoid((az[0] + az[1]) + (az[2] + az[3]));
+        const float rh = hard_sigmoid((ar[0] + ar[1]) + (ar[2] + ar[3])) * h;
+#pragma unroll
+        for (int k = 0; k < H; ++k) {
+            const float v = __shfl_sync(0xffffffffu, rh, k);
+            ah[k & 3] = fmaf(v, wh[F + k], ah[k & 3]);
+        }
+        const float hh = (ah[0] + ah[1]) + (ah[2] + ah[3]);
+        h = z * h + (1.f - z) * hh;
+    }
+    float part = lane < H ? h * P.wd[u] : 0.f;
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
+    // lane 0 finishes; other lanes take part in the ballot with valid = false
+    epilogue(part + P.bd, lane == 0, i, sid, dp, out);
+}
+
+// ------------------------------------------------------------------------------------------------
 // Generic tiled kernel.  wcat = [kernel; recurrent] as one [(F_in + H)][3H] row-major matrix.
 constexpr int K2_TILE_THREADS = 256;
 constexpr int K2_TILE_STREAMS = 64;     // 8 warps x 8 streams

@@ -208,7 +208,7 @@ mfcc_fast_batch_kernel(const int16_t* __restrict__ pcm, long long samples_per_st
 // ------------------------------------------------------------------------------------------------
 // Stateful tick (pb_update / pb_update_vectors on the aligned geometry): a warp owns 16 streams.
 __global__ void __launch_bounds__(K1F_THREADS, 4)
-mfcc_fast_stream_kernel(const int16_t* __restrict__ pcm, const int* __restrict__ ids, int n, int chunk, int hop,
+mfcc_fast_stream_kernel(const int16_t* __restrict__ pcm, const int* __restrict__ ids, int n, int chunk, int hop, int spw,
                         float scale, MelTables tab, FastTables ft, StreamState st) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     K1FShared& ts = *reinterpret_cast<K1FShared*>(smem_raw);
@@ -223,25 +223,26 @@ mfcc_fast_stream_kernel(const int16_t* __restrict__ pcm, const int* __restrict__
     __syncthreads();
 
     constexpr int used = 512;
-    const int n_tiles = (n + K1F_STREAMS_PER_WARP - 1) / K1F_STREAMS_PER_WARP;
+    // spw = streams per warp tile (<= K1F_STREAMS_PER_WARP): small batches spread over more warps
+    const int n_tiles = (n + spw - 1) / spw;
     const int gwarp = blockIdx.x * K1F_WARPS + warp, nwarps = gridDim.x * K1F_WARPS;
     uint32_t uses0 = 0, uses1 = 0;                          // completed uses of each staging buffer (mbarrier phase)
     for (int tile = gwarp; tile < n_tiles; tile += nwarps) {
-        const int base = tile * K1F_STREAMS_PER_WARP;
-        // ---- bookkeeping: lane i < 16 <-> stream base + i
+        const int base = tile * spw;
+        // ---- bookkeeping: lane i < spw <-> stream base + i
         int cnt = 0;
         {
             const int i = base + lane;
             int sid = -1;
             long long n0 = 0, c0 = 0, ts0 = 0;
-            if (lane < K1F_STREAMS_PER_WARP && i < n) {
+            if (lane < spw && i < n) {
                 sid = ids ? ids[i] : i;
                 n0 = st.n_samples[sid];
                 c0 = frames_ready(n0, used, hop);
                 cnt = (int)(frames_ready(n0 + chunk, used, hop) - c0);
                 ts0 = c0 * hop < n0 ? c0 * hop : n0;
             }
-            if (lane < K1F_STREAMS_PER_WARP) {
+            if (lane < spw) {
                 ws.st_id[lane] = sid; ws.st_n0[lane] = n0; ws.st_ts0[lane] = ts0; ws.st_cnt[lane] = cnt; ws.st_c0[lane] = c0;
             }
         }
@@ -287,7 +288,7 @@ mfcc_fast_stream_kernel(const int16_t* __restrict__ pcm, const int* __restrict__
         }
         // ---- tail + sample counter: the warp walks its streams; every old-tail read of this tile is complete
         // (the bulk copies that read it were waited for above)
-        for (int t = 0; t < K1F_STREAMS_PER_WARP; ++t) {
+        for (int t = 0; t < spw; ++t) {
             const int sid = ws.st_id[t];
             if (sid < 0) continue;
             const long long n0 = ws.st_n0[t], n1 = n0 + chunk, ts0 = ws.st_ts0[t];
