@@ -191,6 +191,9 @@ int pb_set_cdf(pb_handle* h, const double* h_cd, int64_t len);
 /* Test hook: route the aligned default geometry through the generic (any-alignment) MFCC kernels
  * instead of the warp-autonomous fast kernels, so both implementations are covered by parity tests. */
 int pb_debug_force_generic(pb_handle* h, int on);
+/* Test hook for the default network (H=20, F=13): 0 = automatic choice (warp-per-stream kernel for small
+ * batches, tensor-core scan otherwise), 1 = CUDA-core thread-per-stream kernel, 2 = tensor-core kernel. */
+int pb_debug_gru_mode(pb_handle* h, int mode);
 
 const char* pb_last_error(void);
 int pb_abi_version(void);

@@ -62,6 +62,7 @@ SYMBOLS = {
     'pb_get_cdf': (_I64, [_VP, _VP, _I64, C.POINTER(_I32), C.POINTER(_I32)]),
     'pb_set_cdf': (C.c_int, [_VP, _VP, _I64]),
     'pb_debug_force_generic': (C.c_int, [_VP, C.c_int]),
+    'pb_debug_gru_mode': (C.c_int, [_VP, C.c_int]),
     'pb_last_error': (C.c_char_p, []),
     'pb_abi_version': (C.c_int, []),
     'pb_build_info': (C.c_char_p, []),
@@ -297,6 +298,9 @@ class PreciseB200:
         check(self.lib.pb_update_host(self._h, vp(pcm_np), vp(ids_np), n, vp(raw_np), vp(conf_np), vp(fired_np),
                                       C.cast(C.byref(cnt), C.c_void_p)))
         return int(cnt.value)
+
+    def gru_mode(self, mode):
+        check(self.lib.pb_debug_gru_mode(self._h, int(mode)))
 
     def force_generic(self, on=True):
         check(self.lib.pb_debug_force_generic(self._h, int(on)))

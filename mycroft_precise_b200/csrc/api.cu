@@ -77,6 +77,9 @@ struct pb_handle {
     bool small_path = false;
     GruSmallW<20, 13> w_small;
     float *d_wcat = nullptr, *d_bias = nullptr, *d_wd = nullptr;
+    float4* d_bfrag = nullptr;       // tensor-core GRU: pre-split, fragment-ordered weights
+    float *d_mma_bias = nullptr, *d_mma_wd = nullptr;
+    int gru_mode = 0;                // 0 = auto, 1 = force CUDA-core small kernel, 2 = force tensor-core kernel
     float bd = 0.f;
     // host pipeline
     cudaStream_t pipe[HOST_PIPE] = {nullptr, nullptr, nullptr};
@@ -211,6 +214,7 @@ PB_API void pb_destroy(pb_handle* h) {
     cudaFree(h->d_tw_stage); cudaFree(h->d_tw_post); cudaFree(h->d_cd); cudaFree(h->d_piece); cudaFree(h->d_seg_first);
     cudaFree(h->st.n_samples); cudaFree(h->st.tail); cudaFree(h->st.ring); cudaFree(h->st.trig);
     cudaFree(h->d_wcat); cudaFree(h->d_bias); cudaFree(h->d_wd); cudaFree(h->d_count);
+    cudaFree(h->d_bfrag); cudaFree(h->d_mma_bias); cudaFree(h->d_mma_wd);
     if (h->h_count_pinned) cudaFreeHost(h->h_count_pinned);
     for (int i = 0; i < HOST_PIPE; ++i) {
         cudaFree(h->d_stage_pcm[i]); cudaFree(h->d_stage_ids[i]); cudaFree(h->d_stage_raw[i]);
@@ -392,6 +396,37 @@ PB_API int pb_load_weights(pb_handle* h, const float* kernel, const float* recur
     h->small_path = (H == 20 && F == 13 && !h->cfg.use_delta && h->cfg.activation == PB_ACT_LINEAR &&
                      h->cfg.recurrent_activation == PB_RACT_HARD_SIGMOID);
     if (h->small_path) {
+        // tensor-core fragments (gru_mma_kernel): logical k slot (kt, t, j) -> input 8 kt + 2 t + j
+        // (x feature for kt < 2, hidden unit 8 (kt - 2) + 2 t + j otherwise); column (nt, g) -> gate nt / 3,
+        // unit 8 (nt % 3) + g.  Values are split into TF32 hi / lo parts (round to nearest, ties away).
+        auto tf32 = [](float x) { uint32_t u; memcpy(&u, &x, 4); u = (u + 0x1000u) & 0xffffe000u; float r; memcpy(&r, &u, 4); return r; };
+        std::vector<float4> bf((size_t)MMA_KT * MMA_NT * 32);
+        for (int kt = 0; kt < MMA_KT; ++kt)
+            for (int nt = 0; nt < MMA_NT; ++nt)
+                for (int lane = 0; lane < 32; ++lane) {
+                    const int g = lane >> 2, t = lane & 3, gate = nt / 3, unit = 8 * (nt % 3) + g;
+                    float b[2];
+                    for (int j = 0; j < 2; ++j) {
+                        const int k = 8 * kt + 2 * t + j;
+                        float v = 0.f;
+                        if (unit < H) {
+                            if (kt < 2) { if (k < F) v = kernel[(size_t)k * H3 + gate * H + unit]; }
+                            else { const int hu = k - 16; if (hu < H) v = recurrent[(size_t)hu * H3 + gate * H + unit]; }
+                        }
+                        b[j] = v;
+                    }
+                    const float b0h = tf32(b[0]), b1h = tf32(b[1]);
+                    bf[((size_t)kt * MMA_NT + nt) * 32 + lane] = make_float4(b0h, b1h, tf32(b[0] - b0h), tf32(b[1] - b1h));
+                }
+        std::vector<float> mb(72, 0.f), mw(24, 0.f);
+        for (int gate = 0; gate < 3; ++gate)
+            for (int u = 0; u < H; ++u) mb[gate * 24 + u] = bias[gate * H + u];
+        for (int u = 0; u < H; ++u) mw[u] = dense_w[u];
+        cudaFree(h->d_bfrag); cudaFree(h->d_mma_bias); cudaFree(h->d_mma_wd);
+        h->d_bfrag = nullptr; h->d_mma_bias = h->d_mma_wd = nullptr;
+        CK(upload(&h->d_bfrag, bf));
+        CK(upload(&h->d_mma_bias, mb));
+        CK(upload(&h->d_mma_wd, mw));
         memcpy(h->w_small.W, kernel, sizeof(h->w_small.W));
         memcpy(h->w_small.U, recurrent, sizeof(h->w_small.U));
         memcpy(h->w_small.b, bias, sizeof(h->w_small.b));
@@ -430,6 +465,8 @@ struct ProfScope {
     }
     ~ProfScope() { if (idx >= 0) cudaEventRecord(h->prof[slot].ev[idx + 1], s); }
 };
+
+PB_API int pb_debug_gru_mode(pb_handle* h, int mode) { if (!h) return fail(PB_ERR_INVALID, "null handle"); h->gru_mode = mode; return PB_OK; }
 
 PB_API int pb_debug_force_generic(pb_handle* h, int on) { if (!h) return fail(PB_ERR_INVALID, "null handle"); h->force_generic = on != 0; return PB_OK; }
 
@@ -527,10 +564,17 @@ PB_API int pb_mfcc_f32(pb_handle* h, const float* d_audio, int64_t n_streams, in
 
 static int launch_gru(pb_handle* h, const K2In& in, bool ring, int64_t n, const DecodeParams& dp, const K2Out& o, cudaStream_t s) {
     ProfScope ps(h, 1, s);
-    if (h->small_path && n <= K2_WARP_PATH_MAX) {                 // latency path: a warp per stream
+    if (h->small_path && n <= K2_WARP_PATH_MAX && h->gru_mode == 0) {                 // latency path: a warp per stream
         const int grid = (int)((n + 3) / 4);
         if (ring) gru_warp_kernel<20, 13, true><<<grid, 128, 0, s>>>(h->w_small, in, n, dp, o);
         else gru_warp_kernel<20, 13, false><<<grid, 128, 0, s>>>(h->w_small, in, n, dp, o);
+    } else if (h->small_path && h->gru_mode != 1) {               // tensor-core scan (mma.sync TF32 x3)
+        GruMmaW w;
+        w.bfrag = h->d_bfrag; w.bias = h->d_mma_bias; w.wd = h->d_mma_wd; w.bd = h->bd;
+        const int per_cta = (MMA_THREADS / 32) * 16 * MMA_MB;
+        const int grid = (int)((n + per_cta - 1) / per_cta);
+        if (ring) gru_mma_kernel<20, 13, true><<<grid, MMA_THREADS, 0, s>>>(w, in, n, dp, o);
+        else gru_mma_kernel<20, 13, false><<<grid, MMA_THREADS, 0, s>>>(w, in, n, dp, o);
     } else if (h->small_path) {
         const int per_cta = K2_SMALL_THREADS * K2_NS;
         const int grid = (int)((n + per_cta - 1) / per_cta);

@@ -320,6 +320,201 @@ gru_warp_kernel(const __grid_constant__ GruSmallW<H, F> P, K2In in, long long n,
 }
 
 // ------------------------------------------------------------------------------------------------
+// Tensor-core variant of the small network (H <= 24, F <= 16): the per-step products [x_t | h] x [W;U]
+// run on the warp-level tensor-core path (mma.sync m16n8k8, TF32 inputs, fp32 accumulate) with the
+// 3xTF32 split (a = a_hi + a_lo, b = b_hi + b_lo; a_lo b_hi + a_hi b_lo + a_hi b_hi) so that the result
+// keeps fp32-level accuracy (parity tolerance 1e-5).  A warp owns 16*MB streams (rows of the A operand);
+// h, z, r*h stay in accumulator-fragment layout in registers for all 29 steps.
+//
+// Contraction-index trick: the k index of an MMA is only a summation label, so the hidden units are
+// assigned to k slots in the order the accumulator fragment already holds them (thread t of a quad owns
+// units 8*tile + 2t, 2t+1).  The weight fragments are permuted once on the host to match; turning h
+// (C layout) into the next step's A operand then needs no shuffle at all.
+constexpr int MMA_KT = 5;            // k tiles: 2 for x (F <= 16), 3 for h (H <= 24)
+constexpr int MMA_NT = 9;            // n tiles: z, r, h gates x 3 tiles of 8 units
+constexpr int MMA_MB = 2;            // row blocks of 16 streams per warp
+constexpr int MMA_THREADS = 128;
+
+struct GruMmaW {
+    const float4* bfrag;             // [MMA_KT][MMA_NT][32 lanes] (b0_hi, b1_hi, b0_lo, b1_lo)
+    const float* bias;               // [3][24] padded per gate
+    const float* wd;                 // [24] padded
+    float bd;
+};
+
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return r;
+}
+
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// d += a * b with the 3xTF32 split; ah/al = hi/lo parts of the A fragment, w = (b0_hi, b1_hi, b0_lo, b1_lo)
+__device__ __forceinline__ void mma3(float (&d)[4], const uint32_t (&ah)[4], const uint32_t (&al)[4], const float4& w) {
+    mma_tf32(d, al, __float_as_uint(w.x), __float_as_uint(w.y));
+    mma_tf32(d, ah, __float_as_uint(w.z), __float_as_uint(w.w));
+    mma_tf32(d, ah, __float_as_uint(w.x), __float_as_uint(w.y));
+}
+
+__device__ __forceinline__ void split_tf32(const float (&v)[4], uint32_t (&hi)[4], uint32_t (&lo)[4]) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        hi[e] = to_tf32(v[e]);
+        lo[e] = to_tf32(v[e] - __uint_as_float(hi[e]));
+    }
+}
+
+template <int H, int F, bool RING>
+__global__ void __launch_bounds__(MMA_THREADS, 3)
+gru_mma_kernel(GruMmaW W, K2In in, long long n, DecodeParams dp, K2Out out) {
+    static_assert(H <= 24 && F <= 16, "tile counts are fixed");
+    __shared__ float4 sB[MMA_KT * MMA_NT * 32];
+    __shared__ float sBias[3 * 24];
+    __shared__ float sWd[24];
+    for (int e = threadIdx.x; e < MMA_KT * MMA_NT * 32; e += blockDim.x) sB[e] = __ldg(W.bfrag + e);
+    for (int e = threadIdx.x; e < 72; e += blockDim.x) sBias[e] = __ldg(W.bias + e);
+    for (int e = threadIdx.x; e < 24; e += blockDim.x) sWd[e] = __ldg(W.wd + e);
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+    const long long base = ((long long)blockIdx.x * (MMA_THREADS / 32) + warp) * (16 * MMA_MB);
+    if (base >= n) return;
+    // rows of this thread: stream (mb, hf) = base + 16 mb + g + 8 hf
+    long long idx[MMA_MB][2];
+    int sid[MMA_MB][2];
+    long long rel[MMA_MB][2];
+    bool ok[MMA_MB][2];
+#pragma unroll
+    for (int mb = 0; mb < MMA_MB; ++mb)
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+            idx[mb][hf] = base + 16 * mb + g + 8 * hf;
+            ok[mb][hf] = idx[mb][hf] < n;
+            sid[mb][hf] = 0; rel[mb][hf] = 0;
+            if (RING && ok[mb][hf]) {
+                sid[mb][hf] = in.ids ? in.ids[idx[mb][hf]] : (int)idx[mb][hf];
+                const long long ns = in.n_samples[sid[mb][hf]];
+                rel[mb][hf] = ns >= in.window ? (ns - in.window) / in.hop + 1 : 0;
+            }
+        }
+    // h in accumulator layout: hreg[mb][tile][e], e = (row g: units 2t, 2t+1; row g+8: units 2t, 2t+1) of tile
+    float hreg[MMA_MB][3][4];
+#pragma unroll
+    for (int mb = 0; mb < MMA_MB; ++mb)
+#pragma unroll
+        for (int nt = 0; nt < 3; ++nt)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) hreg[mb][nt][e] = 0.f;
+
+#pragma unroll 1
+    for (int step = 0; step < in.T; ++step) {
+        // ---- A fragments of x_t: a0 = (row g, k 2t), a1 = (row g+8, k 2t), a2 = (row g, k 2t+1), a3 = (row g+8, k 2t+1)
+        uint32_t xh[MMA_MB][2][4], xl[MMA_MB][2][4];
+#pragma unroll
+        for (int mb = 0; mb < MMA_MB; ++mb) {
+            float xv[2][2][2];                               // [kt][hf][j]
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+                const float* row = nullptr;
+                if (ok[mb][hf]) row = RING ? ring_row(in, sid[mb][hf], rel[mb][hf], step) : in.inputs + (idx[mb][hf] * in.T + step) * F;
+#pragma unroll
+                for (int kt = 0; kt < 2; ++kt)
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        const int f = 8 * kt + 2 * t + j;
+                        xv[kt][hf][j] = (row != nullptr && f < F) ? __ldg(row + f) : 0.f;
+                    }
+            }
+#pragma unroll
+            for (int kt = 0; kt < 2; ++kt) {
+                const float v[4] = {xv[kt][0][0], xv[kt][1][0], xv[kt][0][1], xv[kt][1][1]};
+                split_tf32(v, xh[mb][kt], xl[mb][kt]);
+            }
+        }
+        // ---- accumulators start from the bias (column 2t + j of tile nt)
+        float acc[MMA_MB][MMA_NT][4];
+#pragma unroll
+        for (int nt = 0; nt < MMA_NT; ++nt) {
+            const float b0 = sBias[8 * nt + 2 * t], b1 = sBias[8 * nt + 2 * t + 1];
+#pragma unroll
+            for (int mb = 0; mb < MMA_MB; ++mb) { acc[mb][nt][0] = b0; acc[mb][nt][1] = b1; acc[mb][nt][2] = b0; acc[mb][nt][3] = b1; }
+        }
+        // ---- x part for all three gates
+#pragma unroll
+        for (int kt = 0; kt < 2; ++kt)
+#pragma unroll
+            for (int nt = 0; nt < MMA_NT; ++nt) {
+                const float4 w = sB[(kt * MMA_NT + nt) * 32 + lane];
+#pragma unroll
+                for (int mb = 0; mb < MMA_MB; ++mb) mma3(acc[mb][nt], xh[mb][kt], xl[mb][kt], w);
+            }
+        // ---- h part for z and r
+#pragma unroll
+        for (int kt = 0; kt < 3; ++kt) {
+            uint32_t ah[MMA_MB][4], al[MMA_MB][4];
+#pragma unroll
+            for (int mb = 0; mb < MMA_MB; ++mb) {
+                const float v[4] = {hreg[mb][kt][0], hreg[mb][kt][2], hreg[mb][kt][1], hreg[mb][kt][3]};
+                split_tf32(v, ah[mb], al[mb]);
+            }
+#pragma unroll
+            for (int nt = 0; nt < 6; ++nt) {
+                const float4 w = sB[((2 + kt) * MMA_NT + nt) * 32 + lane];
+#pragma unroll
+                for (int mb = 0; mb < MMA_MB; ++mb) mma3(acc[mb][nt], ah[mb], al[mb], w);
+            }
+        }
+        // ---- gates; r * h becomes the A operand of the candidate product
+#pragma unroll
+        for (int kt = 0; kt < 3; ++kt) {
+            uint32_t ah[MMA_MB][4], al[MMA_MB][4];
+#pragma unroll
+            for (int mb = 0; mb < MMA_MB; ++mb) {
+                float rh[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) rh[e] = hard_sigmoid(acc[mb][3 + kt][e]) * hreg[mb][kt][e];
+                const float v[4] = {rh[0], rh[2], rh[1], rh[3]};
+                split_tf32(v, ah[mb], al[mb]);
+            }
+#pragma unroll
+            for (int nt = 6; nt < 9; ++nt) {
+                const float4 w = sB[((2 + kt) * MMA_NT + nt) * 32 + lane];
+#pragma unroll
+                for (int mb = 0; mb < MMA_MB; ++mb) mma3(acc[mb][nt], ah[mb], al[mb], w);
+            }
+        }
+#pragma unroll
+        for (int mb = 0; mb < MMA_MB; ++mb)
+#pragma unroll
+            for (int nt = 0; nt < 3; ++nt)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float z = hard_sigmoid(acc[mb][nt][e]);
+                    hreg[mb][nt][e] = z * hreg[mb][nt][e] + (1.f - z) * acc[mb][6 + nt][e];      // linear candidate
+                }
+    }
+    // ---- Dense(1): per-thread partial over its 6 units per row, reduced over the quad
+#pragma unroll
+    for (int mb = 0; mb < MMA_MB; ++mb)
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+            float part = 0.f;
+#pragma unroll
+            for (int nt = 0; nt < 3; ++nt) {
+                part = fmaf(hreg[mb][nt][2 * hf], sWd[8 * nt + 2 * t], part);
+                part = fmaf(hreg[mb][nt][2 * hf + 1], sWd[8 * nt + 2 * t + 1], part);
+            }
+            part += __shfl_xor_sync(0xffffffffu, part, 1);
+            part += __shfl_xor_sync(0xffffffffu, part, 2);
+            epilogue(part + W.bd, t == 0 && ok[mb][hf], idx[mb][hf], sid[mb][hf], dp, out);
+        }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Generic tiled kernel.  wcat = [kernel; recurrent] as one [(F_in + H)][3H] row-major matrix.
 constexpr int K2_TILE_THREADS = 256;
 constexpr int K2_TILE_STREAMS = 64;     // 8 warps x 8 streams

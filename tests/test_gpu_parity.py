@@ -192,6 +192,49 @@ def test_predict_small_path(core, scale):
         assert np.median(np.abs(p - p64)) < 1e-5
 
 
+@pytest.mark.parametrize('mode', [0, 1, 2])
+def test_default_network_kernel_variants(core, mode):
+    """warp-per-stream (auto, small n), thread-per-stream CUDA-core (1) and tensor-core 3xTF32 (2) kernels."""
+    w = og.GruWeights.random(13, 20, seed=11, scale=0.1)
+    core.load_weights(w.kernel, w.recurrent, w.bias, w.dense_w, w.dense_b)
+    core.gru_mode(mode)
+    try:
+        for N in (1, 31, 33, 777, 9000):
+            x = (np.random.RandomState(N).randn(N, 29, 13) * 3).astype(np.float32)
+            p, lg = core.predict(cuda(x), want_logit=True)
+            p, lg = p.cpu().numpy(), lg.cpu().numpy()
+            sel = slice(None) if N < 2000 else slice(0, None, 7)
+            p64, l64 = og.gru_forward(w, x[sel], np.float64)
+            err, lerr = np.max(np.abs(p[sel] - p64)), np.max(np.abs(lg[sel] - l64))
+            print('mode', mode, 'N', N, 'prob err %.3g logit err %.3g' % (err, lerr))
+            assert err < 1e-5 and lerr < 5e-5
+    finally:
+        core.gru_mode(0)
+
+
+def test_stream_tick_kernel_variants_agree():
+    m = _mod()
+    S, K, chunk = 300, 34, 1024
+    pcm = noise(S, K * chunk, seed=21)
+    model = m.GruModel.random(13, 20, seed=6, scale=0.1)
+    model.dense_b = 3.0                                   # pushes the confidence over the trigger threshold
+    outs = []
+    for mode in (0, 1, 2):
+        sb = m.StreamBatch(model, S, chunk_samples=chunk)
+        sb.core.gru_mode(mode)
+        raws, fired = [], []
+        for k in range(K):
+            o = sb.update(cuda(pcm[:, k * chunk:(k + 1) * chunk]))
+            raws.append(o['raw'].cpu().numpy().copy()); fired.append(o['fired'].cpu().numpy().copy())
+        outs.append((np.array(raws), np.array(fired), int(sb.count.item())))
+        sb.core.close()
+    for r, f, c in outs[1:]:
+        assert np.max(np.abs(r - outs[0][0])) < 1e-5
+    assert outs[0][2] == outs[0][1].sum() > 0
+    # a conf within rounding of the threshold may flip a trigger between variants; allow a handful
+    assert abs(outs[1][2] - outs[0][2]) <= 3 and abs(outs[2][2] - outs[0][2]) <= 3
+
+
 def _generic_case(pr_kw, H, act='linear', ract='hard_sigmoid', N=200, seed=5):
     m = _mod()
     pr = m.ListenerParams(**pr_kw)
