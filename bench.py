@@ -337,6 +337,35 @@ def run_b200(args):
                  'unit': 'stream-updates/s', 'l2': 'flushed (256 MB write) before every step'}
         sb2.core.close()
 
+    # ---- configs[2]: 100k streams, GRU 128, n_mfcc = n_filt = 40 (tiled GRU kernel)
+    big = None
+    if rank == 0 and args.config3:
+        from mycroft_precise_b200 import ListenerParams
+        pr3 = ListenerParams(n_filt=40, n_mfcc=40)
+        S3 = 100000
+        m3 = GruModel.random(40, 128, seed=1, scale=0.1 / np.sqrt(128 / 20.0))
+        sb3 = StreamBatch(m3, S3, params=pr3, chunk_samples=CHUNK, device=local)
+        tk = [torch.from_numpy(synth_pcm(S3, CHUNK, seed=500 + t)).to(dev) for t in range(4)]
+        for t in range(2):
+            sb3.update(tk[t % 4])
+        torch.cuda.synchronize()
+        sb3.core.profile(True)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        n3 = 6
+        for t in range(n3):
+            sb3.update(tk[(t + 2) % 4])
+        b.record(); torch.cuda.synchronize()
+        kms3, kl3 = sb3.core.profile_read()
+        per = a.elapsed_time(b) / n3
+        flop3 = 2 * (29 * (40 + 128) * 384 + 128)
+        big = {'workload': 'configs[2]: 100000 streams, GRU 128, n_filt = n_mfcc = 40, 1 GPU', 'ms_per_step': per,
+               'value': S3 / (per * 1e-3), 'unit': 'stream-updates/s', 'k1_ms': kms3[0] / max(1, kl3[0]), 'k2_ms': kms3[1] / max(1, kl3[1]),
+               'k2_fp32_frac': S3 * flop3 / (kms3[1] / max(1, kl3[1]) * 1e-3) / 1e12 / FP32_PEAK_TFLOPS,
+               'l2': 'inputs larger than L2 (195 MB of PCM per tick)'}
+        sb3.core.close()
+        del tk
+
     # ---- configs[4]: latency mode, batch = 1: one Engine.get_prediction-sized call at a time
     lat = None
     if rank == 0 and args.latency:
@@ -401,6 +430,7 @@ def run_b200(args):
         'clocks': clocks,
         'small_batch': small,
         'latency': lat,
+        'config3': big,
     }
     print(json.dumps(line))
     if world > 1:
@@ -418,6 +448,7 @@ def main():
     ap.add_argument('--no-small-batch', dest='small_batch', action='store_false')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-latency', dest='latency', action='store_false')
+    ap.add_argument('--no-config3', dest='config3', action='store_false')
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

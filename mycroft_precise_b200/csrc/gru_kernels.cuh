@@ -115,6 +115,29 @@ __device__ __forceinline__ const float* ring_row(const K2In& in, int sid, long l
     return in.ring + ((long long)sid * in.ring_rows + (int)(k % in.ring_rows)) * in.row_stride;
 }
 
+// Incremental form of ring_row for the scan kernels: one 64-bit modulo per stream instead of one per step.
+struct RingCursor {
+    const float* base;     // this stream's ring
+    int slot;              // ring slot of window row 0 (valid once step >= lead)
+    int lead;              // number of leading all-zero rows
+    int rows, stride;
+    __device__ __forceinline__ void init(const K2In& in, int sid, long long released) {
+        const long long first = released - in.T;
+        lead = first < 0 ? (int)(-first < in.T ? -first : in.T) : 0;
+        long long m = first % in.ring_rows;
+        if (m < 0) m += in.ring_rows;
+        slot = (int)m;
+        rows = in.ring_rows; stride = in.row_stride;
+        base = in.ring + (long long)sid * in.ring_rows * in.row_stride;
+    }
+    // row of step t (call with t = 0, 1, 2, ... in order), nullptr for a zero row
+    __device__ __forceinline__ const float* next(int t) {
+        const float* r = t >= lead ? base + slot * stride : nullptr;
+        slot = slot + 1 == rows ? 0 : slot + 1;
+        return r;
+    }
+};
+
 // ------------------------------------------------------------------------------------------------
 template <int H, int F>
 struct GruSmallW {
@@ -181,6 +204,7 @@ gru_small_kernel(const __grid_constant__ GruSmallW<H, F> P, K2In in, long long n
     bool valid[K2_NS];
     int sid[K2_NS];
     long long released[K2_NS];
+    RingCursor cur[K2_NS];
     float h[K2_NS][H];
 #pragma unroll
     for (int s = 0; s < K2_NS; ++s) {
@@ -192,6 +216,7 @@ gru_small_kernel(const __grid_constant__ GruSmallW<H, F> P, K2In in, long long n
             sid[s] = in.ids ? in.ids[i0 + s] : (int)(i0 + s);
             const long long ns = in.n_samples[sid[s]];
             released[s] = ns >= in.window ? (ns - in.window) / in.hop + 1 : 0;
+            cur[s].init(in, sid[s], released[s]);
         }
     }
     if (valid[0]) {
@@ -204,7 +229,7 @@ gru_small_kernel(const __grid_constant__ GruSmallW<H, F> P, K2In in, long long n
                 for (int f = 0; f < F; ++f) x[s][f] = 0.f;
                 if (!valid[s]) continue;
                 if (RING) {
-                    const float* row = ring_row(in, sid[s], released[s], t);
+                    const float* row = cur[s].next(t);
                     if (row != nullptr) {
                         const float4* r4 = reinterpret_cast<const float4*>(row);   // rows: 16-byte aligned, padded to 4k floats
 #pragma unroll
@@ -282,11 +307,13 @@ gru_warp_kernel(const __grid_constant__ GruSmallW<H, F> P, K2In in, long long n,
         const long long ns = in.n_samples[sid];
         released = ns >= in.window ? (ns - in.window) / in.hop + 1 : 0;
     }
+    RingCursor cur;
+    if (RING) cur.init(in, sid, released);
     float h = 0.f;
 #pragma unroll 1
     for (int t = 0; t < in.T; ++t) {
         float x[F];
-        const float* row = RING ? ring_row(in, sid, released, t) : in.inputs + (i * in.T + t) * F;
+        const float* row = RING ? cur.next(t) : in.inputs + (i * in.T + t) * F;
 #pragma unroll
         for (int f = 0; f < F; ++f) x[f] = row ? __ldg(row + f) : 0.f;          // same address in every lane: broadcast
         float az[4] = {bz, 0.f, 0.f, 0.f}, ar[4] = {br, 0.f, 0.f, 0.f}, ah[4] = {bh, 0.f, 0.f, 0.f};
@@ -342,30 +369,40 @@ struct GruMmaW {
     float bd;
 };
 
-__device__ __forceinline__ uint32_t to_tf32(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return r;
-}
-
 __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
     asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                  : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-// d += a * b with the 3xTF32 split; ah/al = hi/lo parts of the A fragment, w = (b0_hi, b1_hi, b0_lo, b1_lo)
-__device__ __forceinline__ void mma3(float (&d)[4], const uint32_t (&ah)[4], const uint32_t (&al)[4], const float4& w) {
-    mma_tf32(d, al, __float_as_uint(w.x), __float_as_uint(w.y));
-    mma_tf32(d, ah, __float_as_uint(w.z), __float_as_uint(w.w));
-    mma_tf32(d, ah, __float_as_uint(w.x), __float_as_uint(w.y));
+// 3xTF32: d += a_lo b_hi + a_hi b_lo + a_hi b_hi for a group of NG n-tiles and MB row blocks.  The three
+// terms are issued as three sweeps over the group so that consecutive MMAs never target the same
+// accumulator (dependent distance NG * MB instructions).
+template <int NG>
+__device__ __forceinline__ void mma3_group(float (*acc)[MMA_NT][4], int nt0, const uint32_t (*ah)[4], const uint32_t (*al)[4],
+                                           const float4 (&w)[NG]) {
+#pragma unroll
+    for (int q = 0; q < NG; ++q)
+#pragma unroll
+        for (int mb = 0; mb < MMA_MB; ++mb) mma_tf32(acc[mb][nt0 + q], al[mb], __float_as_uint(w[q].x), __float_as_uint(w[q].y));
+#pragma unroll
+    for (int q = 0; q < NG; ++q)
+#pragma unroll
+        for (int mb = 0; mb < MMA_MB; ++mb) mma_tf32(acc[mb][nt0 + q], ah[mb], __float_as_uint(w[q].z), __float_as_uint(w[q].w));
+#pragma unroll
+    for (int q = 0; q < NG; ++q)
+#pragma unroll
+        for (int mb = 0; mb < MMA_MB; ++mb) mma_tf32(acc[mb][nt0 + q], ah[mb], __float_as_uint(w[q].x), __float_as_uint(w[q].y));
 }
 
+// hi = a with the 13 low mantissa bits cleared (what the tensor core reads anyway), lo = a - hi (exact in
+// fp32; the tensor core truncates it to TF32 again, leaving a relative error <= 2^-21 per product).
+// One LOP3 + one FADD per element instead of two cvt.rna.tf32 (which issue on the quarter-rate XU pipe).
 __device__ __forceinline__ void split_tf32(const float (&v)[4], uint32_t (&hi)[4], uint32_t (&lo)[4]) {
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-        hi[e] = to_tf32(v[e]);
-        lo[e] = to_tf32(v[e] - __uint_as_float(hi[e]));
+        hi[e] = __float_as_uint(v[e]) & 0xffffe000u;
+        lo[e] = __float_as_uint(v[e] - __uint_as_float(hi[e]));
     }
 }
 
@@ -387,6 +424,7 @@ gru_mma_kernel(GruMmaW W, K2In in, long long n, DecodeParams dp, K2Out out) {
     long long idx[MMA_MB][2];
     int sid[MMA_MB][2];
     long long rel[MMA_MB][2];
+    RingCursor cur[MMA_MB][2];
     bool ok[MMA_MB][2];
 #pragma unroll
     for (int mb = 0; mb < MMA_MB; ++mb)
@@ -399,6 +437,7 @@ gru_mma_kernel(GruMmaW W, K2In in, long long n, DecodeParams dp, K2Out out) {
                 sid[mb][hf] = in.ids ? in.ids[idx[mb][hf]] : (int)idx[mb][hf];
                 const long long ns = in.n_samples[sid[mb][hf]];
                 rel[mb][hf] = ns >= in.window ? (ns - in.window) / in.hop + 1 : 0;
+                cur[mb][hf].init(in, sid[mb][hf], rel[mb][hf]);
             }
         }
     // h in accumulator layout: hreg[mb][tile][e], e = (row g: units 2t, 2t+1; row g+8: units 2t, 2t+1) of tile
@@ -420,7 +459,7 @@ gru_mma_kernel(GruMmaW W, K2In in, long long n, DecodeParams dp, K2Out out) {
 #pragma unroll
             for (int hf = 0; hf < 2; ++hf) {
                 const float* row = nullptr;
-                if (ok[mb][hf]) row = RING ? ring_row(in, sid[mb][hf], rel[mb][hf], step) : in.inputs + (idx[mb][hf] * in.T + step) * F;
+                if (ok[mb][hf]) row = RING ? cur[mb][hf].next(step) : in.inputs + (idx[mb][hf] * in.T + step) * F;
 #pragma unroll
                 for (int kt = 0; kt < 2; ++kt)
 #pragma unroll
@@ -445,13 +484,20 @@ gru_mma_kernel(GruMmaW W, K2In in, long long n, DecodeParams dp, K2Out out) {
         }
         // ---- x part for all three gates
 #pragma unroll
-        for (int kt = 0; kt < 2; ++kt)
+        for (int kt = 0; kt < 2; ++kt) {
+            uint32_t ah[MMA_MB][4], al[MMA_MB][4];
 #pragma unroll
-            for (int nt = 0; nt < MMA_NT; ++nt) {
-                const float4 w = sB[(kt * MMA_NT + nt) * 32 + lane];
+            for (int mb = 0; mb < MMA_MB; ++mb)
 #pragma unroll
-                for (int mb = 0; mb < MMA_MB; ++mb) mma3(acc[mb][nt], xh[mb][kt], xl[mb][kt], w);
+                for (int e = 0; e < 4; ++e) { ah[mb][e] = xh[mb][kt][e]; al[mb][e] = xl[mb][kt][e]; }
+#pragma unroll
+            for (int ng = 0; ng < MMA_NT; ng += 3) {
+                float4 w[3];
+#pragma unroll
+                for (int q = 0; q < 3; ++q) w[q] = sB[(kt * MMA_NT + ng + q) * 32 + lane];
+                mma3_group<3>(acc, ng, ah, al, w);
             }
+        }
         // ---- h part for z and r
 #pragma unroll
         for (int kt = 0; kt < 3; ++kt) {
@@ -462,10 +508,11 @@ gru_mma_kernel(GruMmaW W, K2In in, long long n, DecodeParams dp, K2Out out) {
                 split_tf32(v, ah[mb], al[mb]);
             }
 #pragma unroll
-            for (int nt = 0; nt < 6; ++nt) {
-                const float4 w = sB[((2 + kt) * MMA_NT + nt) * 32 + lane];
+            for (int ng = 0; ng < 6; ng += 3) {
+                float4 w[3];
 #pragma unroll
-                for (int mb = 0; mb < MMA_MB; ++mb) mma3(acc[mb][nt], ah[mb], al[mb], w);
+                for (int q = 0; q < 3; ++q) w[q] = sB[((2 + kt) * MMA_NT + ng + q) * 32 + lane];
+                mma3_group<3>(acc, ng, ah, al, w);
             }
         }
         // ---- gates; r * h becomes the A operand of the candidate product
@@ -480,11 +527,11 @@ gru_mma_kernel(GruMmaW W, K2In in, long long n, DecodeParams dp, K2Out out) {
                 const float v[4] = {rh[0], rh[2], rh[1], rh[3]};
                 split_tf32(v, ah[mb], al[mb]);
             }
+            {
+                float4 w[3];
 #pragma unroll
-            for (int nt = 6; nt < 9; ++nt) {
-                const float4 w = sB[((2 + kt) * MMA_NT + nt) * 32 + lane];
-#pragma unroll
-                for (int mb = 0; mb < MMA_MB; ++mb) mma3(acc[mb][nt], ah[mb], al[mb], w);
+                for (int q = 0; q < 3; ++q) w[q] = sB[((2 + kt) * MMA_NT + 6 + q) * 32 + lane];
+                mma3_group<3>(acc, 6, ah, al, w);
             }
         }
 #pragma unroll
