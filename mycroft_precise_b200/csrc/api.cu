@@ -59,8 +59,10 @@ struct pb_handle {
     size_t k1_batch_smem = 0, k1_stream_smem = 0, k1_fast_smem = 0;
     bool force_generic = false;      // tests: exercise the generic kernels on the aligned geometry
     bool fast_ok = false;            // aligned geometry: warp-autonomous kernels (mfcc_fast.cuh)
-    int n_pieces = 0;
-    int *d_piece = nullptr, *d_seg_first = nullptr;
+    int npl = 0, maxc = 0, nol = 0;
+    float4* d_ptab = nullptr;
+    unsigned char* d_ctab = nullptr;
+    float* d_dct_t = nullptr;
     // host copies of tables
     std::vector<double> fb;        // [n_filt][n_bins]
     std::vector<double> cd;
@@ -211,7 +213,7 @@ PB_API void pb_destroy(pb_handle* h) {
     if (!h) return;
     cudaSetDevice(h->cfg.device);
     cudaFree(h->d_wrise); cudaFree(h->d_wfall); cudaFree(h->d_dct); cudaFree(h->d_grid);
-    cudaFree(h->d_tw_stage); cudaFree(h->d_tw_post); cudaFree(h->d_cd); cudaFree(h->d_piece); cudaFree(h->d_seg_first);
+    cudaFree(h->d_tw_stage); cudaFree(h->d_tw_post); cudaFree(h->d_cd); cudaFree(h->d_ptab); cudaFree(h->d_ctab); cudaFree(h->d_dct_t);
     cudaFree(h->st.n_samples); cudaFree(h->st.tail); cudaFree(h->st.ring); cudaFree(h->st.trig);
     cudaFree(h->d_wcat); cudaFree(h->d_bias); cudaFree(h->d_wd); cudaFree(h->d_count);
     cudaFree(h->d_bfrag); cudaFree(h->d_mma_bias); cudaFree(h->d_mma_wd);
@@ -283,10 +285,38 @@ PB_API int pb_create(const pb_config* cfg, pb_handle** out) {
         seg_first[c.n_filt + 1] = (int)pieces.size();
         add_range(0, std::min(grid[0], h->n_bins));                       // bins outside the grid: total power only
         add_range(grid[c.n_filt + 1], h->n_bins);
-        h->n_pieces = (int)pieces.size();
     }
-    h->fast_ok = c.n_fft == 512 && h->used == 512 && c.hop_samples % 8 == 0 && h->n_pieces <= K1F_MAX_PIECES;
-    h->k1_fast_smem = sizeof(K1FShared) + K1F_WARPS * sizeof(K1FWarp) + (size_t)h->n_out * c.n_filt * sizeof(float);
+    const int n_pieces = (int)pieces.size();
+    h->npl = (n_pieces + 15) / 16;
+    h->nol = (h->n_out + 15) / 16;
+    h->maxc = 1;
+    for (int j = 0; j < c.n_filt; ++j) h->maxc = std::max(h->maxc, seg_first[j + 2] - seg_first[j]);
+    // ptab[q][e][lane]: piece p = lane + 16 q, entry e -> (byte offset of the bin in P, w_rise, w_fall, 0); padding -> zero bin
+    std::vector<float4> ptab((size_t)h->npl * 128);
+    for (int q = 0; q < h->npl; ++q)
+        for (int e = 0; e < 8; ++e)
+            for (int lane = 0; lane < 16; ++lane) {
+                const int pidx = lane + 16 * q;
+                int bin = K1F_ZERO_BIN;
+                float wr = 0.f, wf = 0.f;
+                if (pidx < n_pieces) {
+                    const int start = pieces[pidx] & 0xffff, len = pieces[pidx] >> 16;
+                    if (e < len) { bin = start + e; wr = wrise[bin]; wf = wfall[bin]; }
+                }
+                const int off = bin * 4;
+                float offf; memcpy(&offf, &off, 4);
+                ptab[((size_t)q * 8 + e) * 16 + lane] = make_float4(offf, wr, wf, 0.f);
+            }
+    // ctab[j][c]: partial slots summed into filter j: rise partials of segment j, fall partials (index + 64) of segment j + 1
+    std::vector<unsigned char> ctab((size_t)c.n_filt * h->maxc, 128);
+    for (int j = 0; j < c.n_filt; ++j) {
+        int w = 0;
+        for (int pp = seg_first[j]; pp < seg_first[j + 1]; ++pp) ctab[(size_t)j * h->maxc + w++] = (unsigned char)pp;
+        for (int pp = seg_first[j + 1]; pp < seg_first[j + 2]; ++pp) ctab[(size_t)j * h->maxc + w++] = (unsigned char)(64 + pp);
+    }
+    h->fast_ok = c.n_fft == 512 && h->used == 512 && c.hop_samples % 8 == 0 && n_pieces <= 64 && h->npl <= 4;
+    h->k1_fast_smem = K1F_WARPS * sizeof(K1FWarp) + (size_t)h->npl * 128 * sizeof(float4) +
+                      (size_t)c.n_filt * 16 * h->nol * sizeof(float) + (((size_t)c.n_filt * h->maxc + 15) & ~(size_t)15);
     // DCT-II, norm='ortho' (scipy.fftpack.dct as sonopy.mfcc_spec calls it), first n_out rows
     std::vector<float> dct((size_t)h->n_out * c.n_filt);
     for (int k = 0; k < h->n_out; ++k)
@@ -322,8 +352,14 @@ PB_API int pb_create(const pb_config* cfg, pb_handle** out) {
     CKH(upload(&h->d_tw_stage, tws));
     CKH(upload(&h->d_tw_post, twp));
     CKH(upload(&h->d_cd, h->cd));
-    CKH(upload(&h->d_piece, pieces));
-    CKH(upload(&h->d_seg_first, seg_first));
+    {
+        std::vector<float> dct_t((size_t)c.n_filt * 16 * h->nol, 0.f);
+        for (int k = 0; k < h->n_out; ++k)
+            for (int n = 0; n < c.n_filt; ++n) dct_t[(size_t)n * 16 * h->nol + k] = dct[(size_t)k * c.n_filt + n];
+        CKH(upload(&h->d_dct_t, dct_t));
+    }
+    CKH(upload(&h->d_ptab, ptab));
+    CKH(upload(&h->d_ctab, ctab));
     const size_t S = (size_t)c.max_streams;
     h->st.tail_cap = h->tail_cap; h->st.ring_rows = h->ring_rows; h->st.row_stride = h->row_stride;
     CKH(cudaMalloc((void**)&h->st.n_samples, S * sizeof(long long)));
@@ -506,7 +542,8 @@ static MelTables mel_tables(const pb_handle* h) {
 
 static FastTables fast_tables(const pb_handle* h) {
     FastTables f;
-    f.piece = h->d_piece; f.seg_first = h->d_seg_first; f.n_pieces = h->n_pieces;
+    f.ptab = h->d_ptab; f.ctab = h->d_ctab; f.dct_t = h->d_dct_t;
+    f.npl = h->npl; f.maxc = h->maxc; f.nol = h->nol;
     return f;
 }
 

@@ -55,22 +55,19 @@ constexpr int K1F_STREAMS_PER_WARP = 16;
 constexpr int K1F_MAX_NEW = 8;
 constexpr int K1F_BUF_ELEMS = XCH_ELEMS + 8;   // +64 B: the two half-warps of a warp hit disjoint bank halves on 32-bit accesses
 
-struct FastTables {            // device copies built by the host (api.cu: build_pieces)
-    const int* piece;          // [n_pieces] start | (len << 16)
-    const int* seg_first;      // [n_filt + 2] first piece id of grid segment i; [n_filt + 1] = end
-    int n_pieces;
-};
+constexpr int K1F_PART = 132;                  // per frame: rise partials [0,64), fall partials [64,128), [128] = 0
+constexpr int K1F_ZERO_BIN = 260;              // a bin slot that always reads 0 (padding entries of the piece table)
 
-struct K1FShared {             // per CTA
-    float2 w[K1_MAX_BINS + 3];
-    int piece[K1F_MAX_PIECES];
-    int seg_first[K1_MAX_FILT + 4];
+struct FastTables {            // device copies built by the host (api.cu)
+    const float4* ptab;        // [npl][8][16]  (byte offset of the bin in P, w_rise, w_fall, -) for piece p = lane + 16 q, entry e
+    const unsigned char* ctab; // [n_filt][maxc] indices into the partial array (128 = zero slot)
+    const float* dct_t;        // [n_filt][16 * nol]  DCT rows transposed: dct_t[j][c]
+    int npl, maxc, nol;
 };
 
 struct K1FWarp {               // per warp
     float2 buf[2][2][K1F_BUF_ELEMS];           // [stage][half]: input staging -> transpose scratch -> power bins
-    float pr[2][K1F_MAX_PIECES];
-    float pf[2][K1F_MAX_PIECES];
+    float part[2][K1F_PART];
     float mel[2][K1_MAX_FILT];
     unsigned long long bar[2];
     // stream mode bookkeeping for the warp's tile of streams
@@ -79,62 +76,77 @@ struct K1FWarp {               // per warp
     short fr_stream[K1F_STREAMS_PER_WARP * K1F_MAX_NEW], fr_sub[K1F_STREAMS_PER_WARP * K1F_MAX_NEW];
 };
 
-__device__ __forceinline__ void load_fast_tables(K1FShared& s, const MelTables& t, const FastTables& ft, float* dct_smem) {
-    for (int k = threadIdx.x; k < t.n_bins; k += blockDim.x) s.w[k] = make_float2(__ldg(t.w_rise + k), __ldg(t.w_fall + k));
-    for (int k = threadIdx.x; k < ft.n_pieces; k += blockDim.x) s.piece[k] = __ldg(ft.piece + k);
-    for (int k = threadIdx.x; k < t.n_filt + 2; k += blockDim.x) s.seg_first[k] = __ldg(ft.seg_first + k);
-    if (!t.mels_only)
-        for (int k = threadIdx.x; k < t.n_out * t.n_filt; k += blockDim.x) dct_smem[k] = __ldg(t.dct + k);
+// shared-memory copies of the tables: [ptab | dct_t | ctab], carved from the dynamic tail
+struct K1FTab {
+    const float4* ptab;
+    const float* dct_t;
+    const unsigned char* ctab;
+};
+
+__device__ __forceinline__ K1FTab load_fast_tables(unsigned char* smem, const MelTables& t, const FastTables& ft) {
+    float4* sp = reinterpret_cast<float4*>(smem);
+    const int np = ft.npl * 128;
+    float* sd = reinterpret_cast<float*>(sp + np);
+    const int nd = t.mels_only ? 0 : t.n_filt * 16 * ft.nol;
+    unsigned char* sc = reinterpret_cast<unsigned char*>(sd + nd);
+    for (int k = threadIdx.x; k < np; k += blockDim.x) sp[k] = __ldg(ft.ptab + k);
+    for (int k = threadIdx.x; k < nd; k += blockDim.x) sd[k] = __ldg(ft.dct_t + k);
+    for (int k = threadIdx.x; k < t.n_filt * ft.maxc; k += blockDim.x) sc[k] = ft.ctab[k];
+    K1FTab r;
+    r.ptab = sp; r.dct_t = sd; r.ctab = sc;
+    return r;
 }
 
-// mel / log / DCT for one frame by its 16 lanes.  P: 257 power bins (shared).  out: n_out floats.
-// All 32 lanes of the warp call this (the other half works on its own frame); `active` only gates
-// the final store.
-__device__ __forceinline__ void mel16(const float* P, const K1FShared& ts, const float* dct, const MelTables& t, int n_pieces,
-                                      float* pr, float* pf, float* mel, int l16, bool active, float* __restrict__ out) {
+// mel / log / DCT for one frame by its 16 lanes, table driven and branch free.
+//   P     : 257 power bins in shared memory; P[K1F_ZERO_BIN] must read 0
+//   part  : K1F_PART floats of scratch; part[128] must read 0
+//   eoff  : this lane's 8 entry offsets (in float4 units) into a piece-table block: ((i + rot) & 7) * 16 + l16
+// All 32 lanes of the warp call this (the other half works on its own frame); `active` gates the store.
+__device__ __forceinline__ void mel16(const float* P, const K1FTab& tb, const FastTables& ft, const MelTables& t,
+                                      float* part, float* mel, const int (&eoff)[8], int l16, bool active,
+                                      float* __restrict__ out) {
+    const char* Pb = reinterpret_cast<const char*>(P);
     float tot = 0.f;
-    // consecutive lanes own consecutive 8-bin pieces (stride 8 words = 4 bank groups): rotating the walk
-    // by (lane / 4) inside a piece, and by 4 more in the second half-warp, keeps 32 lanes on 32 banks
-    const int rot = ((l16 >> 2) + ((threadIdx.x & 16) >> 2)) & 7;
-    for (int p = l16; p < n_pieces; p += 16) {
-        const int pc = ts.piece[p];
-        const int start = pc & 0xffff, len = pc >> 16;
+#pragma unroll 1
+    for (int q = 0; q < ft.npl; ++q) {
+        const float4* blk = tb.ptab + q * 128;
         float r = 0.f, f = 0.f;
 #pragma unroll
-        for (int i0 = 0; i0 < K1F_PIECE_LEN; ++i0) {
-            const int i = (i0 + rot) & 7;
-            if (i < len) {
-                const float pw = P[start + i];
-                const float2 w = ts.w[start + i];
-                tot += pw;
-                r = fmaf(w.x, pw, r);
-                f = fmaf(w.y, pw, f);
-            }
+        for (int i = 0; i < 8; ++i) {
+            const float4 e = blk[eoff[i]];
+            const float pw = *reinterpret_cast<const float*>(Pb + __float_as_int(e.x));
+            tot += pw;
+            r = fmaf(e.y, pw, r);
+            f = fmaf(e.z, pw, f);
         }
-        pr[p] = r; pf[p] = f;
+        part[q * 16 + l16] = r;
+        part[64 + q * 16 + l16] = f;
     }
-    // total power over the 16 lanes of this half-warp
 #pragma unroll
     for (int d = 8; d >= 1; d >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, d);
     __syncwarp();
+#pragma unroll 1
     for (int j = l16; j < t.n_filt; j += 16) {
-        const int a = ts.seg_first[j], b = ts.seg_first[j + 1], c = ts.seg_first[j + 2];
-        float m = 0.f;
-        for (int p = a; p < b; ++p) m += pr[p];
-        for (int p = b; p < c; ++p) m += pf[p];
-        mel[j] = logf(fmaxf(m, K1_EPS));
+        const unsigned char* ci = tb.ctab + j * ft.maxc;
+        float m0 = 0.f, m1 = 0.f;
+#pragma unroll 1
+        for (int c = 0; c + 1 < ft.maxc; c += 2) { m0 += part[ci[c]]; m1 += part[ci[c + 1]]; }
+        if (ft.maxc & 1) m0 += part[ci[ft.maxc - 1]];
+        mel[j] = logf(fmaxf(m0 + m1, K1_EPS));
     }
     __syncwarp();
     if (t.mels_only) {
         for (int j = l16; j < t.n_out; j += 16)
             if (active) out[j] = mel[j];
     } else {
+        const int ld = 16 * ft.nol;
+#pragma unroll 1
         for (int c = l16; c < t.n_out; c += 16) {
             float a0 = 0.f, a1 = 0.f;
-            const float* d = dct + c * t.n_filt;
-            int j = 0;
-            for (; j + 1 < t.n_filt; j += 2) { a0 = fmaf(d[j], mel[j], a0); a1 = fmaf(d[j + 1], mel[j + 1], a1); }
-            if (j < t.n_filt) a0 = fmaf(d[j], mel[j], a0);
+            const float* d = tb.dct_t + c;
+#pragma unroll 4
+            for (int j = 0; j + 1 < t.n_filt; j += 2) { a0 = fmaf(d[j * ld], mel[j], a0); a1 = fmaf(d[(j + 1) * ld], mel[j + 1], a1); }
+            if (t.n_filt & 1) a0 = fmaf(d[(t.n_filt - 1) * ld], mel[t.n_filt - 1], a0);
             const float v = c == 0 ? logf(fmaxf(tot, K1_EPS)) : a0 + a1;
             if (active) out[c] = v;
         }
@@ -143,9 +155,9 @@ __device__ __forceinline__ void mel16(const float* P, const K1FShared& ts, const
 }
 
 // One FFT + mel pass for the warp's two frames whose 1 KB inputs have landed in ws.buf[stage].
-__device__ __forceinline__ void fast_pass(K1FWarp& ws, int stage, uint32_t parity, const FftLaneConst& lc, const K1FShared& ts,
-                                          const float* dct, const MelTables& t, int n_pieces, float scale, int l16, int half,
-                                          bool active, float* __restrict__ out) {
+__device__ __forceinline__ void fast_pass(K1FWarp& ws, int stage, uint32_t parity, const FftLaneConst& lc, const K1FTab& tb,
+                                          const FastTables& ft, const MelTables& t, float scale, const int (&eoff)[8],
+                                          int l16, int half, bool active, float* __restrict__ out) {
     mbar_wait(&ws.bar[stage], parity);
     const int* in = reinterpret_cast<const int*>(ws.buf[stage][half]);
     cpx z[16];
@@ -158,8 +170,9 @@ __device__ __forceinline__ void fast_pass(K1FWarp& ws, int stage, uint32_t parit
     __syncwarp();                                  // all lanes have read the staged samples: the buffer becomes scratch
     float* P = reinterpret_cast<float*>(ws.buf[stage][half]);
     fft512_power(z, lc, ws.buf[stage][half], P, scale, l16, active);   // P aliases the scratch: written after the last scratch read
+    if (l16 == 0) P[K1F_ZERO_BIN] = 0.f;           // padding entries of the piece table point here
     __syncwarp();
-    mel16(P, ts, dct, t, n_pieces, ws.pr[half], ws.pf[half], ws.mel[half], l16, active, out);
+    mel16(P, tb, ft, t, ws.part[half], ws.mel[half], eoff, l16, active, out);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -168,13 +181,18 @@ __global__ void __launch_bounds__(K1F_THREADS, 4)
 mfcc_fast_batch_kernel(const int16_t* __restrict__ pcm, long long samples_per_stream, long long n_frames_per_stream,
                        long long total_frames, int hop, float scale, MelTables tab, FastTables ft, float* __restrict__ out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    K1FShared& ts = *reinterpret_cast<K1FShared*>(smem_raw);
-    K1FWarp* wsm = reinterpret_cast<K1FWarp*>(smem_raw + sizeof(K1FShared));
-    float* dct = reinterpret_cast<float*>(smem_raw + sizeof(K1FShared) + K1F_WARPS * sizeof(K1FWarp));
+    K1FWarp* wsm = reinterpret_cast<K1FWarp*>(smem_raw);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, l16 = lane & 15, half = lane >> 4;
     K1FWarp& ws = wsm[warp];
-    load_fast_tables(ts, tab, ft, dct);
+    const K1FTab tb = load_fast_tables(smem_raw + K1F_WARPS * sizeof(K1FWarp), tab, ft);
     if (lane == 0) { mbar_init(&ws.bar[0], 1); mbar_init(&ws.bar[1], 1); fence_mbar_init(); }
+    if (l16 == 0) ws.part[half][128] = 0.f;
+    int eoff[8];                                   // rotated walk through a piece: see mel16
+    {
+        const int rot = ((l16 >> 2) + (half << 2)) & 7;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) eoff[i] = ((i + rot) & 7) * 16 + l16;
+    }
     FftLaneConst lc;
     load_lane_const(lc, tab.tw_stage, tab.tw_post, l16);
     __syncthreads();
@@ -200,7 +218,7 @@ mfcc_fast_batch_kernel(const int16_t* __restrict__ pcm, long long samples_per_st
         if (next < n_pairs && lane == 0) issue(next, stage ^ 1);
         const long long g = 2 * pair + half;
         const bool active = g < total_frames;
-        fast_pass(ws, stage, (uint32_t)((it >> 1) & 1), lc, ts, dct, tab, ft.n_pieces, scale, l16, half, active,
+        fast_pass(ws, stage, (uint32_t)((it >> 1) & 1), lc, tb, ft, tab, scale, eoff, l16, half, active,
                   out + (active ? g : 0) * tab.n_out);
     }
 }
@@ -211,13 +229,18 @@ __global__ void __launch_bounds__(K1F_THREADS, 4)
 mfcc_fast_stream_kernel(const int16_t* __restrict__ pcm, const int* __restrict__ ids, int n, int chunk, int hop, int spw,
                         float scale, MelTables tab, FastTables ft, StreamState st) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    K1FShared& ts = *reinterpret_cast<K1FShared*>(smem_raw);
-    K1FWarp* wsm = reinterpret_cast<K1FWarp*>(smem_raw + sizeof(K1FShared));
-    float* dct = reinterpret_cast<float*>(smem_raw + sizeof(K1FShared) + K1F_WARPS * sizeof(K1FWarp));
+    K1FWarp* wsm = reinterpret_cast<K1FWarp*>(smem_raw);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, l16 = lane & 15, half = lane >> 4;
     K1FWarp& ws = wsm[warp];
-    load_fast_tables(ts, tab, ft, dct);
+    const K1FTab tb = load_fast_tables(smem_raw + K1F_WARPS * sizeof(K1FWarp), tab, ft);
     if (lane == 0) { mbar_init(&ws.bar[0], 1); mbar_init(&ws.bar[1], 1); fence_mbar_init(); }
+    if (l16 == 0) ws.part[half][128] = 0.f;
+    int eoff[8];                                   // rotated walk through a piece: see mel16
+    {
+        const int rot = ((l16 >> 2) + (half << 2)) & 7;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) eoff[i] = ((i + rot) & 7) * 16 + l16;
+    }
     FftLaneConst lc;
     load_lane_const(lc, tab.tw_stage, tab.tw_post, l16);
     __syncthreads();
@@ -283,24 +306,39 @@ mfcc_fast_stream_kernel(const int16_t* __restrict__ pcm, const int* __restrict__
                 row = st.ring + ((long long)ws.st_id[t] * st.ring_rows + (int)(k % st.ring_rows)) * st.row_stride;
             }
             const uint32_t parity = (stage == 0 ? uses0 : uses1) & 1;
-            fast_pass(ws, stage, parity, lc, ts, dct, tab, ft.n_pieces, scale, l16, half, active, row);
+            fast_pass(ws, stage, parity, lc, tb, ft, tab, scale, eoff, l16, half, active, row);
             if (stage == 0) ++uses0; else ++uses1;
         }
-        // ---- tail + sample counter: the warp walks its streams; every old-tail read of this tile is complete
-        // (the bulk copies that read it were waited for above)
-        for (int t = 0; t < spw; ++t) {
-            const int sid = ws.st_id[t];
-            if (sid < 0) continue;
-            const long long n0 = ws.st_n0[t], n1 = n0 + chunk, ts0 = ws.st_ts0[t];
-            const long long c1 = ws.st_c0[t] + ws.st_cnt[t];
+        // ---- tail + sample counter.  Every old-tail read of this tile is complete (the bulk copies that read it
+        // were waited for above).  Lane t < spw derives stream t's copy plan; then the whole warp copies all
+        // streams' tails in one flat loop of 16-byte vectors so the loads of different streams overlap.
+        int my_nv = 0, my_nold = 0;
+        if (lane < spw && ws.st_id[lane] >= 0) {
+            const long long n0 = ws.st_n0[lane], n1 = n0 + chunk;
+            const long long c1 = ws.st_c0[lane] + ws.st_cnt[lane];
             const long long ts1 = c1 * hop < n1 ? c1 * hop : n1;
-            const int len1 = (int)(n1 - ts1);
-            const int n_old = ts1 < n0 ? (int)(n0 - ts1) : 0;
-            int16_t* tl = st.tail + (long long)sid * st.tail_cap;
-            const int16_t* chunk_p = pcm + (long long)(base + t) * chunk;
-            if (n_old > 0) {                                  // shift inside the tail (chunk shorter than the FFT window)
-                int4 keep[2];                                 // n_old < 512 samples = 64 int4 = 2 per lane
-                const int4* srcv = reinterpret_cast<const int4*>(tl + (ts1 - ts0));
+            my_nold = ts1 < n0 ? (int)(n0 - ts1) : 0;
+            my_nv = ((int)(n1 - ts1) - my_nold) >> 3;
+            ws.st_ts0[lane] = ts1 > n0 ? ts1 - n0 : 0;      // reuse: offset of the copied part inside the chunk
+            ws.st_cnt[lane] = my_nv | (my_nold << 16);
+            st.n_samples[ws.st_id[lane]] = n1;
+        }
+        const unsigned any_old = __ballot_sync(0xffffffffu, my_nold > 0);
+        __syncwarp();
+        if (any_old) {                                        // chunk shorter than the FFT window: shift inside the tail first
+            for (int t = 0; t < spw; ++t) {
+                const int sid = ws.st_id[t];
+                if (sid < 0) continue;
+                const int n_old = ws.st_cnt[t] >> 16;
+                if (n_old == 0) continue;
+                const long long n0 = ws.st_n0[t];
+                int16_t* tl = st.tail + (long long)sid * st.tail_cap;
+                // old tail held [n0 - len0, n0); the part that survives is its last n_old samples
+                const long long c0 = frames_ready(n0, used, hop);
+                const long long ts0 = c0 * hop < n0 ? c0 * hop : n0;
+                const int len0 = (int)(n0 - ts0);
+                int4 keep[2];
+                const int4* srcv = reinterpret_cast<const int4*>(tl + (len0 - n_old));
                 const int nv = n_old >> 3;
 #pragma unroll
                 for (int j = 0; j < 2; ++j) if (j * 32 + lane < nv) keep[j] = srcv[j * 32 + lane];
@@ -308,11 +346,17 @@ mfcc_fast_stream_kernel(const int16_t* __restrict__ pcm, const int* __restrict__
 #pragma unroll
                 for (int j = 0; j < 2; ++j) if (j * 32 + lane < nv) reinterpret_cast<int4*>(tl)[j * 32 + lane] = keep[j];
             }
-            const int4* srcv = reinterpret_cast<const int4*>(chunk_p + (ts1 > n0 ? ts1 - n0 : 0));
-            int4* dstv = reinterpret_cast<int4*>(tl + n_old);
-            const int nv = (len1 - n_old) >> 3;
-            for (int v = lane; v < nv; v += 32) dstv[v] = __ldg(srcv + v);
-            if (lane == 0) st.n_samples[sid] = n1;
+            __syncwarp();
+        }
+        for (int e = lane; e < spw * 64; e += 32) {           // <= 64 vectors (511 samples) per stream
+            const int t = e >> 6, v = e & 63;
+            const int sid = ws.st_id[t];
+            if (sid < 0) continue;
+            const int cn = ws.st_cnt[t];
+            if (v >= (cn & 0xffff)) continue;
+            const int4* srcv = reinterpret_cast<const int4*>(pcm + (long long)(base + t) * chunk + ws.st_ts0[t]);
+            int4* dstv = reinterpret_cast<int4*>(st.tail + (long long)sid * st.tail_cap + (cn >> 16));
+            dstv[v] = __ldg(srcv + v);
         }
         __syncwarp();
     }
