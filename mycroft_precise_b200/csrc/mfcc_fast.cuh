@@ -348,15 +348,27 @@ mfcc_fast_stream_kernel(const int16_t* __restrict__ pcm, const int* __restrict__
             }
             __syncwarp();
         }
-        for (int e = lane; e < spw * 64; e += 32) {           // <= 64 vectors (511 samples) per stream
-            const int t = e >> 6, v = e & 63;
-            const int sid = ws.st_id[t];
-            if (sid < 0) continue;
-            const int cn = ws.st_cnt[t];
-            if (v >= (cn & 0xffff)) continue;
-            const int4* srcv = reinterpret_cast<const int4*>(pcm + (long long)(base + t) * chunk + ws.st_ts0[t]);
-            int4* dstv = reinterpret_cast<int4*>(st.tail + (long long)sid * st.tail_cap + (cn >> 16));
-            dstv[v] = __ldg(srcv + v);
+        // flat loop over (stream, vector) slots, 4 loads in flight per lane before the first store
+#pragma unroll 1
+        for (int e0 = lane; e0 < spw * 64; e0 += 32 * 4) {
+            int4 v[4];
+            int4* dst[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int e = e0 + 32 * u;
+                dst[u] = nullptr;
+                if (e < spw * 64) {
+                    const int t = e >> 6, vi = e & 63;
+                    const int cn = ws.st_cnt[t];
+                    if (ws.st_id[t] >= 0 && vi < (cn & 0xffff)) {
+                        v[u] = __ldg(reinterpret_cast<const int4*>(pcm + (long long)(base + t) * chunk + ws.st_ts0[t]) + vi);
+                        dst[u] = reinterpret_cast<int4*>(st.tail + (long long)ws.st_id[t] * st.tail_cap + (cn >> 16)) + vi;
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (dst[u] != nullptr) *dst[u] = v[u];
         }
         __syncwarp();
     }
