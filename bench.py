@@ -229,6 +229,8 @@ def run_b200(args):
     model.dense_b = 3.0          # confidence above the trigger threshold: the detection path and the count all-reduce carry real data
     sb = StreamBatch(model, S, chunk_samples=CHUNK, device=local)
     core = sb.core
+    if args.gru_mode:
+        core.gru_mode(args.gru_mode)
 
     # ---- synthetic PCM: NT distinct ticks resident in HBM (each tick 2 KB x S > L2 at the default S)
     NT = args.ticks_resident
@@ -449,6 +451,7 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-latency', dest='latency', action='store_false')
     ap.add_argument('--no-config3', dest='config3', action='store_false')
+    ap.add_argument('--gru-mode', type=int, default=0, help='debug: 0 auto, 1 CUDA-core, 2 mma.sync, 3 tcgen05')
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

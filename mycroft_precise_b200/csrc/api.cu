@@ -17,6 +17,7 @@
 #include "gru_kernels.cuh"
 #include "mfcc_kernels.cuh"
 #include "mfcc_fast.cuh"
+#include "gru_tc5.cuh"
 
 using namespace pb;
 
@@ -81,6 +82,7 @@ struct pb_handle {
     float *d_wcat = nullptr, *d_bias = nullptr, *d_wd = nullptr;
     float4* d_bfrag = nullptr;       // tensor-core GRU: pre-split, fragment-ordered weights
     float *d_mma_bias = nullptr, *d_mma_wd = nullptr;
+    float *d_tc5 = nullptr;           // tcgen05 GRU: [b1_hi | b1_lo | b2_hi | b2_lo | bias(80) | wd(24)]
     int gru_mode = 0;                // 0 = auto, 1 = force CUDA-core small kernel, 2 = force tensor-core kernel
     float bd = 0.f;
     // host pipeline
@@ -216,7 +218,7 @@ PB_API void pb_destroy(pb_handle* h) {
     cudaFree(h->d_tw_stage); cudaFree(h->d_tw_post); cudaFree(h->d_cd); cudaFree(h->d_ptab); cudaFree(h->d_ctab); cudaFree(h->d_dct_t);
     cudaFree(h->st.n_samples); cudaFree(h->st.tail); cudaFree(h->st.ring); cudaFree(h->st.trig);
     cudaFree(h->d_wcat); cudaFree(h->d_bias); cudaFree(h->d_wd); cudaFree(h->d_count);
-    cudaFree(h->d_bfrag); cudaFree(h->d_mma_bias); cudaFree(h->d_mma_wd);
+    cudaFree(h->d_bfrag); cudaFree(h->d_mma_bias); cudaFree(h->d_mma_wd); cudaFree(h->d_tc5);
     if (h->h_count_pinned) cudaFreeHost(h->h_count_pinned);
     for (int i = 0; i < HOST_PIPE; ++i) {
         cudaFree(h->d_stage_pcm[i]); cudaFree(h->d_stage_ids[i]); cudaFree(h->d_stage_raw[i]);
@@ -463,6 +465,34 @@ PB_API int pb_load_weights(pb_handle* h, const float* kernel, const float* recur
         CK(upload(&h->d_bfrag, bf));
         CK(upload(&h->d_mma_bias, mb));
         CK(upload(&h->d_mma_wd, mw));
+        {   // tcgen05 operand tiles (gru_tc5.cuh): B[k/4][n][k%4], k = x feature (0..15) then hidden unit (16..39)
+            const int n1 = TC5_N1, n2 = TC5_N2, sz1 = 10 * n1 * 4, sz2 = 10 * n2 * 4;
+            std::vector<float> t((size_t)2 * sz1 + 2 * sz2 + 80 + 24, 0.f);
+            float *b1h = t.data(), *b1l = b1h + sz1, *b2h = b1l + sz1, *b2l = b2h + sz2, *tb = b2l + sz2, *tw = tb + 80;
+            auto wv = [&](int k, int gate, int unit) -> float {
+                if (unit >= H) return 0.f;
+                if (k < 16) return k < F ? kernel[(size_t)k * H3 + gate * H + unit] : 0.f;
+                const int hu = k - 16;
+                return hu < H ? recurrent[(size_t)hu * H3 + gate * H + unit] : 0.f;
+            };
+            for (int k = 0; k < 40; ++k) {
+                for (int c = 0; c < n1; ++c) {
+                    const float v = wv(k, c / 24, c % 24), vh = tf32(v);
+                    b1h[((size_t)(k / 4) * n1 + c) * 4 + k % 4] = vh;
+                    b1l[((size_t)(k / 4) * n1 + c) * 4 + k % 4] = tf32(v - vh);
+                }
+                for (int c = 0; c < n2; ++c) {
+                    const float v = wv(k, 2, c), vh = tf32(v);
+                    b2h[((size_t)(k / 4) * n2 + c) * 4 + k % 4] = vh;
+                    b2l[((size_t)(k / 4) * n2 + c) * 4 + k % 4] = tf32(v - vh);
+                }
+            }
+            for (int u = 0; u < H; ++u) { tb[u] = bias[u]; tb[24 + u] = bias[H + u]; tb[48 + u] = bias[2 * H + u]; tw[u] = dense_w[u]; }
+            cudaFree(h->d_tc5); h->d_tc5 = nullptr;
+            CK(upload(&h->d_tc5, t));
+            CK(cudaFuncSetAttribute(gru_tc5_kernel<20, 13, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Tc5Smem) + 128));
+            CK(cudaFuncSetAttribute(gru_tc5_kernel<20, 13, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Tc5Smem) + 128));
+        }
         memcpy(h->w_small.W, kernel, sizeof(h->w_small.W));
         memcpy(h->w_small.U, recurrent, sizeof(h->w_small.U));
         memcpy(h->w_small.b, bias, sizeof(h->w_small.b));
@@ -605,6 +635,15 @@ static int launch_gru(pb_handle* h, const K2In& in, bool ring, int64_t n, const 
         const int grid = (int)((n + 3) / 4);
         if (ring) gru_warp_kernel<20, 13, true><<<grid, 128, 0, s>>>(h->w_small, in, n, dp, o);
         else gru_warp_kernel<20, 13, false><<<grid, 128, 0, s>>>(h->w_small, in, n, dp, o);
+    } else if (h->small_path && h->gru_mode == 3) {               // tcgen05 + TMEM scan
+        GruTc5W w;
+        const int sz1 = 10 * TC5_N1 * 4, sz2 = 10 * TC5_N2 * 4;
+        w.b1_hi = h->d_tc5; w.b1_lo = w.b1_hi + sz1; w.b2_hi = w.b1_lo + sz1; w.b2_lo = w.b2_hi + sz2;
+        w.bias = w.b2_lo + sz2; w.wd = w.bias + 80; w.bd = h->bd;
+        const int grid = (int)((n + TC5_THREADS - 1) / TC5_THREADS);
+        const size_t smem = sizeof(Tc5Smem) + 128;
+        if (ring) gru_tc5_kernel<20, 13, true><<<grid, TC5_THREADS, smem, s>>>(w, in, n, dp, o);
+        else gru_tc5_kernel<20, 13, false><<<grid, TC5_THREADS, smem, s>>>(w, in, n, dp, o);
     } else if (h->small_path && h->gru_mode != 1) {               // tensor-core scan (mma.sync TF32 x3)
         GruMmaW w;
         w.bfrag = h->d_bfrag; w.bias = h->d_mma_bias; w.wd = h->d_mma_wd; w.bd = h->bd;
