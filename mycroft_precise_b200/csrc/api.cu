@@ -18,6 +18,7 @@
 #include "mfcc_kernels.cuh"
 #include "mfcc_fast.cuh"
 #include "gru_tc5.cuh"
+#include "gru_tc5_big.cuh"
 
 using namespace pb;
 
@@ -82,6 +83,9 @@ struct pb_handle {
     float *d_wcat = nullptr, *d_bias = nullptr, *d_wd = nullptr;
     float4* d_bfrag = nullptr;       // tensor-core GRU: pre-split, fragment-ordered weights
     float *d_mma_bias = nullptr, *d_mma_wd = nullptr;
+    float *d_tcb = nullptr;           // tcgen05 wide-network GRU: [b1 tiles | b2 tiles | bias(384) | wd(128)]
+    bool tcb_ok = false;
+    int tcb_kx = 0;
     float *d_tc5 = nullptr;           // tcgen05 GRU: [b1_hi | b1_lo | b2_hi | b2_lo | bias(80) | wd(24)]
     int gru_mode = 0;                // 0 = auto, 1 = force CUDA-core small kernel, 2 = force tensor-core kernel
     float bd = 0.f;
@@ -218,7 +222,7 @@ PB_API void pb_destroy(pb_handle* h) {
     cudaFree(h->d_tw_stage); cudaFree(h->d_tw_post); cudaFree(h->d_cd); cudaFree(h->d_ptab); cudaFree(h->d_ctab); cudaFree(h->d_dct_t);
     cudaFree(h->st.n_samples); cudaFree(h->st.tail); cudaFree(h->st.ring); cudaFree(h->st.trig);
     cudaFree(h->d_wcat); cudaFree(h->d_bias); cudaFree(h->d_wd); cudaFree(h->d_count);
-    cudaFree(h->d_bfrag); cudaFree(h->d_mma_bias); cudaFree(h->d_mma_wd); cudaFree(h->d_tc5);
+    cudaFree(h->d_bfrag); cudaFree(h->d_mma_bias); cudaFree(h->d_mma_wd); cudaFree(h->d_tc5); cudaFree(h->d_tcb);
     if (h->h_count_pinned) cudaFreeHost(h->h_count_pinned);
     for (int i = 0; i < HOST_PIPE; ++i) {
         cudaFree(h->d_stage_pcm[i]); cudaFree(h->d_stage_ids[i]); cudaFree(h->d_stage_raw[i]);
@@ -499,6 +503,42 @@ PB_API int pb_load_weights(pb_handle* h, const float* kernel, const float* recur
         memcpy(h->w_small.wd, dense_w, sizeof(h->w_small.wd));
         h->w_small.bd = dense_b;
     } else {
+        h->tcb_ok = H <= TCB_HP && F <= 8 * TCB_MAX_KX && !h->cfg.use_delta;
+        if (h->tcb_ok) {
+            // weight tiles of gru_tcb_kernel: per k-step s one contiguous tile [hi: chunk0[N][4], chunk1[N][4] | lo: same];
+            // k-step s < kx covers x features 8s..8s+7, s >= kx hidden units 8(s-kx)..; phase 1: N = 256 (z | r), phase 2: N = 128
+            auto tf32 = [](float x) { uint32_t u; memcpy(&u, &x, 4); u = (u + 0x1000u) & 0xffffe000u; float r; memcpy(&r, &u, 4); return r; };
+            const int kx = (F + 7) / 8, ks = kx + TCB_KH;
+            h->tcb_kx = kx;
+            std::vector<float> t((size_t)ks * 4096 + (size_t)ks * 2048 + 3 * TCB_HP + TCB_HP, 0.f);
+            float* b1 = t.data(); float* b2 = b1 + (size_t)ks * 4096; float* tb = b2 + (size_t)ks * 2048; float* tw = tb + 3 * TCB_HP;
+            auto wv = [&](int s, int j, int gate, int unit) -> float {
+                if (unit >= H) return 0.f;
+                if (s < kx) { const int f = 8 * s + j; return f < F ? kernel[(size_t)f * H3 + gate * H + unit] : 0.f; }
+                const int hu = 8 * (s - kx) + j;
+                return hu < H ? recurrent[(size_t)hu * H3 + gate * H + unit] : 0.f;
+            };
+            for (int s = 0; s < ks; ++s)
+                for (int j = 0; j < 8; ++j) {
+                    for (int c = 0; c < 256; ++c) {
+                        const float v = wv(s, j, c / TCB_HP, c % TCB_HP), vh = tf32(v);
+                        const size_t o = (size_t)s * 4096 + ((size_t)(j / 4) * 256 + c) * 4 + j % 4;
+                        b1[o] = vh; b1[o + 2048] = tf32(v - vh);
+                    }
+                    for (int c = 0; c < 128; ++c) {
+                        const float v = wv(s, j, 2, c), vh = tf32(v);
+                        const size_t o = (size_t)s * 2048 + ((size_t)(j / 4) * 128 + c) * 4 + j % 4;
+                        b2[o] = vh; b2[o + 1024] = tf32(v - vh);
+                    }
+                }
+            for (int g = 0; g < 3; ++g)
+                for (int u = 0; u < H; ++u) tb[g * TCB_HP + u] = bias[g * H + u];
+            for (int u = 0; u < H; ++u) tw[u] = dense_w[u];
+            cudaFree(h->d_tcb); h->d_tcb = nullptr;
+            CK(upload(&h->d_tcb, t));
+            CK(cudaFuncSetAttribute(gru_tcb_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TcbSmem) + 128));
+            CK(cudaFuncSetAttribute(gru_tcb_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TcbSmem) + 128));
+        }
         size_t smem = (size_t)(F + 3 * H) * K2_TILE_STREAMS * sizeof(float);
         if (smem > 200 * 1024) return fail(PB_ERR_UNSUPPORTED, "feature_size + 3*hidden = %d is too large for the tiled GRU kernel", F + 3 * H);
         CK(cudaFuncSetAttribute(gru_tiled_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -656,6 +696,15 @@ static int launch_gru(pb_handle* h, const K2In& in, bool ring, int64_t n, const 
         const int grid = (int)((n + per_cta - 1) / per_cta);
         if (ring) gru_small_kernel<20, 13, true><<<grid, K2_SMALL_THREADS, 0, s>>>(h->w_small, in, n, dp, o);
         else gru_small_kernel<20, 13, false><<<grid, K2_SMALL_THREADS, 0, s>>>(h->w_small, in, n, dp, o);
+    } else if (h->tcb_ok && h->gru_mode != 1) {                    // wide network on tcgen05 + TMEM, weights via TMA pipeline
+        GruTcbW w;
+        const int ks = h->tcb_kx + TCB_KH;
+        w.b1 = h->d_tcb; w.b2 = w.b1 + (size_t)ks * 4096; w.bias = w.b2 + (size_t)ks * 2048; w.wd = w.bias + 3 * TCB_HP;
+        w.bd = h->bd; w.kx = h->tcb_kx; w.F = h->feat; w.H = h->cfg.hidden; w.act = h->cfg.activation; w.ract = h->cfg.recurrent_activation;
+        const int grid = (int)((n + TCB_THREADS - 1) / TCB_THREADS);
+        const size_t smem = sizeof(TcbSmem) + 128;
+        if (ring) gru_tcb_kernel<true><<<grid, TCB_THREADS, smem, s>>>(w, in, n, dp, o);
+        else gru_tcb_kernel<false><<<grid, TCB_THREADS, smem, s>>>(w, in, n, dp, o);
     } else {
         GruTiledW w;
         w.wcat = h->d_wcat; w.bias = h->d_bias; w.wd = h->d_wd; w.bd = h->bd;

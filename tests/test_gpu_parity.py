@@ -235,7 +235,7 @@ def test_stream_tick_kernel_variants_agree():
     assert all(abs(o[2] - outs[0][2]) <= 3 for o in outs[1:])
 
 
-def _generic_case(pr_kw, H, act='linear', ract='hard_sigmoid', N=200, seed=5):
+def _generic_case(pr_kw, H, act='linear', ract='hard_sigmoid', N=200, seed=5, mode=0):
     m = _mod()
     pr = m.ListenerParams(**pr_kw)
     c = m.PreciseB200(pr, hidden=H, max_streams=8, activation=act, recurrent_activation=ract)
@@ -243,6 +243,7 @@ def _generic_case(pr_kw, H, act='linear', ract='hard_sigmoid', N=200, seed=5):
     w = og.GruWeights.random(F, H, seed=seed, scale=0.1 / np.sqrt(max(H, 20) / 20.0))   # contractive recurrence
     w.activation, w.recurrent_activation = act, ract
     c.load_weights(w.kernel, w.recurrent, w.bias, w.dense_w, w.dense_b)
+    c.gru_mode(mode)
     x = (np.random.RandomState(seed).randn(N, pr.n_features, F) * 2).astype(np.float32)
     p = c.predict(cuda(x)).cpu().numpy()
     p64 = og.gru_forward(w, x, np.float64)[0]
@@ -257,9 +258,11 @@ def _generic_case(pr_kw, H, act='linear', ract='hard_sigmoid', N=200, seed=5):
     (20, {}, 'tanh', 'sigmoid'),
     (7, dict(n_mfcc=5), 'tanh', 'hard_sigmoid'),
 ])
-def test_predict_tiled_path(H, kw, act, ract):
-    err = _generic_case(kw, H, act, ract)
-    print('tiled GRU err', err)
+@pytest.mark.parametrize('mode', [0, 1])
+def test_predict_tiled_path(H, kw, act, ract, mode):
+    """mode 0: automatic choice (tcgen05 wide-network kernel where it applies), mode 1: CUDA-core tiled kernel."""
+    err = _generic_case(kw, H, act, ract, mode=mode, N=333)
+    print('generic GRU err', err)
     assert err < 1e-5
 
 
