@@ -703,8 +703,8 @@ static int launch_gru(pb_handle* h, const K2In& in, bool ring, int64_t n, const 
         w.bd = h->bd; w.kx = h->tcb_kx; w.F = h->feat; w.H = h->cfg.hidden; w.act = h->cfg.activation; w.ract = h->cfg.recurrent_activation;
         const int grid = (int)((n + TCB_THREADS - 1) / TCB_THREADS);
         const size_t smem = sizeof(TcbSmem) + 128;
-        if (ring) gru_tcb_kernel<true><<<grid, TCB_THREADS, smem, s>>>(w, in, n, dp, o);
-        else gru_tcb_kernel<false><<<grid, TCB_THREADS, smem, s>>>(w, in, n, dp, o);
+        if (ring) gru_tcb_kernel<true><<<grid, TCB_BLOCK, smem, s>>>(w, in, n, dp, o);
+        else gru_tcb_kernel<false><<<grid, TCB_BLOCK, smem, s>>>(w, in, n, dp, o);
     } else {
         GruTiledW w;
         w.wcat = h->d_wcat; w.bias = h->d_bias; w.wd = h->d_wd; w.bd = h->bd;

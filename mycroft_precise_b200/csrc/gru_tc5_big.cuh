@@ -20,7 +20,8 @@
 
 namespace pb {
 
-constexpr int TCB_THREADS = 128;
+constexpr int TCB_THREADS = 128;            // row threads (thread i <-> stream row i)
+constexpr int TCB_BLOCK = 192;              // + a weight-producer warp and an MMA-issuer warp (one lane each), free-running
 constexpr int TCB_HP = 128;                 // padded hidden width
 constexpr int TCB_KH = TCB_HP / 8;          // recurrent k-steps
 constexpr int TCB_MAX_KX = 5;               // F <= 40
@@ -46,7 +47,7 @@ struct TcbSmem {
     float hs[TCB_HP][128];                   // h, fp32, [unit][row]
     float bias[3 * TCB_HP];
     float wd[TCB_HP];
-    unsigned long long full[TCB_STAGES], empty[TCB_STAGES], done[2];
+    unsigned long long full[TCB_STAGES], empty[TCB_STAGES], done[2], ready[2];
     uint32_t tmem_base;
 };
 
@@ -76,19 +77,23 @@ __device__ __forceinline__ void tcb_put_a16(uint32_t t_row, int col, const float
     tcb_st16(t_row + TCB_TMEM_AL + col, lo);
 }
 
+__device__ __forceinline__ void tcb_row_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }   // the 128 row threads only
+
 template <bool RING>
-__global__ void __launch_bounds__(TCB_THREADS, 1)
+__global__ void __launch_bounds__(TCB_BLOCK, 1)
 gru_tcb_kernel(GruTcbW W, K2In in, long long n, DecodeParams dp, K2Out out) {
     extern __shared__ __align__(128) unsigned char tcb_raw[];
     TcbSmem& sm = *reinterpret_cast<TcbSmem*>(tcb_raw);
     const int tid = threadIdx.x, warp = tid >> 5;
     const int kx = W.kx, ksteps = kx + TCB_KH;
-    for (int e = tid; e < 3 * TCB_HP; e += TCB_THREADS) sm.bias[e] = __ldg(W.bias + e);
-    for (int e = tid; e < TCB_HP; e += TCB_THREADS) sm.wd[e] = __ldg(W.wd + e);
-    for (int u = 0; u < TCB_HP; ++u) sm.hs[u][tid] = 0.f;
+    for (int e = tid; e < 3 * TCB_HP; e += TCB_BLOCK) sm.bias[e] = __ldg(W.bias + e);
+    for (int e = tid; e < TCB_HP; e += TCB_BLOCK) sm.wd[e] = __ldg(W.wd + e);
+    if (tid < TCB_THREADS)
+        for (int u = 0; u < TCB_HP; ++u) sm.hs[u][tid] = 0.f;
     if (tid == 0) {
         for (int s = 0; s < TCB_STAGES; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], 1); }
         mbar_init(&sm.done[0], 1); mbar_init(&sm.done[1], 1);
+        mbar_init(&sm.ready[0], TCB_THREADS); mbar_init(&sm.ready[1], TCB_THREADS);
         fence_mbar_init();
     }
     if (warp == 0) {
@@ -100,8 +105,63 @@ gru_tcb_kernel(GruTcbW W, K2In in, long long n, DecodeParams dp, K2Out out) {
     __syncthreads();
     tc5_fence_after();
     const uint32_t tmem = sm.tmem_base;
-    const uint32_t t_row = tmem + ((uint32_t)(warp * 32) << 16);
+    if (warp == 4) {
+        // ---- weight producer: free-running over steps x phases x k-steps, throttled only by the stage ring, so the
+        // tiles of the next phase / step arrive while the row threads do their element-wise work
+        if (tid == TCB_THREADS) {
+            uint32_t it = 0;
+            for (int step = 0; step < in.T; ++step)
+                for (int phase = 0; phase < 2; ++phase) {
+                    const uint32_t tile_bytes = phase == 0 ? 16384u : 8192u;
+                    const float* src = phase == 0 ? W.b1 : W.b2;
+                    for (int s = 0; s < ksteps; ++s, ++it) {
+                        const int st = it % TCB_STAGES;
+                        const uint32_t use = it / TCB_STAGES;
+                        if (use > 0) mbar_wait(&sm.empty[st], (use - 1) & 1);
+                        mbar_expect_tx(&sm.full[st], tile_bytes);
+                        bulk_g2s(sm.stage[st], src + (size_t)s * (tile_bytes / 4), tile_bytes, &sm.full[st]);
+                    }
+                }
+        }
+        return;
+    }
     const uint32_t idesc1 = tc5_idesc(256), idesc2 = tc5_idesc(128);
+    if (warp == 5) {
+        // ---- MMA issuer: its own warp, so that no row thread parked in mbarrier.try_wait shares a warp with it
+        if (tid == TCB_THREADS + 32) {
+            uint32_t it = 0;
+            for (int step = 0; step < in.T; ++step)
+                for (int phase = 0; phase < 2; ++phase) {
+                    const int N = phase == 0 ? 256 : 128;
+                    mbar_wait(&sm.ready[phase], step & 1);             // operands of this phase are in place
+                    tc5_fence_after();
+                    const uint32_t d = tmem + (phase == 0 ? 0 : TCB_HP);
+                    const uint32_t idesc = phase == 0 ? idesc1 : idesc2;
+                    for (int s = 0; s < ksteps; ++s, ++it) {
+                        const int st = it % TCB_STAGES;
+                        mbar_wait(&sm.full[st], (it / TCB_STAGES) & 1);
+                        tc5_fence_after();
+                        const uint64_t dbh = tc5_desc(sm.stage[st], N * 16, 128);
+                        const uint64_t dbl = tc5_desc(sm.stage[st] + 2 * N * 4, N * 16, 128);
+                        if (s < kx) {
+                            const uint64_t dah = tc5_desc(sm.ax_hi[2 * s], 2048, 128), dal = tc5_desc(sm.ax_lo[2 * s], 2048, 128);
+                            tc5_mma(d, dal, dbh, idesc, s > 0);
+                            tc5_mma(d, dah, dbl, idesc, 1);
+                            tc5_mma(d, dah, dbh, idesc, 1);
+                        } else {
+                            const uint32_t ah = tmem + TCB_TMEM_AH + 8 * (s - kx), al = tmem + TCB_TMEM_AL + 8 * (s - kx);
+                            tcb_mma_ts(d, al, dbh, idesc, 1);
+                            tcb_mma_ts(d, ah, dbl, idesc, 1);
+                            tcb_mma_ts(d, ah, dbh, idesc, 1);
+                        }
+                        tc5_commit(&sm.empty[st]);                     // stage reusable once these MMAs have read it
+                    }
+                    tc5_commit(&sm.done[phase]);
+                }
+        }
+        return;
+    }
+    const uint32_t t_row = tmem + ((uint32_t)(warp * 32) << 16);
     // h = 0 in the TMEM A operand
     {
         float zero[16];
@@ -119,7 +179,6 @@ gru_tcb_kernel(GruTcbW W, K2In in, long long n, DecodeParams dp, K2Out out) {
         const long long ns = in.n_samples[sid];
         cur.init(in, sid, ns >= in.window ? (ns - in.window) / in.hop + 1 : 0);
     }
-    uint32_t prod_it = 0, cons_it = 0;              // running stage counters of the producer / issuer threads
 
 #pragma unroll 1
     for (int step = 0; step < in.T; ++step) {
@@ -136,45 +195,9 @@ gru_tcb_kernel(GruTcbW W, K2In in, long long n, DecodeParams dp, K2Out out) {
         }
         fence_proxy_async();
         tc5_fence_before();
-        __syncthreads();
+        mbar_arrive(&sm.ready[0]);                                     // x_t (and, from the previous step, h) are in place
 #pragma unroll 1
         for (int phase = 0; phase < 2; ++phase) {
-            const int N = phase == 0 ? 256 : 128;
-            const uint32_t tile_bytes = (uint32_t)N * 64u;                 // hi + lo: 2 * (2 chunks * N * 16 B)
-            if (tid == 32) {                                               // ---- weight producer
-                const float* src = phase == 0 ? W.b1 : W.b2;
-                for (int s = 0; s < ksteps; ++s, ++prod_it) {
-                    const int st = prod_it % TCB_STAGES;
-                    const uint32_t use = prod_it / TCB_STAGES;
-                    if (use > 0) mbar_wait(&sm.empty[st], (use - 1) & 1);
-                    mbar_expect_tx(&sm.full[st], tile_bytes);
-                    bulk_g2s(sm.stage[st], src + (size_t)s * (tile_bytes / 4), tile_bytes, &sm.full[st]);
-                }
-            } else if (tid == 0) {                                         // ---- MMA issuer
-                tc5_fence_after();
-                const uint32_t d = tmem + (phase == 0 ? 0 : TCB_HP);
-                const uint32_t idesc = phase == 0 ? idesc1 : idesc2;
-                for (int s = 0; s < ksteps; ++s, ++cons_it) {
-                    const int st = cons_it % TCB_STAGES;
-                    mbar_wait(&sm.full[st], (cons_it / TCB_STAGES) & 1);
-                    tc5_fence_after();
-                    const uint64_t dbh = tc5_desc(sm.stage[st], N * 16, 128);
-                    const uint64_t dbl = tc5_desc(sm.stage[st] + 2 * N * 4, N * 16, 128);
-                    if (s < kx) {
-                        const uint64_t dah = tc5_desc(sm.ax_hi[2 * s], 2048, 128), dal = tc5_desc(sm.ax_lo[2 * s], 2048, 128);
-                        tc5_mma(d, dal, dbh, idesc, s > 0);
-                        tc5_mma(d, dah, dbl, idesc, 1);
-                        tc5_mma(d, dah, dbh, idesc, 1);
-                    } else {
-                        const uint32_t ah = tmem + TCB_TMEM_AH + 8 * (s - kx), al = tmem + TCB_TMEM_AL + 8 * (s - kx);
-                        tcb_mma_ts(d, al, dbh, idesc, 1);
-                        tcb_mma_ts(d, ah, dbl, idesc, 1);
-                        tcb_mma_ts(d, ah, dbh, idesc, 1);
-                    }
-                    tc5_commit(&sm.empty[st]);                             // stage reusable once these MMAs have read it
-                }
-                tc5_commit(&sm.done[phase]);
-            }
             mbar_wait(&sm.done[phase], step & 1);
             tc5_fence_after();
             if (phase == 0) {
@@ -205,14 +228,14 @@ gru_tcb_kernel(GruTcbW W, K2In in, long long n, DecodeParams dp, K2Out out) {
             }
             tcb_wait_st();
             tc5_fence_before();
-            __syncthreads();
+            if (phase == 0) mbar_arrive(&sm.ready[1]);                 // r*h is in place; phase 1's h is announced with the next x_t
         }
     }
     float logit = W.bd;
     for (int j = 0; j < W.H; ++j) logit = fmaf(sm.hs[j][tid], sm.wd[j], logit);
     epilogue(logit, valid, i, sid, dp, out);
     tc5_fence_before();
-    __syncthreads();
+    tcb_row_sync();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512) : "memory");
 }
 
