@@ -194,6 +194,9 @@ int pb_debug_force_generic(pb_handle* h, int on);
 /* Test hook for the default network (H=20, F=13): 0 = automatic choice (warp-per-stream kernel for small
  * batches, tensor-core scan otherwise), 1 = CUDA-core thread-per-stream kernel, 2 = tensor-core kernel. */
 int pb_debug_gru_mode(pb_handle* h, int mode);
+/* Test/profiling hook: the first call arms, later calls read four device-side cycle counters of the wide-network
+ * tensor-core kernel's MMA-issuer thread (operand wait, weight-tile wait, issue, total) for CTA 0. */
+int pb_debug_counters(pb_handle* h, long long out[4]);
 
 const char* pb_last_error(void);
 int pb_abi_version(void);

@@ -63,6 +63,7 @@ SYMBOLS = {
     'pb_set_cdf': (C.c_int, [_VP, _VP, _I64]),
     'pb_debug_force_generic': (C.c_int, [_VP, C.c_int]),
     'pb_debug_gru_mode': (C.c_int, [_VP, C.c_int]),
+    'pb_debug_counters': (C.c_int, [_VP, C.POINTER(C.c_longlong)]),
     'pb_last_error': (C.c_char_p, []),
     'pb_abi_version': (C.c_int, []),
     'pb_build_info': (C.c_char_p, []),
@@ -298,6 +299,11 @@ class PreciseB200:
         check(self.lib.pb_update_host(self._h, vp(pcm_np), vp(ids_np), n, vp(raw_np), vp(conf_np), vp(fired_np),
                                       C.cast(C.byref(cnt), C.c_void_p)))
         return int(cnt.value)
+
+    def debug_counters(self):
+        out = (C.c_longlong * 4)()
+        check(self.lib.pb_debug_counters(self._h, out))
+        return list(out)
 
     def gru_mode(self, mode):
         check(self.lib.pb_debug_gru_mode(self._h, int(mode)))

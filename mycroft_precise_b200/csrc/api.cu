@@ -83,6 +83,7 @@ struct pb_handle {
     float *d_wcat = nullptr, *d_bias = nullptr, *d_wd = nullptr;
     float4* d_bfrag = nullptr;       // tensor-core GRU: pre-split, fragment-ordered weights
     float *d_mma_bias = nullptr, *d_mma_wd = nullptr;
+    long long* d_dbg = nullptr;       // optional debug counters (pb_debug_counters)
     float *d_tcb = nullptr;           // tcgen05 wide-network GRU: [b1 tiles | b2 tiles | bias(384) | wd(128)]
     bool tcb_ok = false;
     int tcb_kx = 0;
@@ -222,7 +223,7 @@ PB_API void pb_destroy(pb_handle* h) {
     cudaFree(h->d_tw_stage); cudaFree(h->d_tw_post); cudaFree(h->d_cd); cudaFree(h->d_ptab); cudaFree(h->d_ctab); cudaFree(h->d_dct_t);
     cudaFree(h->st.n_samples); cudaFree(h->st.tail); cudaFree(h->st.ring); cudaFree(h->st.trig);
     cudaFree(h->d_wcat); cudaFree(h->d_bias); cudaFree(h->d_wd); cudaFree(h->d_count);
-    cudaFree(h->d_bfrag); cudaFree(h->d_mma_bias); cudaFree(h->d_mma_wd); cudaFree(h->d_tc5); cudaFree(h->d_tcb);
+    cudaFree(h->d_bfrag); cudaFree(h->d_mma_bias); cudaFree(h->d_mma_wd); cudaFree(h->d_tc5); cudaFree(h->d_tcb); cudaFree(h->d_dbg);
     if (h->h_count_pinned) cudaFreeHost(h->h_count_pinned);
     for (int i = 0; i < HOST_PIPE; ++i) {
         cudaFree(h->d_stage_pcm[i]); cudaFree(h->d_stage_ids[i]); cudaFree(h->d_stage_raw[i]);
@@ -572,6 +573,15 @@ struct ProfScope {
     ~ProfScope() { if (idx >= 0) cudaEventRecord(h->prof[slot].ev[idx + 1], s); }
 };
 
+PB_API int pb_debug_counters(pb_handle* h, long long out[4]) {
+    if (!h || !out) return fail(PB_ERR_INVALID, "null argument");
+    CK(cudaSetDevice(h->cfg.device));
+    if (!h->d_dbg) { CK(cudaMalloc((void**)&h->d_dbg, 4 * sizeof(long long))); CK(cudaMemset(h->d_dbg, 0, 4 * sizeof(long long))); }
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(out, h->d_dbg, 4 * sizeof(long long), cudaMemcpyDeviceToHost));
+    return PB_OK;
+}
+
 PB_API int pb_debug_gru_mode(pb_handle* h, int mode) { if (!h) return fail(PB_ERR_INVALID, "null handle"); h->gru_mode = mode; return PB_OK; }
 
 PB_API int pb_debug_force_generic(pb_handle* h, int on) { if (!h) return fail(PB_ERR_INVALID, "null handle"); h->force_generic = on != 0; return PB_OK; }
@@ -701,7 +711,8 @@ static int launch_gru(pb_handle* h, const K2In& in, bool ring, int64_t n, const 
         const int ks = h->tcb_kx + TCB_KH;
         w.b1 = h->d_tcb; w.b2 = w.b1 + (size_t)ks * 4096; w.bias = w.b2 + (size_t)ks * 2048; w.wd = w.bias + 3 * TCB_HP;
         w.bd = h->bd; w.kx = h->tcb_kx; w.F = h->feat; w.H = h->cfg.hidden; w.act = h->cfg.activation; w.ract = h->cfg.recurrent_activation;
-        const int grid = (int)((n + TCB_THREADS - 1) / TCB_THREADS);
+        w.dbg = h->d_dbg;
+        const int grid = (int)((n + 127) / 128);
         const size_t smem = sizeof(TcbSmem) + 128;
         if (ring) gru_tcb_kernel<true><<<grid, TCB_BLOCK, smem, s>>>(w, in, n, dp, o);
         else gru_tcb_kernel<false><<<grid, TCB_BLOCK, smem, s>>>(w, in, n, dp, o);
