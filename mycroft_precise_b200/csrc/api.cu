@@ -692,8 +692,8 @@ static int launch_gru(pb_handle* h, const K2In& in, bool ring, int64_t n, const 
         w.bias = w.b2_lo + sz2; w.wd = w.bias + 80; w.bd = h->bd;
         const int grid = (int)((n + TC5_THREADS - 1) / TC5_THREADS);
         const size_t smem = sizeof(Tc5Smem) + 128;
-        if (ring) gru_tc5_kernel<20, 13, true><<<grid, TC5_THREADS, smem, s>>>(w, in, n, dp, o);
-        else gru_tc5_kernel<20, 13, false><<<grid, TC5_THREADS, smem, s>>>(w, in, n, dp, o);
+        if (ring) gru_tc5_kernel<20, 13, true><<<grid, TC5_BLOCK, smem, s>>>(w, in, n, dp, o);
+        else gru_tc5_kernel<20, 13, false><<<grid, TC5_BLOCK, smem, s>>>(w, in, n, dp, o);
     } else if (h->small_path && h->gru_mode != 1) {               // tensor-core scan (mma.sync TF32 x3)
         GruMmaW w;
         w.bfrag = h->d_bfrag; w.bias = h->d_mma_bias; w.wd = h->d_mma_wd; w.bd = h->bd;

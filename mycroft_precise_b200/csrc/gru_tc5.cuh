@@ -22,7 +22,8 @@
 
 namespace pb {
 
-constexpr int TC5_THREADS = 128;
+constexpr int TC5_THREADS = 128;     // row threads
+constexpr int TC5_BLOCK = 160;       // + the MMA-issuer warp (a row thread parked in mbarrier.try_wait must not share a warp with it)
 constexpr int TC5_KXC = 4;           // x: 16 k's = 4 chunks of 4
 constexpr int TC5_KHC = 6;           // h: 24 k's = 6 chunks
 constexpr int TC5_N1 = 48;           // z | r  (24 + 24)
@@ -46,7 +47,7 @@ struct Tc5Smem {
     float b2_hi[10][TC5_N2][4], b2_lo[10][TC5_N2][4];
     float bias[TC5_N1 + TC5_N2];
     float wd[24];
-    unsigned long long bar[2];
+    unsigned long long bar[2], ready[2];
     uint32_t tmem_base;
 };
 
@@ -95,18 +96,22 @@ __device__ __forceinline__ void tc5_put4(float (*hi)[4], float (*lo)[4], int row
 }
 
 template <int H, int F, bool RING>
-__global__ void __launch_bounds__(TC5_THREADS)
+__global__ void __launch_bounds__(TC5_BLOCK)
 gru_tc5_kernel(GruTc5W W, K2In in, long long n, DecodeParams dp, K2Out out) {
     static_assert(H <= 24 && F <= 16, "operand tiles are sized for the default network");
     extern __shared__ __align__(128) unsigned char tc5_raw[];
     Tc5Smem& sm = *reinterpret_cast<Tc5Smem*>(tc5_raw);
     const int tid = threadIdx.x, warp = tid >> 5;
     // ---- one-time setup: weights to shared memory, barriers, TMEM
-    for (int e = tid; e < 10 * TC5_N1 * 4; e += TC5_THREADS) { (&sm.b1_hi[0][0][0])[e] = __ldg(W.b1_hi + e); (&sm.b1_lo[0][0][0])[e] = __ldg(W.b1_lo + e); }
-    for (int e = tid; e < 10 * TC5_N2 * 4; e += TC5_THREADS) { (&sm.b2_hi[0][0][0])[e] = __ldg(W.b2_hi + e); (&sm.b2_lo[0][0][0])[e] = __ldg(W.b2_lo + e); }
-    for (int e = tid; e < TC5_N1 + TC5_N2; e += TC5_THREADS) sm.bias[e] = __ldg(W.bias + e);
+    for (int e = tid; e < 10 * TC5_N1 * 4; e += TC5_BLOCK) { (&sm.b1_hi[0][0][0])[e] = __ldg(W.b1_hi + e); (&sm.b1_lo[0][0][0])[e] = __ldg(W.b1_lo + e); }
+    for (int e = tid; e < 10 * TC5_N2 * 4; e += TC5_BLOCK) { (&sm.b2_hi[0][0][0])[e] = __ldg(W.b2_hi + e); (&sm.b2_lo[0][0][0])[e] = __ldg(W.b2_lo + e); }
+    for (int e = tid; e < TC5_N1 + TC5_N2; e += TC5_BLOCK) sm.bias[e] = __ldg(W.bias + e);
     if (tid < 24) sm.wd[tid] = __ldg(W.wd + tid);
-    if (tid == 0) { mbar_init(&sm.bar[0], 1); mbar_init(&sm.bar[1], 1); fence_mbar_init(); }
+    if (tid == 0) {
+        mbar_init(&sm.bar[0], 1); mbar_init(&sm.bar[1], 1);
+        mbar_init(&sm.ready[0], TC5_THREADS); mbar_init(&sm.ready[1], TC5_THREADS);
+        fence_mbar_init();
+    }
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm.tmem_base)), "n"(TC5_TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -116,8 +121,51 @@ gru_tc5_kernel(GruTc5W W, K2In in, long long n, DecodeParams dp, K2Out out) {
     __syncthreads();
     tc5_fence_after();
     const uint32_t tmem = sm.tmem_base;
-    const uint32_t t_row = tmem + ((uint32_t)(warp * 32) << 16);       // this warp's 32 TMEM lanes
     const uint32_t idesc1 = tc5_idesc(TC5_N1), idesc2 = tc5_idesc(TC5_N2);
+    if (warp == 4) {
+        // ---- MMA issuer (one lane), free-running; hands results back through tcgen05.commit -> mbarrier
+        if (tid == TC5_THREADS) {
+#pragma unroll 1
+            for (int step = 0; step < in.T; ++step) {
+                mbar_wait(&sm.ready[0], step & 1);
+                tc5_fence_after();
+                // D1 = [x|h] . [Wz|Wr]
+#pragma unroll 1
+                for (int s = 0; s < 5; ++s) {
+                    const float* a_hi = s < 2 ? &sm.ax_hi[2 * s][0][0] : &sm.ah_hi[2 * (s - 2)][0][0];
+                    const float* a_lo = s < 2 ? &sm.ax_lo[2 * s][0][0] : &sm.ah_lo[2 * (s - 2)][0][0];
+                    const uint64_t dah = tc5_desc(a_hi, 2048, 128), dal = tc5_desc(a_lo, 2048, 128);
+                    const uint64_t dbh = tc5_desc(sm.b1_hi[2 * s], TC5_N1 * 16, 128), dbl = tc5_desc(sm.b1_lo[2 * s], TC5_N1 * 16, 128);
+                    tc5_mma(tmem, dal, dbh, idesc1, s > 0);
+                    tc5_mma(tmem, dah, dbl, idesc1, 1);
+                    tc5_mma(tmem, dah, dbh, idesc1, 1);
+                }
+                // D2 = x . Wh
+#pragma unroll 1
+                for (int s = 0; s < 2; ++s) {
+                    const uint64_t dah = tc5_desc(sm.ax_hi[2 * s], 2048, 128), dal = tc5_desc(sm.ax_lo[2 * s], 2048, 128);
+                    const uint64_t dbh = tc5_desc(sm.b2_hi[2 * s], TC5_N2 * 16, 128), dbl = tc5_desc(sm.b2_lo[2 * s], TC5_N2 * 16, 128);
+                    tc5_mma(tmem + TC5_N1, dal, dbh, idesc2, s > 0);
+                    tc5_mma(tmem + TC5_N1, dah, dbl, idesc2, 1);
+                    tc5_mma(tmem + TC5_N1, dah, dbh, idesc2, 1);
+                }
+                tc5_commit(&sm.bar[0]);
+                mbar_wait(&sm.ready[1], step & 1);
+                tc5_fence_after();
+#pragma unroll 1
+                for (int s = 2; s < 5; ++s) {
+                    const uint64_t dah = tc5_desc(sm.ah_hi[2 * (s - 2)], 2048, 128), dal = tc5_desc(sm.ah_lo[2 * (s - 2)], 2048, 128);
+                    const uint64_t dbh = tc5_desc(sm.b2_hi[2 * s], TC5_N2 * 16, 128), dbl = tc5_desc(sm.b2_lo[2 * s], TC5_N2 * 16, 128);
+                    tc5_mma(tmem + TC5_N1, dal, dbh, idesc2, 1);
+                    tc5_mma(tmem + TC5_N1, dah, dbl, idesc2, 1);
+                    tc5_mma(tmem + TC5_N1, dah, dbh, idesc2, 1);
+                }
+                tc5_commit(&sm.bar[1]);
+            }
+        }
+        return;
+    }
+    const uint32_t t_row = tmem + ((uint32_t)(warp * 32) << 16);       // this warp's 32 TMEM lanes
 
     const long long i = (long long)blockIdx.x * TC5_THREADS + tid;
     const bool valid = i < n;
@@ -151,31 +199,7 @@ gru_tc5_kernel(GruTc5W W, K2In in, long long n, DecodeParams dp, K2Out out) {
         for (int c = 0; c < TC5_KHC; ++c) tc5_put4(sm.ah_hi[c], sm.ah_lo[c], tid, h[4 * c], h[4 * c + 1], h[4 * c + 2], h[4 * c + 3]);
         fence_proxy_async();
         tc5_fence_before();
-        __syncthreads();
-        if (tid == 0) {
-            tc5_fence_after();
-            // D1 = [x|h] . [Wz|Wr]
-#pragma unroll
-            for (int s = 0; s < 5; ++s) {
-                const void* a_hi = s < 2 ? (const void*)sm.ax_hi[2 * s] : (const void*)sm.ah_hi[2 * (s - 2)];
-                const void* a_lo = s < 2 ? (const void*)sm.ax_lo[2 * s] : (const void*)sm.ah_lo[2 * (s - 2)];
-                const uint64_t dah = tc5_desc(a_hi, 2048, 128), dal = tc5_desc(a_lo, 2048, 128);
-                const uint64_t dbh = tc5_desc(sm.b1_hi[2 * s], TC5_N1 * 16, 128), dbl = tc5_desc(sm.b1_lo[2 * s], TC5_N1 * 16, 128);
-                tc5_mma(tmem, dal, dbh, idesc1, s > 0);
-                tc5_mma(tmem, dah, dbl, idesc1, 1);
-                tc5_mma(tmem, dah, dbh, idesc1, 1);
-            }
-            // D2 = x . Wh
-#pragma unroll
-            for (int s = 0; s < 2; ++s) {
-                const uint64_t dah = tc5_desc(sm.ax_hi[2 * s], 2048, 128), dal = tc5_desc(sm.ax_lo[2 * s], 2048, 128);
-                const uint64_t dbh = tc5_desc(sm.b2_hi[2 * s], TC5_N2 * 16, 128), dbl = tc5_desc(sm.b2_lo[2 * s], TC5_N2 * 16, 128);
-                tc5_mma(tmem + TC5_N1, dal, dbh, idesc2, s > 0);
-                tc5_mma(tmem + TC5_N1, dah, dbl, idesc2, 1);
-                tc5_mma(tmem + TC5_N1, dah, dbh, idesc2, 1);
-            }
-            tc5_commit(&sm.bar[0]);
-        }
+        mbar_arrive(&sm.ready[0]);
         mbar_wait(&sm.bar[0], step & 1);
         tc5_fence_after();
         float z[24];
@@ -199,19 +223,7 @@ gru_tc5_kernel(GruTc5W W, K2In in, long long n, DecodeParams dp, K2Out out) {
         }
         fence_proxy_async();
         tc5_fence_before();
-        __syncthreads();
-        if (tid == 0) {
-            tc5_fence_after();
-#pragma unroll
-            for (int s = 2; s < 5; ++s) {
-                const uint64_t dah = tc5_desc(sm.ah_hi[2 * (s - 2)], 2048, 128), dal = tc5_desc(sm.ah_lo[2 * (s - 2)], 2048, 128);
-                const uint64_t dbh = tc5_desc(sm.b2_hi[2 * s], TC5_N2 * 16, 128), dbl = tc5_desc(sm.b2_lo[2 * s], TC5_N2 * 16, 128);
-                tc5_mma(tmem + TC5_N1, dal, dbh, idesc2, 1);
-                tc5_mma(tmem + TC5_N1, dah, dbl, idesc2, 1);
-                tc5_mma(tmem + TC5_N1, dah, dbh, idesc2, 1);
-            }
-            tc5_commit(&sm.bar[1]);
-        }
+        mbar_arrive(&sm.ready[1]);
         mbar_wait(&sm.bar[1], step & 1);
         tc5_fence_after();
         {
@@ -231,7 +243,7 @@ gru_tc5_kernel(GruTc5W W, K2In in, long long n, DecodeParams dp, K2Out out) {
     for (int j = 0; j < H; ++j) logit = fmaf(h[j], sm.wd[j], logit);
     epilogue(logit, valid, i, sid, dp, out);
     tc5_fence_before();
-    __syncthreads();
+    asm volatile("bar.sync 1, 128;" ::: "memory");
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TC5_TMEM_COLS) : "memory");
 }
 
