@@ -43,6 +43,7 @@ static int fail(int code, const char* fmt, ...) {
 constexpr int N_PROFILE_SLOTS = 4;
 constexpr int PROFILE_POOL = 2048;
 constexpr int K2_WARP_PATH_MAX = 8192;       // streams: below this the warp-per-stream GRU kernel wins (latency-bound regime)
+constexpr int64_t HOST_ZERO_COPY_MAX = 64;  // streams: at or below this pb_update_host works in place on pinned host buffers
 constexpr int HOST_PIPE = 3;                 // internal streams of pb_update_host
 constexpr int64_t HOST_SUB_BATCH = 16384;    // streams per pipelined sub-batch (32 MiB of PCM at 1024 samples)
 
@@ -909,6 +910,25 @@ PB_API int pb_update_host(pb_handle* h, const int16_t* h_pcm, const int32_t* h_i
     if (rc != PB_OK) return rc;
     const int64_t sb = std::min<int64_t>(HOST_SUB_BATCH, h->cfg.max_streams);
     const int chunk = h->cfg.chunk_samples;
+    // ---- latency path (BASELINE configs[4]): a handful of streams in pinned host memory.  With unified addressing the
+    // kernels read the PCM and write the results through the mapped host pointers directly: two launches and one
+    // synchronisation instead of three staged copies.
+    if (n <= HOST_ZERO_COPY_MAX) {
+        auto pinned = [](const void* p) {
+            if (!p) return true;
+            cudaPointerAttributes a;
+            if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+            return a.type == cudaMemoryTypeHost;
+        };
+        if (pinned(h_pcm) && pinned(h_ids) && pinned(h_raw) && pinned(h_conf) && pinned(h_fired)) {
+            *h->h_count_pinned = 0;
+            rc = pb_update(h, h_pcm, h_ids, n, h_raw, h_conf, h_fired, h->h_count_pinned, h->pipe[0]);
+            if (rc != PB_OK) return rc;
+            CK(cudaStreamSynchronize(h->pipe[0]));
+            if (h_count) *h_count = *h->h_count_pinned;
+            return PB_OK;
+        }
+    }
     // the counter is zeroed on pipe 0; the other pipes wait for that, pipe 0 waits for them at the end,
     // so the whole tick costs one host synchronisation
     CK(cudaMemsetAsync(h->d_count, 0, sizeof(unsigned long long), h->pipe[0]));

@@ -179,16 +179,23 @@ class B200Engine(Engine):
                                 device=self.device, activation=m.activation,
                                 recurrent_activation=m.recurrent_activation)
         self.core.load_weights(m.kernel, m.recurrent, m.bias, m.dense_w, m.dense_b)
-        self._conf = np.zeros(1, dtype=np.float64)
+        # pinned staging: pb_update_host then works in place on these buffers (no staged copies)
+        from .core import pinned_empty
+        self._pcm, self._pcm_p = pinned_empty((1, self.chunk_size // 2), np.int16)
+        self._conf, self._conf_p = pinned_empty((1,), np.float64)
 
     def stop(self):
         if self.core is not None:
+            from .core import pinned_free
             self.core.close()
             self.core = None
+            pinned_free(self._pcm_p)
+            pinned_free(self._conf_p)
+            self._pcm = self._conf = None
 
     def get_prediction(self, chunk):
         if len(chunk) != self.chunk_size:
             raise ValueError('Invalid chunk size: ' + str(len(chunk)))
-        pcm = np.frombuffer(chunk, dtype='<i2').reshape(1, -1)
-        self.core.update_host(pcm, self._conf)
+        self._pcm[0, :] = np.frombuffer(chunk, dtype='<i2')
+        self.core.update_host(self._pcm, self._conf)
         return float(self._conf[0])

@@ -300,7 +300,7 @@ def test_decode_vs_reference_golden(core, golden_dir):
 
 
 # ------------------------------------------------------------------------------------------ stateful
-def _run_gpu_streams(m, model, pcm, chunk, pr=None, sens=0.5, lvl=3, host=False):
+def _run_gpu_streams(m, model, pcm, chunk, pr=None, sens=0.5, lvl=3, host=False, pinned=False):
     S = pcm.shape[0]
     K = pcm.shape[1] // chunk
     sb = m.StreamBatch(model, S, params=pr, chunk_samples=chunk, sensitivity=sens, trigger_level=lvl)
@@ -311,7 +311,15 @@ def _run_gpu_streams(m, model, pcm, chunk, pr=None, sens=0.5, lvl=3, host=False)
     counts = 0
     for k in range(K):
         c = np.ascontiguousarray(pcm[:, k * chunk:(k + 1) * chunk])
-        if host:
+        if host and pinned:
+            from mycroft_precise_b200.core import pinned_empty, pinned_free
+            pc, p0 = pinned_empty(c.shape, np.int16); pc[:] = c
+            r, p1 = pinned_empty((S,), np.float32); cf, p2 = pinned_empty((S,), np.float64); f, p3 = pinned_empty((S,), np.uint8)
+            counts += sb.update_host(pc, cf, r, f)
+            raw[:, k], conf[:, k], fired[:, k] = r, cf, f.astype(bool)
+            for p in (p0, p1, p2, p3):
+                pinned_free(p)
+        elif host:
             r = np.zeros(S, np.float32); cf = np.zeros(S); f = np.zeros(S, np.uint8)
             counts += sb.update_host(c, cf, r, f)
             raw[:, k], conf[:, k], fired[:, k] = r, cf, f.astype(bool)
@@ -380,11 +388,13 @@ def test_stream_host_path_equals_device_path():
     S, K, chunk = 50, 14, 1024
     pcm = noise(S, K * chunk, seed=9)
     model = m.GruModel.random(13, 20, seed=1, scale=0.1)
+    model.dense_b = 3.0
     a = _run_gpu_streams(m, model, pcm, chunk)
-    b = _run_gpu_streams(m, model, pcm, chunk, host=True)
-    for x, y in zip(a[:4], b[:4]):
-        assert np.array_equal(x, y)
-    assert a[4] == b[4]
+    for pinned in (False, True):                    # staged copies / in-place on pinned buffers (n <= 64)
+        b = _run_gpu_streams(m, model, pcm, chunk, host=True, pinned=pinned)
+        for x, y in zip(a[:4], b[:4]):
+            assert np.array_equal(x, y)
+        assert a[4] == b[4] and a[4] > 0
 
 
 def test_stream_ids_subset_and_clear():
