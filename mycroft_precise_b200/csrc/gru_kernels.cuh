@@ -309,13 +309,39 @@ gru_warp_kernel(const __grid_constant__ GruSmallW<H, F> P, K2In in, long long n,
     }
     RingCursor cur;
     if (RING) cur.init(in, sid, released);
+    // the whole window is fetched up front, one row per lane (T <= 32), so the scan itself never waits on memory:
+    // step t takes its x_t from lane t with shuffles
+    const bool prefetched = in.T <= 32;
+    float xrow[F];
+#pragma unroll
+    for (int f = 0; f < F; ++f) xrow[f] = 0.f;
+    if (prefetched) {
+        const float* row = nullptr;
+        if (lane < in.T) {
+            if (RING) {
+                const int t = lane;
+                if (t >= cur.lead) { int sl = cur.slot + t; sl = sl >= cur.rows ? sl - cur.rows : sl; row = cur.base + sl * cur.stride; }
+            } else {
+                row = in.inputs + (i * in.T + lane) * F;
+            }
+        }
+        if (row != nullptr) {
+#pragma unroll
+            for (int f = 0; f < F; ++f) xrow[f] = __ldg(row + f);
+        }
+    }
     float h = 0.f;
 #pragma unroll 1
     for (int t = 0; t < in.T; ++t) {
         float x[F];
-        const float* row = RING ? cur.next(t) : in.inputs + (i * in.T + t) * F;
+        if (prefetched) {
 #pragma unroll
-        for (int f = 0; f < F; ++f) x[f] = row ? __ldg(row + f) : 0.f;          // same address in every lane: broadcast
+            for (int f = 0; f < F; ++f) x[f] = __shfl_sync(0xffffffffu, xrow[f], t);
+        } else {
+            const float* row = RING ? cur.next(t) : in.inputs + (i * in.T + t) * F;
+#pragma unroll
+            for (int f = 0; f < F; ++f) x[f] = row ? __ldg(row + f) : 0.f;          // same address in every lane: broadcast
+        }
         float az[4] = {bz, 0.f, 0.f, 0.f}, ar[4] = {br, 0.f, 0.f, 0.f}, ah[4] = {bh, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int f = 0; f < F; ++f) {
