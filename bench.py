@@ -425,7 +425,7 @@ def run_b200(args):
                      'algorithmic_bytes_per_launch': S * ALG_BYTES_PER_UPDATE, 'ms_per_launch': k1_ms, 'launches': klaunch[0]},
         'roofline_gru': {'kernel': 'gru_mma_kernel<20,13> (K2+K3; mma.sync TF32x3)', 'bound': 'fp32-fma (algorithmic FLOP vs CUDA-core fp32 peak)', 'achieved': S * ALG_FLOP_PER_UPDATE_GRU / (k2_ms * 1e-3) / 1e12 if k2_ms > 0 else None,
                          'peak': FP32_PEAK_TFLOPS, 'unit': 'TFLOP/s', 'frac': (S * ALG_FLOP_PER_UPDATE_GRU / (k2_ms * 1e-3) / 1e12 / FP32_PEAK_TFLOPS) if k2_ms > 0 else None,
-                         'of': 'nominal 148 SM x 128 lanes x 2 x 1.965 GHz', 'ms_per_launch': k2_ms, 'launches': klaunch[1]},
+                         'of': 'nominal 148 SM x 128 lanes x 2 x 1.965 GHz', 'ms_per_launch': k2_ms, 'launches': klaunch[1], 'input_projection_ms_per_launch': (kms[3] / klaunch[3] if klaunch[3] else None)},
         'e2e': e2e,
         'gpu_launches': int(sum(klaunch)),
         'cpu_baseline': ({'value': cpu[0], 'unit': 'stream-updates/s', 'cores': cpu[1], 'kind': 'port', 'sample': cpu[2]} if cpu else None),

@@ -59,6 +59,9 @@ struct pb_handle {
     int sm_count = 148;
     // derived
     int used = 0, n_bins = 0, n_out = 0, feat = 0, ring_rows = 0, row_stride = 0, tail_cap = 0, max_new = 0;
+    int proj_off = 0;
+    bool proj_dirty = true;          // some ring rows lack a valid cached projection (weights changed / projection skipped)
+    float *d_proj_w = nullptr, *d_proj_b = nullptr;
     size_t k1_batch_smem = 0, k1_stream_smem = 0, k1_fast_smem = 0;
     bool force_generic = false;      // tests: exercise the generic kernels on the aligned geometry
     bool fast_ok = false;            // aligned geometry: warp-autonomous kernels (mfcc_fast.cuh)
@@ -224,7 +227,7 @@ PB_API void pb_destroy(pb_handle* h) {
     cudaFree(h->d_tw_stage); cudaFree(h->d_tw_post); cudaFree(h->d_cd); cudaFree(h->d_ptab); cudaFree(h->d_ctab); cudaFree(h->d_dct_t);
     cudaFree(h->st.n_samples); cudaFree(h->st.tail); cudaFree(h->st.ring); cudaFree(h->st.trig);
     cudaFree(h->d_wcat); cudaFree(h->d_bias); cudaFree(h->d_wd); cudaFree(h->d_count);
-    cudaFree(h->d_bfrag); cudaFree(h->d_mma_bias); cudaFree(h->d_mma_wd); cudaFree(h->d_tc5); cudaFree(h->d_tcb); cudaFree(h->d_dbg);
+    cudaFree(h->d_bfrag); cudaFree(h->d_mma_bias); cudaFree(h->d_mma_wd); cudaFree(h->d_proj_w); cudaFree(h->d_proj_b); cudaFree(h->d_tc5); cudaFree(h->d_tcb); cudaFree(h->d_dbg);
     if (h->h_count_pinned) cudaFreeHost(h->h_count_pinned);
     for (int i = 0; i < HOST_PIPE; ++i) {
         cudaFree(h->d_stage_pcm[i]); cudaFree(h->d_stage_ids[i]); cudaFree(h->d_stage_raw[i]);
@@ -270,6 +273,9 @@ PB_API int pb_create(const pb_config* cfg, pb_handle** out) {
     h->n_out = c.vectorizer == PB_VEC_MELS ? c.n_filt : std::min(c.n_filt, c.n_mfcc);
     h->feat = h->n_out * (c.use_delta ? 2 : 1);
     h->row_stride = (h->n_out + 3) & ~3;
+    // default-sized networks cache the input projection of every frame behind its MFCC row (gru_mma_kernel<.., PROJ>)
+    h->proj_off = 0;
+    if (c.hidden == 20 && h->n_out == 13 && !c.use_delta && c.vectorizer == PB_VEC_MFCCS) { h->proj_off = h->row_stride; h->row_stride += PROJ_COLS; }
     h->ring_rows = c.n_features + (c.window_samples - h->used) / c.hop_samples + 2;
     h->tail_cap = (h->used + 7) & ~7;            // rows stay 16-byte aligned
     h->max_new = c.chunk_samples / c.hop_samples + 2;
@@ -462,6 +468,17 @@ PB_API int pb_load_weights(pb_handle* h, const float* kernel, const float* recur
                     const float b0h = tf32(b[0]), b1h = tf32(b[1]);
                     bf[((size_t)kt * MMA_NT + nt) * 32 + lane] = make_float4(b0h, b1h, tf32(b[0] - b0h), tf32(b[1] - b1h));
                 }
+        {   // input projection table: wx[f][col], col = gate * 24 + unit (same column order as the accumulator tiles)
+            std::vector<float> pw((size_t)F * PROJ_COLS, 0.f), pbias(PROJ_COLS, 0.f);
+            for (int gate = 0; gate < 3; ++gate)
+                for (int u = 0; u < H; ++u) {
+                    pbias[gate * 24 + u] = bias[gate * H + u];
+                    for (int f = 0; f < F; ++f) pw[(size_t)f * PROJ_COLS + gate * 24 + u] = kernel[(size_t)f * H3 + gate * H + u];
+                }
+            cudaFree(h->d_proj_w); cudaFree(h->d_proj_b); h->d_proj_w = h->d_proj_b = nullptr;
+            CK(upload(&h->d_proj_w, pw));
+            CK(upload(&h->d_proj_b, pbias));
+        }
         std::vector<float> mb(72, 0.f), mw(24, 0.f);
         for (int gate = 0; gate < 3; ++gate)
             for (int u = 0; u < H; ++u) mb[gate * 24 + u] = bias[gate * H + u];
@@ -547,6 +564,7 @@ PB_API int pb_load_weights(pb_handle* h, const float* kernel, const float* recur
         CK(cudaFuncSetAttribute(gru_tiled_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
     h->have_weights = true;
+    h->proj_dirty = true;
     return PB_OK;
 }
 
@@ -700,8 +718,9 @@ static int launch_gru(pb_handle* h, const K2In& in, bool ring, int64_t n, const 
         w.bfrag = h->d_bfrag; w.bias = h->d_mma_bias; w.wd = h->d_mma_wd; w.bd = h->bd;
         const int per_cta = (MMA_THREADS / 32) * 16 * MMA_MB;
         const int grid = (int)((n + per_cta - 1) / per_cta);
-        if (ring) gru_mma_kernel<20, 13, true><<<grid, MMA_THREADS, 0, s>>>(w, in, n, dp, o);
-        else gru_mma_kernel<20, 13, false><<<grid, MMA_THREADS, 0, s>>>(w, in, n, dp, o);
+        if (ring && in.proj_off > 0) gru_mma_kernel<20, 13, true, true><<<grid, MMA_THREADS, 0, s>>>(w, in, n, dp, o);
+        else if (ring) gru_mma_kernel<20, 13, true, false><<<grid, MMA_THREADS, 0, s>>>(w, in, n, dp, o);
+        else gru_mma_kernel<20, 13, false, false><<<grid, MMA_THREADS, 0, s>>>(w, in, n, dp, o);
     } else if (h->small_path) {
         const int per_cta = K2_SMALL_THREADS * K2_NS;
         const int grid = (int)((n + per_cta - 1) / per_cta);
@@ -792,6 +811,7 @@ PB_API int pb_update_vectors(pb_handle* h, const int16_t* d_pcm, const int32_t* 
     int rc = check_tick(h, d_pcm, n);
     if (rc != PB_OK || n == 0) return rc;
     CK(cudaSetDevice(h->cfg.device));
+    h->proj_dirty = true;
     return launch_stream_mfcc(h, d_pcm, d_ids, n, (cudaStream_t)stream);
 }
 
@@ -805,11 +825,34 @@ PB_API int pb_update(pb_handle* h, const int16_t* d_pcm, const int32_t* d_ids, i
     cudaStream_t s = (cudaStream_t)stream;
     rc = launch_stream_mfcc(h, d_pcm, d_ids, n, s);
     if (rc != PB_OK) return rc;
+    bool use_proj = false;
+    if (h->proj_off > 0 && h->small_path) {
+        if (n > K2_WARP_PATH_MAX && (h->gru_mode == 0 || h->gru_mode == 2)) {
+            ProfScope ps(h, 3, s);
+            if (h->proj_dirty) {                               // bring every ring row up to date once, then stay incremental
+                const long long rows = (long long)h->cfg.max_streams * h->ring_rows;
+                const int grid = (int)std::min<long long>((rows + PROJ_FRAMES_PER_CTA - 1) / PROJ_FRAMES_PER_CTA, (long long)h->sm_count * 16);
+                input_proj_all_kernel<13><<<grid, PROJ_COLS * PROJ_FRAMES_PER_CTA, 0, s>>>(h->d_proj_w, h->d_proj_b, rows, h->st.ring, h->row_stride, h->proj_off);
+                h->proj_dirty = false;
+            } else {
+                const long long items = (long long)n * h->max_new;
+                const int grid = (int)((items + PROJ_THREADS - 1) / PROJ_THREADS);     // 32 frames per warp
+                input_proj_kernel<13><<<grid, PROJ_THREADS, 0, s>>>(h->d_bfrag, h->d_proj_b, h->st.n_samples, d_ids, (int)n,
+                    h->cfg.chunk_samples, h->used, h->cfg.hop_samples, h->max_new, h->st.ring, h->ring_rows, h->row_stride, h->proj_off);
+            }
+            CK(cudaGetLastError());
+            use_proj = true;
+        } else {
+            h->proj_dirty = true;                              // this tick's frames get no projection
+        }
+    }
     K2In in{};
     in.ring = h->st.ring; in.n_samples = h->st.n_samples; in.ids = d_ids;
     in.ring_rows = h->ring_rows; in.row_stride = h->row_stride; in.window = h->cfg.window_samples; in.hop = h->cfg.hop_samples;
     in.T = h->cfg.n_features; in.F_base = h->n_out; in.use_delta = h->cfg.use_delta;
     K2Out o{};
+    in.proj_off = use_proj ? h->proj_off : 0;
+    in.chunk = h->cfg.chunk_samples;
     o.raw = d_raw; o.conf = d_conf; o.fired = d_fired; o.count = d_count; o.trig = h->st.trig;
     return launch_gru(h, in, true, n, decode_params(h), o, s);
 }

@@ -46,6 +46,8 @@ struct K2In {
     int ring_rows, row_stride, window, hop;
     int T, F_base;                   // F_base = MFCC width (without deltas)
     int use_delta;
+    int proj_off;                    // > 0: ring rows carry the cached input projection x.W + b (72 floats) at this offset
+    int chunk;                       // samples added by this tick (to tell which window rows are new)
 };
 
 __device__ __forceinline__ float hard_sigmoid(float x) { return fminf(fmaxf(fmaf(0.2f, x, 0.5f), 0.f), 1.f); }
@@ -432,7 +434,10 @@ __device__ __forceinline__ void split_tf32(const float (&v)[4], uint32_t (&hi)[4
     }
 }
 
-template <int H, int F, bool RING>
+// PROJ (stream mode): the input projection x_t.[Wz|Wr|Wh] + b of every frame was computed once when the frame was
+// produced (input_proj_kernel) and sits in the ring next to the MFCC row, so the scan only runs the recurrent products:
+// 162 instead of 270 HMMA per step on the pipe that bounds this kernel.
+template <int H, int F, bool RING, bool PROJ>
 __global__ void __launch_bounds__(MMA_THREADS, 3)
 gru_mma_kernel(GruMmaW W, K2In in, long long n, DecodeParams dp, K2Out out) {
     static_assert(H <= 24 && F <= 16, "tile counts are fixed");
@@ -477,51 +482,68 @@ gru_mma_kernel(GruMmaW W, K2In in, long long n, DecodeParams dp, K2Out out) {
 
 #pragma unroll 1
     for (int step = 0; step < in.T; ++step) {
-        // ---- A fragments of x_t: a0 = (row g, k 2t), a1 = (row g+8, k 2t), a2 = (row g, k 2t+1), a3 = (row g+8, k 2t+1)
-        uint32_t xh[MMA_MB][2][4], xl[MMA_MB][2][4];
-#pragma unroll
-        for (int mb = 0; mb < MMA_MB; ++mb) {
-            float xv[2][2][2];                               // [kt][hf][j]
-#pragma unroll
-            for (int hf = 0; hf < 2; ++hf) {
-                const float* row = nullptr;
-                if (ok[mb][hf]) row = RING ? cur[mb][hf].next(step) : in.inputs + (idx[mb][hf] * in.T + step) * F;
-#pragma unroll
-                for (int kt = 0; kt < 2; ++kt)
-#pragma unroll
-                    for (int j = 0; j < 2; ++j) {
-                        const int f = 8 * kt + 2 * t + j;
-                        xv[kt][hf][j] = (row != nullptr && f < F) ? __ldg(row + f) : 0.f;
-                    }
-            }
-#pragma unroll
-            for (int kt = 0; kt < 2; ++kt) {
-                const float v[4] = {xv[kt][0][0], xv[kt][1][0], xv[kt][0][1], xv[kt][1][1]};
-                split_tf32(v, xh[mb][kt], xl[mb][kt]);
-            }
-        }
-        // ---- accumulators start from the bias (column 2t + j of tile nt)
         float acc[MMA_MB][MMA_NT][4];
-#pragma unroll
-        for (int nt = 0; nt < MMA_NT; ++nt) {
-            const float b0 = sBias[8 * nt + 2 * t], b1 = sBias[8 * nt + 2 * t + 1];
-#pragma unroll
-            for (int mb = 0; mb < MMA_MB; ++mb) { acc[mb][nt][0] = b0; acc[mb][nt][1] = b1; acc[mb][nt][2] = b0; acc[mb][nt][3] = b1; }
-        }
-        // ---- x part for all three gates
-#pragma unroll
-        for (int kt = 0; kt < 2; ++kt) {
-            uint32_t ah[MMA_MB][4], al[MMA_MB][4];
+        if (PROJ) {
+            // ---- accumulators start from the cached projection (bias included); rows before the stream's first frame: bias
 #pragma unroll
             for (int mb = 0; mb < MMA_MB; ++mb)
 #pragma unroll
-                for (int e = 0; e < 4; ++e) { ah[mb][e] = xh[mb][kt][e]; al[mb][e] = xl[mb][kt][e]; }
+                for (int hf = 0; hf < 2; ++hf) {
+                    const float* row = ok[mb][hf] ? cur[mb][hf].next(step) : nullptr;
 #pragma unroll
-            for (int ng = 0; ng < MMA_NT; ng += 3) {
-                float4 w[3];
+                    for (int nt = 0; nt < MMA_NT; ++nt) {
+                        float2 v;
+                        if (row != nullptr) v = __ldg(reinterpret_cast<const float2*>(row + in.proj_off + 8 * nt + 2 * t));
+                        else v = make_float2(sBias[8 * nt + 2 * t], sBias[8 * nt + 2 * t + 1]);
+                        acc[mb][nt][2 * hf] = v.x; acc[mb][nt][2 * hf + 1] = v.y;
+                    }
+                }
+        } else {
+            // ---- A fragments of x_t: a0 = (row g, k 2t), a1 = (row g+8, k 2t), a2 = (row g, k 2t+1), a3 = (row g+8, k 2t+1)
+            uint32_t xh[MMA_MB][2][4], xl[MMA_MB][2][4];
 #pragma unroll
-                for (int q = 0; q < 3; ++q) w[q] = sB[(kt * MMA_NT + ng + q) * 32 + lane];
-                mma3_group<3>(acc, ng, ah, al, w);
+            for (int mb = 0; mb < MMA_MB; ++mb) {
+                float xv[2][2][2];                               // [kt][hf][j]
+#pragma unroll
+                for (int hf = 0; hf < 2; ++hf) {
+                    const float* row = nullptr;
+                    if (ok[mb][hf]) row = RING ? cur[mb][hf].next(step) : in.inputs + (idx[mb][hf] * in.T + step) * F;
+#pragma unroll
+                    for (int kt = 0; kt < 2; ++kt)
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) {
+                            const int f = 8 * kt + 2 * t + j;
+                            xv[kt][hf][j] = (row != nullptr && f < F) ? __ldg(row + f) : 0.f;
+                        }
+                }
+#pragma unroll
+                for (int kt = 0; kt < 2; ++kt) {
+                    const float v[4] = {xv[kt][0][0], xv[kt][1][0], xv[kt][0][1], xv[kt][1][1]};
+                    split_tf32(v, xh[mb][kt], xl[mb][kt]);
+                }
+            }
+            // ---- accumulators start from the bias (column 2t + j of tile nt)
+#pragma unroll
+            for (int nt = 0; nt < MMA_NT; ++nt) {
+                const float b0 = sBias[8 * nt + 2 * t], b1 = sBias[8 * nt + 2 * t + 1];
+#pragma unroll
+                for (int mb = 0; mb < MMA_MB; ++mb) { acc[mb][nt][0] = b0; acc[mb][nt][1] = b1; acc[mb][nt][2] = b0; acc[mb][nt][3] = b1; }
+            }
+            // ---- x part for all three gates
+#pragma unroll
+            for (int kt = 0; kt < 2; ++kt) {
+                uint32_t ah[MMA_MB][4], al[MMA_MB][4];
+#pragma unroll
+                for (int mb = 0; mb < MMA_MB; ++mb)
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) { ah[mb][e] = xh[mb][kt][e]; al[mb][e] = xl[mb][kt][e]; }
+#pragma unroll
+                for (int ng = 0; ng < MMA_NT; ng += 3) {
+                    float4 w[3];
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) w[q] = sB[(kt * MMA_NT + ng + q) * 32 + lane];
+                    mma3_group<3>(acc, ng, ah, al, w);
+                }
             }
         }
         // ---- h part for z and r
@@ -585,6 +607,123 @@ gru_mma_kernel(GruMmaW W, K2In in, long long n, DecodeParams dp, K2Out out) {
             part += __shfl_xor_sync(0xffffffffu, part, 2);
             epilogue(part + W.bd, t == 0 && ok[mb][hf], idx[mb][hf], sid[mb][hf], dp, out);
         }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Cached input projection (default network, stream mode): a = b + x . [Wz|Wr|Wh] for the 72 padded gate columns is kept
+// behind each MFCC row.  gru_mma_kernel<.., PROJ> computes it for the rows that enter a stream's window and stores it;
+// the kernel below refreshes every row after the cache was invalidated.
+constexpr int PROJ_COLS = 72;
+constexpr int PROJ_FRAMES_PER_CTA = 4;
+
+// Per-tick projection of the frames a tick has just produced, on the tensor cores: a warp takes 32 new frames as the rows
+// of two m16 blocks and runs the 3xTF32 x-part MMAs (2 k-tiles x 9 n-tiles) once per frame instead of once per scan step.
+// Register-lean (n-tiles in groups of three) so that one or two waves cover a whole tick: the kernel is latency-bound
+// (two dependent scattered reads per frame).  Items are ordered j-major (item = j * n + i): warps stay converged when the
+// streams run in lock step.
+constexpr int PROJ_THREADS = 128;
+
+template <int F>
+__global__ void __launch_bounds__(PROJ_THREADS, 6)
+input_proj_kernel(const float4* __restrict__ bfrag, const float* __restrict__ bias, const long long* __restrict__ n_samples,
+                  const int* __restrict__ ids, int n, int chunk, int need, int hop, int max_new,
+                  float* __restrict__ ring, int ring_rows, int row_stride, int proj_off) {
+    __shared__ float4 sB[2 * MMA_NT * 32];
+    __shared__ float sBias[PROJ_COLS];
+    for (int e = threadIdx.x; e < 2 * MMA_NT * 32; e += blockDim.x) sB[e] = __ldg(bfrag + e);
+    for (int e = threadIdx.x; e < PROJ_COLS; e += blockDim.x) sBias[e] = __ldg(bias + e);
+    __syncthreads();
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const long long items = (long long)n * max_new;
+    const long long base = ((long long)blockIdx.x * (PROJ_THREADS / 32) + (threadIdx.x >> 5)) * 32;
+    if (base >= items) return;
+    float* rows[MMA_MB][2];
+#pragma unroll
+    for (int mb = 0; mb < MMA_MB; ++mb)
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+            rows[mb][hf] = nullptr;
+            const long long item = base + 16 * mb + g + 8 * hf;
+            if (item < items) {
+                const int j = (int)(item / n);
+                const long long i = item - (long long)j * n;
+                const int sid = ids ? ids[i] : (int)i;
+                const long long n1 = n_samples[sid], n0 = n1 - chunk;
+                const long long c0 = n0 >= need ? (n0 - need) / hop + 1 : 0, c1 = n1 >= need ? (n1 - need) / hop + 1 : 0;
+                if (j < c1 - c0) rows[mb][hf] = ring + ((long long)sid * ring_rows + (int)((c0 + j) % ring_rows)) * row_stride;
+            }
+        }
+    uint32_t ah[2][MMA_MB][4], al[2][MMA_MB][4];
+#pragma unroll
+    for (int kt = 0; kt < 2; ++kt)
+#pragma unroll
+        for (int mb = 0; mb < MMA_MB; ++mb) {
+            float v[4];
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf)
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const int f = 8 * kt + 2 * t + j;
+                    v[2 * j + hf] = (rows[mb][hf] != nullptr && f < F) ? rows[mb][hf][f] : 0.f;     // a0,a1 = rows (g, g+8), k = 2t ; a2,a3: k = 2t+1
+                }
+            split_tf32(v, ah[kt][mb], al[kt][mb]);
+        }
+#pragma unroll 1
+    for (int ng = 0; ng < MMA_NT; ng += 3) {
+        float acc[MMA_MB][3][4];
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            const float b0 = sBias[8 * (ng + q) + 2 * t], b1 = sBias[8 * (ng + q) + 2 * t + 1];
+#pragma unroll
+            for (int mb = 0; mb < MMA_MB; ++mb) { acc[mb][q][0] = b0; acc[mb][q][1] = b1; acc[mb][q][2] = b0; acc[mb][q][3] = b1; }
+        }
+#pragma unroll
+        for (int kt = 0; kt < 2; ++kt) {
+            float4 w[3];
+#pragma unroll
+            for (int q = 0; q < 3; ++q) w[q] = sB[(kt * MMA_NT + ng + q) * 32 + lane];
+#pragma unroll
+            for (int q = 0; q < 3; ++q)
+#pragma unroll
+                for (int mb = 0; mb < MMA_MB; ++mb) mma_tf32(acc[mb][q], al[kt][mb], __float_as_uint(w[q].x), __float_as_uint(w[q].y));
+#pragma unroll
+            for (int q = 0; q < 3; ++q)
+#pragma unroll
+                for (int mb = 0; mb < MMA_MB; ++mb) mma_tf32(acc[mb][q], ah[kt][mb], __float_as_uint(w[q].z), __float_as_uint(w[q].w));
+#pragma unroll
+            for (int q = 0; q < 3; ++q)
+#pragma unroll
+                for (int mb = 0; mb < MMA_MB; ++mb) mma_tf32(acc[mb][q], ah[kt][mb], __float_as_uint(w[q].x), __float_as_uint(w[q].y));
+        }
+#pragma unroll
+        for (int mb = 0; mb < MMA_MB; ++mb)
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf)
+                if (rows[mb][hf] != nullptr) {
+#pragma unroll
+                    for (int q = 0; q < 3; ++q)
+                        *reinterpret_cast<float2*>(rows[mb][hf] + proj_off + 8 * (ng + q) + 2 * t) = make_float2(acc[mb][q][2 * hf], acc[mb][q][2 * hf + 1]);
+                }
+    }
+}
+
+// Same projection for EVERY ring row of every stream: run once after the weights change or after ticks that skipped the
+// per-tick projection (small batches served by the warp-per-stream kernel), so that cached projections are always valid.
+template <int F>
+__global__ void __launch_bounds__(PROJ_COLS * PROJ_FRAMES_PER_CTA)
+input_proj_all_kernel(const float* __restrict__ wx, const float* __restrict__ bias, long long total_rows,
+                      float* __restrict__ ring, int row_stride, int proj_off) {
+    __shared__ float sW[F * PROJ_COLS];
+    for (int e = threadIdx.x; e < F * PROJ_COLS; e += blockDim.x) sW[e] = __ldg(wx + e);
+    __syncthreads();
+    const int col = threadIdx.x % PROJ_COLS, fl = threadIdx.x / PROJ_COLS;
+    for (long long r = (long long)blockIdx.x * PROJ_FRAMES_PER_CTA + fl; r < total_rows; r += (long long)gridDim.x * PROJ_FRAMES_PER_CTA) {
+        float* row = ring + r * row_stride;
+        float a = __ldg(bias + col);
+#pragma unroll
+        for (int f = 0; f < F; ++f) a = fmaf(row[f], sW[f * PROJ_COLS + col], a);
+        row[proj_off + col] = a;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -235,6 +235,39 @@ def test_stream_tick_kernel_variants_agree():
     assert all(abs(o[2] - outs[0][2]) <= 3 for o in outs[1:])
 
 
+def test_cached_projection_path_large_batch():
+    """n > 8192 streams: tensor-core scan reading cached input projections (input_proj_kernel) vs the CUDA-core kernel,
+    including a weight reload and a small-batch tick in between (both invalidate the cache)."""
+    m = _mod()
+    S, K, chunk = 9000, 36, 1024
+    pcm = noise(64, K * chunk, seed=33)
+    pcm = np.tile(pcm, (S // 64 + 1, 1))[:S].copy()
+    pcm[::7] = np.roll(pcm[::7], 123, axis=1)
+    model = m.GruModel.random(13, 20, seed=8, scale=0.1)
+    model.dense_b = 3.0
+    res = []
+    for mode in (0, 1):
+        sb = m.StreamBatch(model, S, chunk_samples=chunk)
+        sb.core.gru_mode(mode)
+        raws = []
+        for k in range(K):
+            if k == 20:                                              # reload weights mid-stream
+                sb.core.load_weights(model.kernel, model.recurrent, model.bias, model.dense_w, model.dense_b)
+            if k == 25:                                              # a small tick for a few streams (warp-per-stream kernel)
+                ids = torch.arange(5, dtype=torch.int32, device='cuda')
+                o = sb.update(cuda(pcm[:5, k * chunk:(k + 1) * chunk]), ids)
+                r5 = o['raw'].cpu().numpy().copy()
+                o2 = sb.update(cuda(pcm[5:, k * chunk:(k + 1) * chunk]), torch.arange(5, S, dtype=torch.int32, device='cuda'))
+                raws.append(np.concatenate([r5, o2['raw'].cpu().numpy()]))
+                continue
+            o = sb.update(cuda(pcm[:, k * chunk:(k + 1) * chunk]))
+            raws.append(o['raw'].cpu().numpy().copy())
+        res.append((np.array(raws), int(sb.count.item())))
+        sb.core.close()
+    assert np.max(np.abs(res[0][0] - res[1][0])) < 1e-5
+    assert res[0][1] > 0 and abs(res[0][1] - res[1][1]) <= 3
+
+
 def _generic_case(pr_kw, H, act='linear', ract='hard_sigmoid', N=200, seed=5, mode=0):
     m = _mod()
     pr = m.ListenerParams(**pr_kw)
