@@ -7,7 +7,7 @@ TAG=${1:-r1}
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -s 6 -c 60 --csv --log-file gpurun_out/launches_$TAG.csv \
     python bench.py --steps 8 --warmup 3 --no-small-batch --no-cpu-baseline --no-latency > gpurun_out/launches_$TAG.log 2>&1
 # (2) full capture of the hot kernels (one launch each): K1, K2 (default network), K2 (wide network, configs[2])
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:'mfcc_fast_stream_kernel|gru_mma_kernel' -s 8 -c 2 \
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:'mfcc_fast_stream_kernel|gru_mma_kernel|input_proj_kernel' -s 12 -c 3 \
     -o gpurun_out/prof_$TAG python bench.py --steps 4 --warmup 3 --no-small-batch --no-cpu-baseline --no-latency --no-config3 > gpurun_out/prof_$TAG.log 2>&1
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:'gru_tcb_kernel' -s 3 -c 1 \
     -o gpurun_out/prof_c3_$TAG python bench.py --steps 3 --warmup 3 --no-small-batch --no-cpu-baseline --no-latency > gpurun_out/prof_c3_$TAG.log 2>&1
