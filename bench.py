@@ -88,6 +88,23 @@ def _cpu_worker(args):
     return n_streams * ticks, time.perf_counter() - t0, fired
 
 
+def cpu_c_port_rate(streams_per_thread=48, ticks=80):
+    """The plain-C restatement (oracle/c/precise_oracle.c), streams sharded over one thread per usable core."""
+    from oracle.cport import COracle
+    from oracle.gru import GruWeights
+    from oracle.params import OracleParams
+    threads = usable_cores()
+    co = COracle(GruWeights.random(13, 20, seed=0, scale=0.1), OracleParams(), chunk_samples=CHUNK)
+    S = streams_per_thread * threads
+    pcm = synth_pcm(S, ticks * CHUNK, 2468)
+    co.run_streams(pcm[:threads, :4 * CHUNK], threads=threads)            # warm-up
+    t0 = time.perf_counter()
+    co.run_streams(pcm, threads=threads)
+    dt = time.perf_counter() - t0
+    return S * ticks / dt, threads, '%d threads x %d streams x %d ticks of 1024 samples, scalar C restatement (gcc -O2), float64 MFCC / float32 GRU' % (
+        threads, streams_per_thread, ticks)
+
+
 def usable_cores():
     """Host cores this process may actually use: affinity mask capped by the cgroup CPU quota."""
     n = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1)
@@ -155,7 +172,10 @@ def run_reference(args, rank):
         'value': v, 'unit': 'stream-updates/s', 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': 1e3 * (time.perf_counter() - t0) / max(1, args.steps + args.warmup),
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64 MFCC / f32 GRU', 'data': 'synthetic',
-        'config': {'workload': 'default hey-mycroft parameters (n_fft 512, n_filt 20, n_mfcc 13, GRU 20), 1024-sample chunks; bounded CPU sample'},
+        'config': {'workload': 'per-GPU shard of configs[3]: default hey-mycroft parameters (n_fft 512, hop 800, window 1600, n_filt 20, n_mfcc 13, '
+                               'GRU 20, 29-frame window), 1024-sample chunks; CPU arm: bounded sample of the same per-stream work '
+                               '(one stream per worker process, as the reference runs one Listener per process)',
+                   'streams_per_gpu': args.streams_per_gpu, 'chunk_samples': CHUNK},
         'cpu_baseline': {'value': v, 'unit': 'stream-updates/s', 'cores': cores, 'kind': 'port', 'sample': sample + ' per step'},
         'e2e': {'value': v, 'unit': 'stream-updates/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'realtime_streams': v / 15.625,
@@ -215,9 +235,15 @@ def run_b200(args):
 
     cpu = None
     cpu_lat = None
+    cpu_c = None
     if int(os.environ.get('WORLD_SIZE', '1')) == 1 and not args.no_cpu_baseline:
         cpu = cpu_port_rate()                  # before CUDA is initialised in this process (fork safety)
         cpu_lat = cpu_latency() if args.latency else None
+        try:
+            cpu_c = cpu_c_port_rate()
+        except Exception as e:                     # the C port is optional evidence; never fail the bench on it
+            cpu_c = None
+            print('note: C port baseline skipped: %r' % (e,), file=sys.stderr)
     rank, local, world = init_from_env()
     if world != args.gpus and rank == 0:
         print('note: WORLD_SIZE=%d, --gpus=%d' % (world, args.gpus), file=sys.stderr)
@@ -429,6 +455,7 @@ def run_b200(args):
         'e2e': e2e,
         'gpu_launches': int(sum(klaunch)),
         'cpu_baseline': ({'value': cpu[0], 'unit': 'stream-updates/s', 'cores': cpu[1], 'kind': 'port', 'sample': cpu[2]} if cpu else None),
+        'cpu_baseline_c': ({'value': cpu_c[0], 'unit': 'stream-updates/s', 'cores': cpu_c[1], 'kind': 'port', 'sample': cpu_c[2]} if cpu_c else None),
         'clocks': clocks,
         'small_batch': small,
         'latency': lat,
