@@ -10,6 +10,9 @@ Only ``tests/``, ``__graft_entry__.smoke()`` and the ``cpu_baseline`` / ``--impl
 legs of ``bench.py`` may import it, and only as the checker / the CPU arm.  The product
 (``mycroft_precise_b200``) never imports it and has no CPU fallback.
 
+``cport.py`` / ``c/precise_oracle.c`` are a second, independent restatement of the same algorithm in plain C; the two
+must agree (tests/test_oracle_c_port.py).
+
 Parity pinning status
 ---------------------
 * ``decoder.py``, ``trigger.py``, ``params.py``, ``listener.py`` (state machine): PINNED.  The
