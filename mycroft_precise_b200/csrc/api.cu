@@ -76,7 +76,7 @@ struct pb_handle {
     // device tables
     float *d_wrise = nullptr, *d_wfall = nullptr, *d_dct = nullptr;
     int* d_grid = nullptr;
-    float2 *d_tw_stage = nullptr, *d_tw_post = nullptr;
+    float2 *d_tw_stage = nullptr, *d_tw_post = nullptr, *d_tw_any = nullptr;
     double* d_cd = nullptr;
     // state
     StreamState st{};
@@ -224,7 +224,7 @@ PB_API void pb_destroy(pb_handle* h) {
     if (!h) return;
     cudaSetDevice(h->cfg.device);
     cudaFree(h->d_wrise); cudaFree(h->d_wfall); cudaFree(h->d_dct); cudaFree(h->d_grid);
-    cudaFree(h->d_tw_stage); cudaFree(h->d_tw_post); cudaFree(h->d_cd); cudaFree(h->d_ptab); cudaFree(h->d_ctab); cudaFree(h->d_dct_t);
+    cudaFree(h->d_tw_stage); cudaFree(h->d_tw_post); cudaFree(h->d_tw_any); cudaFree(h->d_cd); cudaFree(h->d_ptab); cudaFree(h->d_ctab); cudaFree(h->d_dct_t);
     cudaFree(h->st.n_samples); cudaFree(h->st.tail); cudaFree(h->st.ring); cudaFree(h->st.trig);
     cudaFree(h->d_wcat); cudaFree(h->d_bias); cudaFree(h->d_wd); cudaFree(h->d_count);
     cudaFree(h->d_bfrag); cudaFree(h->d_mma_bias); cudaFree(h->d_mma_wd); cudaFree(h->d_proj_w); cudaFree(h->d_proj_b); cudaFree(h->d_tc5); cudaFree(h->d_tcb); cudaFree(h->d_dbg);
@@ -252,8 +252,8 @@ PB_API int pb_create(const pb_config* cfg, pb_handle** out) {
     if (c.vectorizer == PB_VEC_SPEECHPY_MFCCS)
         return fail(PB_ERR_UNSUPPORTED, "Vectorizer.speechpy_mfccs (legacy .params without 'vectorizer', precise/params.py:147) is not implemented");
     if (c.vectorizer != PB_VEC_MFCCS && c.vectorizer != PB_VEC_MELS) return fail(PB_ERR_INVALID, "unknown vectorizer %d", c.vectorizer);
-    if (c.n_fft != 512) return fail(PB_ERR_UNSUPPORTED, "n_fft %d: only n_fft = 512 (the reference default) is implemented", c.n_fft);
-    if (!is_pow2(c.n_fft)) return fail(PB_ERR_INVALID, "n_fft must be a power of two");
+    if (!is_pow2(c.n_fft) || c.n_fft < 64 || c.n_fft > 512)
+        return fail(PB_ERR_UNSUPPORTED, "n_fft %d: powers of two in [64, 512] are implemented (512 is the reference default)", c.n_fft);
     if (c.n_filt < 1 || c.n_filt > 64 || c.n_mfcc < 1 || c.n_mfcc > 64) return fail(PB_ERR_UNSUPPORTED, "n_filt and n_mfcc must be in [1, 64]");
     if (c.n_thresholds < 1 || c.n_thresholds > PB_MAX_THRESHOLDS) return fail(PB_ERR_INVALID, "n_thresholds must be in [1, %d]", PB_MAX_THRESHOLDS);
     if (c.activation < 0 || c.activation > 1 || c.recurrent_activation < 0 || c.recurrent_activation > 1)
@@ -349,6 +349,11 @@ PB_API int pb_create(const pb_config* cfg, pb_handle** out) {
         double a = 2.0 * M_PI * (double)k1 / 512.0;
         twp[k1] = make_float2((float)cos(a), (float)sin(a));
     }
+    std::vector<float2> twa(c.n_fft / 2);
+    for (int k = 0; k < c.n_fft / 2; ++k) {
+        double a = 2.0 * M_PI * (double)k / (double)c.n_fft;
+        twa[k] = make_float2((float)cos(a), (float)-sin(a));
+    }
     build_cdf(h);
 
 #define CKH(call)                                                                                 \
@@ -365,6 +370,7 @@ PB_API int pb_create(const pb_config* cfg, pb_handle** out) {
     CKH(upload(&h->d_dct, dct));
     CKH(upload(&h->d_tw_stage, tws));
     CKH(upload(&h->d_tw_post, twp));
+    CKH(upload(&h->d_tw_any, twa));
     CKH(upload(&h->d_cd, h->cd));
     {
         std::vector<float> dct_t((size_t)c.n_filt * 16 * h->nol, 0.f);
@@ -636,6 +642,7 @@ static MelTables mel_tables(const pb_handle* h) {
     t.tw_stage = h->d_tw_stage; t.tw_post = h->d_tw_post;
     t.n_bins = h->n_bins; t.n_filt = h->cfg.n_filt; t.n_out = h->n_out;
     t.mels_only = h->cfg.vectorizer == PB_VEC_MELS;
+    t.n_fft = h->cfg.n_fft; t.tw_any = h->d_tw_any;
     return t;
 }
 

@@ -38,6 +38,8 @@ struct MelTables {
     const float2* tw_post;    // [16]      (cos, +sin)(2 pi k1 / 512)
     int n_bins, n_filt, n_out;
     int mels_only;            // Vectorizer.mels: emit log-mels, no DCT / c0
+    int n_fft;                // 512: register FFT (fft512.cuh); other powers of two <= 512: fft_any_power below
+    const float2* tw_any;     // [n_fft / 2]  (cos, -sin)(2 pi k / n_fft)
 };
 
 // Where the `used` samples of one frame live: sample i is p0[i] for i < len0, else p1[i - len0];
@@ -75,6 +77,33 @@ __device__ __forceinline__ cpx load_elem(const FrameSrc<T>& s, int m) {
     ++i;
     r.y = (i < s.used) ? to_f(__ldg((i < s.len0) ? s.p0 + i : s.p1 + (i - s.len0))) : 0.f;
     return r;
+}
+
+// Any power-of-two n_fft <= 512 (the reference lets n_fft be configured, precise/params.py:49): a whole warp transforms
+// one frame with a plain radix-2 shared-memory FFT (real input as complex), then writes the scaled power bins.  Slow path.
+template <typename T>
+__device__ __forceinline__ void fft_any_power(const FrameSrc<T>& s, int n_fft, const float2* __restrict__ tw, float2* scratch,
+                                              float* P, float scale, int lane) {
+    const int lg = 31 - __clz(n_fft);
+    for (int i = lane; i < n_fft; i += 32) {
+        float v = 0.f;
+        if (i < s.used) v = to_f(__ldg(i < s.len0 ? s.p0 + i : s.p1 + (i - s.len0)));
+        scratch[__brev((unsigned)i) >> (32 - lg)] = make_float2(v, 0.f);
+    }
+    __syncwarp();
+    for (int len = 2; len <= n_fft; len <<= 1) {
+        const int hl = len >> 1, step = n_fft / len;
+        for (int b = lane; b < n_fft / 2; b += 32) {
+            const int grp = b / hl, k = b - grp * hl, i0 = grp * len + k, i1 = i0 + hl;
+            const float2 w = __ldg(tw + k * step), a = scratch[i0], c = scratch[i1];
+            const float vr = fmaf(c.x, w.x, -c.y * w.y), vi = fmaf(c.x, w.y, c.y * w.x);
+            scratch[i0] = make_float2(a.x + vr, a.y + vi);
+            scratch[i1] = make_float2(a.x - vr, a.y - vi);
+        }
+        __syncwarp();
+    }
+    for (int k = lane; k <= n_fft / 2; k += 32) { const float2 a = scratch[k]; P[k] = fmaf(a.x, a.x, a.y * a.y) * scale; }
+    __syncwarp();
 }
 
 // Per-CTA copy of the small tables (broadcast reads in phase B).
@@ -186,6 +215,18 @@ mfcc_batch_kernel(const T* __restrict__ pcm, long long samples_per_stream, long 
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const long long g_base = tile * K1_TILE;
         // ---- phase A: 32 frames, 8 per pass over the 4 warps
+        if (tab.n_fft != 512) {
+#pragma unroll 1
+            for (int slot = warp; slot < K1_TILE; slot += K1_WARPS) {           // generic n_fft: one frame per warp at a time
+                const long long g = g_base + slot;
+                if (g >= total_frames) break;
+                const long long s = g / n_frames_per_stream, f = g - s * n_frames_per_stream;
+                FrameSrc<T> src;
+                src.p0 = pcm + s * samples_per_stream + f * hop;
+                src.p1 = src.p0; src.len0 = used; src.used = used;
+                fft_any_power<T>(src, tab.n_fft, tab.tw_any, sm.xch + warp * 2 * XCH_ELEMS, sm.power + slot * K1_PSTRIDE, scale, lane);
+            }
+        } else
 #pragma unroll 1
         for (int pass = 0; pass < K1_TILE / (K1_WARPS * 2); ++pass) {
             const int slot = pass * (K1_WARPS * 2) + warp * 2 + half;
@@ -283,6 +324,23 @@ mfcc_stream_kernel(const int16_t* __restrict__ pcm, const int* __restrict__ ids,
         for (int r0 = 0; r0 < nf; r0 += K1_TILE) {
             const int nr = min(K1_TILE, nf - r0);
             // ---- phase A
+            if (tab.n_fft != 512) {
+#pragma unroll 1
+                for (int slot = warp; slot < nr; slot += K1_WARPS) {               // generic n_fft: one frame per warp at a time
+                    const int t = sm.fr_stream[r0 + slot];
+                    const long long a0 = (sm.st_c0[t] + sm.fr_sub[r0 + slot]) * hop, n0 = sm.st_n0[t];
+                    const int16_t* chunk_p = pcm + (long long)(base + t) * chunk;
+                    FrameSrc<int16_t> src;
+                    src.used = used;
+                    if (a0 >= n0) { src.len0 = 0; src.p0 = chunk_p; src.p1 = chunk_p + (a0 - n0); }
+                    else {
+                        src.len0 = (int)min((long long)used, n0 - a0);
+                        src.p0 = st.tail + (long long)sm.st_id[t] * st.tail_cap + (a0 - sm.st_ts0[t]);
+                        src.p1 = chunk_p;
+                    }
+                    fft_any_power<int16_t>(src, tab.n_fft, tab.tw_any, sm.k1.xch + warp * 2 * XCH_ELEMS, sm.k1.power + slot * K1_PSTRIDE, scale, lane);
+                }
+            } else
 #pragma unroll 1
             for (int pass = 0; pass * (K1_WARPS * 2) < nr; ++pass) {
                 const int slot = pass * (K1_WARPS * 2) + warp * 2 + half;

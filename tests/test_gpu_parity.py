@@ -484,8 +484,38 @@ def test_mels_vectorizer():
     c.close()
 
 
+@pytest.mark.parametrize('kw', [dict(n_fft=256), dict(n_fft=128, window_t=0.02, hop_t=0.01), dict(n_fft=64, n_filt=12, n_mfcc=8),
+                                dict(n_fft=256, window_t=0.01, hop_t=0.005)])
+def test_generic_n_fft(kw):
+    """n_fft is a ListenerParams field (precise/params.py:49); any power of two in [64, 512] runs through the radix-2 path.
+    Covers crop (window > n_fft) and zero-pad (window < n_fft) framing, batch and streaming."""
+    m = _mod()
+    pr = m.ListenerParams(**kw)
+    opr = OracleParams(**pr.to_dict())
+    c = m.PreciseB200(pr)
+    pcm = noise(5, 9000, seed=23)
+    got = c.mfcc(cuda(pcm)).cpu().numpy()
+    want = np.stack([om.mfcc_spec(r.astype(np.float32) / 32768.0, 16000, pr.window_samples, pr.hop_samples,
+                                  pr.n_fft, pr.n_filt, pr.n_mfcc) for r in pcm])
+    assert got.shape == want.shape
+    print(kw, 'mfcc err', np.max(np.abs(got - want)))
+    assert np.max(np.abs(got - want)) < 2e-4
+    c.close()
+    chunk = min(1024, 4 * pr.hop_samples)          # a tick may release at most 8 frames
+    pcm = noise(4, 24 * chunk, seed=29)
+    model = m.GruModel.random(pr.feature_size, 20, seed=5, scale=0.1)
+    raw, conf, fired, wins, count = _run_gpu_streams(m, model, pcm, chunk, pr=pr)
+    w = og.GruWeights(model.kernel, model.recurrent, model.bias, model.dense_w, model.dense_b)
+    oraw, oconf, ofired = run_streams(w, pcm, chunk, pr=opr)
+    assert np.max(np.abs(raw - oraw)) < 1e-4 and np.array_equal(fired, ofired)
+
+
 def test_unsupported_and_errors():
     m = _mod()
+    with pytest.raises(NotImplementedError):
+        m.PreciseB200(m.ListenerParams(n_fft=1024))
+    with pytest.raises(NotImplementedError):
+        m.PreciseB200(m.ListenerParams(n_fft=384))
     with pytest.raises(NotImplementedError):
         m.PreciseB200(m.ListenerParams(vectorizer=m.Vectorizer.speechpy_mfccs))
     c = m.PreciseB200(max_streams=4)
