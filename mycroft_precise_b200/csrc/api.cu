@@ -59,7 +59,8 @@ struct pb_handle {
     int sm_count = 148;
     // derived
     int used = 0, n_bins = 0, n_out = 0, feat = 0, ring_rows = 0, row_stride = 0, tail_cap = 0, max_new = 0;
-    int proj_off = 0;
+    bool has_proj = false;           // default network: a second ring caches the input projections (gru_kernels.cuh)
+    float* d_proj_ring = nullptr;
     bool proj_dirty = true;          // some ring rows lack a valid cached projection (weights changed / projection skipped)
     float *d_proj_w = nullptr, *d_proj_b = nullptr;
     size_t k1_batch_smem = 0, k1_stream_smem = 0, k1_fast_smem = 0;
@@ -92,7 +93,7 @@ struct pb_handle {
     bool tcb_ok = false;
     int tcb_kx = 0;
     float *d_tc5 = nullptr;           // tcgen05 GRU: [b1_hi | b1_lo | b2_hi | b2_lo | bias(80) | wd(24)]
-    int gru_mode = 0;                // 0 = auto, 1 = force CUDA-core small kernel, 2 = force tensor-core kernel
+    int gru_mode = 0;                // 0 = auto, 1 = force CUDA-core small kernel, 2 = force tensor-core kernel, 3 = tcgen05 scan, 4 = tensor-core kernel without the cp.async prefetch
     float bd = 0.f;
     // host pipeline
     cudaStream_t pipe[HOST_PIPE] = {nullptr, nullptr, nullptr};
@@ -227,7 +228,7 @@ PB_API void pb_destroy(pb_handle* h) {
     cudaFree(h->d_tw_stage); cudaFree(h->d_tw_post); cudaFree(h->d_tw_any); cudaFree(h->d_cd); cudaFree(h->d_ptab); cudaFree(h->d_ctab); cudaFree(h->d_dct_t);
     cudaFree(h->st.n_samples); cudaFree(h->st.tail); cudaFree(h->st.ring); cudaFree(h->st.trig);
     cudaFree(h->d_wcat); cudaFree(h->d_bias); cudaFree(h->d_wd); cudaFree(h->d_count);
-    cudaFree(h->d_bfrag); cudaFree(h->d_mma_bias); cudaFree(h->d_mma_wd); cudaFree(h->d_proj_w); cudaFree(h->d_proj_b); cudaFree(h->d_tc5); cudaFree(h->d_tcb); cudaFree(h->d_dbg);
+    cudaFree(h->d_bfrag); cudaFree(h->d_mma_bias); cudaFree(h->d_mma_wd); cudaFree(h->d_proj_w); cudaFree(h->d_proj_b); cudaFree(h->d_proj_ring); cudaFree(h->d_tc5); cudaFree(h->d_tcb); cudaFree(h->d_dbg);
     if (h->h_count_pinned) cudaFreeHost(h->h_count_pinned);
     for (int i = 0; i < HOST_PIPE; ++i) {
         cudaFree(h->d_stage_pcm[i]); cudaFree(h->d_stage_ids[i]); cudaFree(h->d_stage_raw[i]);
@@ -273,9 +274,8 @@ PB_API int pb_create(const pb_config* cfg, pb_handle** out) {
     h->n_out = c.vectorizer == PB_VEC_MELS ? c.n_filt : std::min(c.n_filt, c.n_mfcc);
     h->feat = h->n_out * (c.use_delta ? 2 : 1);
     h->row_stride = (h->n_out + 3) & ~3;
-    // default-sized networks cache the input projection of every frame behind its MFCC row (gru_mma_kernel<.., PROJ>)
-    h->proj_off = 0;
-    if (c.hidden == 20 && h->n_out == 13 && !c.use_delta && c.vectorizer == PB_VEC_MFCCS) { h->proj_off = h->row_stride; h->row_stride += PROJ_COLS; }
+    // default-sized networks cache the input projection of every frame in a second ring (gru_mma_kernel<.., PROJ>)
+    h->has_proj = c.hidden == 20 && h->n_out == 13 && !c.use_delta && c.vectorizer == PB_VEC_MFCCS;
     h->ring_rows = c.n_features + (c.window_samples - h->used) / c.hop_samples + 2;
     h->tail_cap = (h->used + 7) & ~7;            // rows stay 16-byte aligned
     h->max_new = c.chunk_samples / c.hop_samples + 2;
@@ -389,6 +389,7 @@ PB_API int pb_create(const pb_config* cfg, pb_handle** out) {
     CKH(cudaMemset(h->st.n_samples, 0, S * sizeof(long long)));
     CKH(cudaMemset(h->st.tail, 0, S * h->tail_cap * sizeof(int16_t)));
     CKH(cudaMemset(h->st.ring, 0, S * h->ring_rows * h->row_stride * sizeof(float)));
+    if (h->has_proj) CKH(cudaMalloc((void**)&h->d_proj_ring, S * h->ring_rows * PROJ_STRIDE * sizeof(float)));
     CKH(cudaMemset(h->st.trig, 0, S * sizeof(int)));
     CKH(cudaMalloc((void**)&h->d_count, sizeof(unsigned long long)));
     CKH(cudaMemset(h->d_count, 0, sizeof(unsigned long long)));
@@ -519,6 +520,7 @@ PB_API int pb_load_weights(pb_handle* h, const float* kernel, const float* recur
             for (int u = 0; u < H; ++u) { tb[u] = bias[u]; tb[24 + u] = bias[H + u]; tb[48 + u] = bias[2 * H + u]; tw[u] = dense_w[u]; }
             cudaFree(h->d_tc5); h->d_tc5 = nullptr;
             CK(upload(&h->d_tc5, t));
+            CK(cudaFuncSetAttribute(gru_mma_kernel<20, 13, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MMA_PRE_SMEM));
             CK(cudaFuncSetAttribute(gru_tc5_kernel<20, 13, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Tc5Smem) + 128));
             CK(cudaFuncSetAttribute(gru_tc5_kernel<20, 13, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Tc5Smem) + 128));
         }
@@ -725,7 +727,8 @@ static int launch_gru(pb_handle* h, const K2In& in, bool ring, int64_t n, const 
         w.bfrag = h->d_bfrag; w.bias = h->d_mma_bias; w.wd = h->d_mma_wd; w.bd = h->bd;
         const int per_cta = (MMA_THREADS / 32) * 16 * MMA_MB;
         const int grid = (int)((n + per_cta - 1) / per_cta);
-        if (ring && in.proj_off > 0) gru_mma_kernel<20, 13, true, true><<<grid, MMA_THREADS, 0, s>>>(w, in, n, dp, o);
+        if (ring && in.proj != nullptr && h->gru_mode != 4) gru_mma_kernel<20, 13, true, true, true><<<grid, MMA_THREADS, MMA_PRE_SMEM, s>>>(w, in, n, dp, o);
+        else if (ring && in.proj != nullptr) gru_mma_kernel<20, 13, true, true><<<grid, MMA_THREADS, 0, s>>>(w, in, n, dp, o);   // mode 4: no prefetch (A/B)
         else if (ring) gru_mma_kernel<20, 13, true, false><<<grid, MMA_THREADS, 0, s>>>(w, in, n, dp, o);
         else gru_mma_kernel<20, 13, false, false><<<grid, MMA_THREADS, 0, s>>>(w, in, n, dp, o);
     } else if (h->small_path) {
@@ -833,19 +836,19 @@ PB_API int pb_update(pb_handle* h, const int16_t* d_pcm, const int32_t* d_ids, i
     rc = launch_stream_mfcc(h, d_pcm, d_ids, n, s);
     if (rc != PB_OK) return rc;
     bool use_proj = false;
-    if (h->proj_off > 0 && h->small_path) {
-        if (n > K2_WARP_PATH_MAX && (h->gru_mode == 0 || h->gru_mode == 2)) {
+    if (h->has_proj && h->small_path) {
+        if (n > K2_WARP_PATH_MAX && (h->gru_mode == 0 || h->gru_mode == 2 || h->gru_mode == 4)) {
             ProfScope ps(h, 3, s);
             if (h->proj_dirty) {                               // bring every ring row up to date once, then stay incremental
                 const long long rows = (long long)h->cfg.max_streams * h->ring_rows;
                 const int grid = (int)std::min<long long>((rows + PROJ_FRAMES_PER_CTA - 1) / PROJ_FRAMES_PER_CTA, (long long)h->sm_count * 16);
-                input_proj_all_kernel<13><<<grid, PROJ_COLS * PROJ_FRAMES_PER_CTA, 0, s>>>(h->d_proj_w, h->d_proj_b, rows, h->st.ring, h->row_stride, h->proj_off);
+                input_proj_all_kernel<13><<<grid, 64 * PROJ_FRAMES_PER_CTA, 0, s>>>(h->d_proj_w, h->d_proj_b, rows, h->st.ring, h->row_stride, h->d_proj_ring);
                 h->proj_dirty = false;
             } else {
                 const long long items = (long long)n * h->max_new;
                 const int grid = (int)((items + PROJ_THREADS - 1) / PROJ_THREADS);     // 32 frames per warp
                 input_proj_kernel<13><<<grid, PROJ_THREADS, 0, s>>>(h->d_bfrag, h->d_proj_b, h->st.n_samples, d_ids, (int)n,
-                    h->cfg.chunk_samples, h->used, h->cfg.hop_samples, h->max_new, h->st.ring, h->ring_rows, h->row_stride, h->proj_off);
+                    h->cfg.chunk_samples, h->used, h->cfg.hop_samples, h->max_new, h->st.ring, h->ring_rows, h->row_stride, h->d_proj_ring);
             }
             CK(cudaGetLastError());
             use_proj = true;
@@ -858,7 +861,7 @@ PB_API int pb_update(pb_handle* h, const int16_t* d_pcm, const int32_t* d_ids, i
     in.ring_rows = h->ring_rows; in.row_stride = h->row_stride; in.window = h->cfg.window_samples; in.hop = h->cfg.hop_samples;
     in.T = h->cfg.n_features; in.F_base = h->n_out; in.use_delta = h->cfg.use_delta;
     K2Out o{};
-    in.proj_off = use_proj ? h->proj_off : 0;
+    in.proj = use_proj ? h->d_proj_ring : nullptr;
     in.chunk = h->cfg.chunk_samples;
     o.raw = d_raw; o.conf = d_conf; o.fired = d_fired; o.count = d_count; o.trig = h->st.trig;
     return launch_gru(h, in, true, n, decode_params(h), o, s);

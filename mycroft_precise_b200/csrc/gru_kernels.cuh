@@ -46,7 +46,7 @@ struct K2In {
     int ring_rows, row_stride, window, hop;
     int T, F_base;                   // F_base = MFCC width (without deltas)
     int use_delta;
-    int proj_off;                    // > 0: ring rows carry the cached input projection x.W + b (72 floats) at this offset
+    const float* proj;               // non-null: cached input projections x.W + b, [max_streams][ring_rows][PROJ_STRIDE], same slots as ring
     int chunk;                       // samples added by this tick (to tell which window rows are new)
 };
 
@@ -131,6 +131,12 @@ struct RingCursor {
         slot = (int)m;
         rows = in.ring_rows; stride = in.row_stride;
         base = in.ring + (long long)sid * in.ring_rows * in.row_stride;
+    }
+    // same window over the projection ring (rows of `pstride` floats)
+    __device__ __forceinline__ void init_proj(const K2In& in, int sid, long long released, int pstride) {
+        init(in, sid, released);
+        stride = pstride;
+        base = in.proj + (long long)sid * in.ring_rows * pstride;
     }
     // row of step t (call with t = 0, 1, 2, ... in order), nullptr for a zero row
     __device__ __forceinline__ const float* next(int t) {
@@ -385,6 +391,12 @@ gru_warp_kernel(const __grid_constant__ GruSmallW<H, F> P, K2In in, long long n,
 // assigned to k slots in the order the accumulator fragment already holds them (thread t of a quad owns
 // units 8*tile + 2t, 2t+1).  The weight fragments are permuted once on the host to match; turning h
 // (C layout) into the next step's A operand then needs no shuffle at all.
+constexpr int PROJ_COLS = 72;        // padded gate columns of the fragment layout: 24 * gate + unit
+constexpr int PROJ_STRIDE = 60;      // stored projection row: 20 * gate + unit (the padding units are not stored)
+constexpr int PROJ_FRAMES_PER_CTA = 4;
+// position in a stored projection row of accumulator columns (2t, 2t+1) of n-tile nt (gate nt / 3, units 8 (nt % 3) + 2t, +1)
+__device__ __forceinline__ int proj_col(int nt, int t) { return 20 * (nt / 3) + 8 * (nt % 3) + 2 * t; }
+
 constexpr int MMA_KT = 5;            // k tiles: 2 for x (F <= 16), 3 for h (H <= 24)
 constexpr int MMA_NT = 9;            // n tiles: z, r, h gates x 3 tiles of 8 units
 constexpr int MMA_MB = 2;            // row blocks of 16 streams per warp
@@ -437,10 +449,26 @@ __device__ __forceinline__ void split_tf32(const float (&v)[4], uint32_t (&hi)[4
 // PROJ (stream mode): the input projection x_t.[Wz|Wr|Wh] + b of every frame was computed once when the frame was
 // produced (input_proj_kernel) and sits in the ring next to the MFCC row, so the scan only runs the recurrent products:
 // 162 instead of 270 HMMA per step on the pipe that bounds this kernel.
-template <int H, int F, bool RING, bool PROJ>
+// PRE (with PROJ): the projection rows of step s+1 are fetched with cp.async into per-thread shared-memory slots while
+// step s computes -- the loads are scattered 32-byte sectors whose loaded DRAM latency (several microseconds at 131 072
+// streams) is otherwise exposed at the top of every step (ncu: long_scoreboard was the first stall reason).
+constexpr int MMA_PRE_SLOTS = 2 * MMA_MB * MMA_NT;                      // float2 slots per thread
+constexpr int MMA_PRE_SMEM = (MMA_THREADS / 32) * MMA_PRE_SLOTS * 32 * 8;  // bytes of dynamic shared memory
+
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_wait_all(bool wait) {
+    if (wait) asm volatile("cp.async.wait_all;" ::: "memory");
+    else asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
+template <int H, int F, bool RING, bool PROJ, bool PRE = false>
 __global__ void __launch_bounds__(MMA_THREADS, 3)
 gru_mma_kernel(GruMmaW W, K2In in, long long n, DecodeParams dp, K2Out out) {
     static_assert(H <= 24 && F <= 16, "tile counts are fixed");
+    static_assert(!PRE || PROJ, "the prefetch variant reads cached projections");
+    extern __shared__ __align__(16) unsigned char mma_dyn_smem[];
     __shared__ float4 sB[MMA_KT * MMA_NT * 32];
     __shared__ float sBias[3 * 24];
     __shared__ float sWd[24];
@@ -468,7 +496,8 @@ gru_mma_kernel(GruMmaW W, K2In in, long long n, DecodeParams dp, K2Out out) {
                 sid[mb][hf] = in.ids ? in.ids[idx[mb][hf]] : (int)idx[mb][hf];
                 const long long ns = in.n_samples[sid[mb][hf]];
                 rel[mb][hf] = ns >= in.window ? (ns - in.window) / in.hop + 1 : 0;
-                cur[mb][hf].init(in, sid[mb][hf], rel[mb][hf]);
+                if (PROJ) cur[mb][hf].init_proj(in, sid[mb][hf], rel[mb][hf], PROJ_STRIDE);
+                else cur[mb][hf].init(in, sid[mb][hf], rel[mb][hf]);
             }
         }
     // h in accumulator layout: hreg[mb][tile][e], e = (row g: units 2t, 2t+1; row g+8: units 2t, 2t+1) of tile
@@ -480,10 +509,50 @@ gru_mma_kernel(GruMmaW W, K2In in, long long n, DecodeParams dp, K2Out out) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) hreg[mb][nt][e] = 0.f;
 
+    // PRE: slot j = (2 mb + hf) * 9 + nt of this thread at pre[j * 32] (lanes interleaved: conflict-free LDS.64)
+    float2* pre = reinterpret_cast<float2*>(mma_dyn_smem) + (size_t)warp * MMA_PRE_SLOTS * 32 + lane;
+    unsigned vnext = 0;                                                  // bit (2 mb + hf): the prefetched row exists
+    auto prefetch = [&](int step) {
+        vnext = 0;
+#pragma unroll
+        for (int mb = 0; mb < MMA_MB; ++mb)
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+                const float* row = ok[mb][hf] ? cur[mb][hf].next(step) : nullptr;
+                if (row != nullptr) {
+                    vnext |= 1u << (2 * mb + hf);
+#pragma unroll
+                    for (int nt = 0; nt < MMA_NT; ++nt)
+                        if (nt % 3 != 2 || t < 2) cp_async8(pre + ((2 * mb + hf) * MMA_NT + nt) * 32, row + proj_col(nt, t));
+                }
+            }
+        cp_async_commit_wait_all(false);
+    };
+    if (PRE) prefetch(0);
+
 #pragma unroll 1
     for (int step = 0; step < in.T; ++step) {
         float acc[MMA_MB][MMA_NT][4];
-        if (PROJ) {
+        if (PRE) {
+            // ---- accumulators start from the prefetched projection; then the next step's rows start to stream in
+            cp_async_commit_wait_all(true);
+            const unsigned vcur = vnext;
+#pragma unroll
+            for (int mb = 0; mb < MMA_MB; ++mb)
+#pragma unroll
+                for (int hf = 0; hf < 2; ++hf) {
+                    const bool have = (vcur >> (2 * mb + hf)) & 1u;
+#pragma unroll
+                    for (int nt = 0; nt < MMA_NT; ++nt) {
+                        float2 v;
+                        if (!have) v = make_float2(sBias[8 * nt + 2 * t], sBias[8 * nt + 2 * t + 1]);
+                        else if (nt % 3 != 2 || t < 2) v = pre[((2 * mb + hf) * MMA_NT + nt) * 32];
+                        else v = make_float2(0.f, 0.f);
+                        acc[mb][nt][2 * hf] = v.x; acc[mb][nt][2 * hf + 1] = v.y;
+                    }
+                }
+            if (step + 1 < in.T) prefetch(step + 1);
+        } else if (PROJ) {
             // ---- accumulators start from the cached projection (bias included); rows before the stream's first frame: bias
 #pragma unroll
             for (int mb = 0; mb < MMA_MB; ++mb)
@@ -493,8 +562,9 @@ gru_mma_kernel(GruMmaW W, K2In in, long long n, DecodeParams dp, K2Out out) {
 #pragma unroll
                     for (int nt = 0; nt < MMA_NT; ++nt) {
                         float2 v;
-                        if (row != nullptr) v = __ldg(reinterpret_cast<const float2*>(row + in.proj_off + 8 * nt + 2 * t));
-                        else v = make_float2(sBias[8 * nt + 2 * t], sBias[8 * nt + 2 * t + 1]);
+                        if (row == nullptr) v = make_float2(sBias[8 * nt + 2 * t], sBias[8 * nt + 2 * t + 1]);
+                        else if (nt % 3 != 2 || t < 2) v = __ldg(reinterpret_cast<const float2*>(row + proj_col(nt, t)));
+                        else v = make_float2(0.f, 0.f);                  // padding units 20..23 of a gate: not stored
                         acc[mb][nt][2 * hf] = v.x; acc[mb][nt][2 * hf + 1] = v.y;
                     }
                 }
@@ -610,11 +680,11 @@ gru_mma_kernel(GruMmaW W, K2In in, long long n, DecodeParams dp, K2Out out) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// Cached input projection (default network, stream mode): a = b + x . [Wz|Wr|Wh] for the 72 padded gate columns is kept
-// behind each MFCC row.  gru_mma_kernel<.., PROJ> computes it for the rows that enter a stream's window and stores it;
-// the kernel below refreshes every row after the cache was invalidated.
-constexpr int PROJ_COLS = 72;
-constexpr int PROJ_FRAMES_PER_CTA = 4;
+// Cached input projection (default network, stream mode): a = b + x . [Wz|Wr|Wh] (60 floats per frame) is kept in a second
+// ring with the same slot numbering as the MFCC ring.  A steady-state scan reads 29 x 240 B of it per stream -- the scan is
+// bound by that traffic, which is why the rows are stored compact (no padding units) and apart from the MFCC rows.
+// input_proj_kernel fills the rows of a tick's new frames; input_proj_all_kernel refreshes every row after the cache was
+// invalidated.
 
 // Per-tick projection of the frames a tick has just produced, on the tensor cores: a warp takes 32 new frames as the rows
 // of two m16 blocks and runs the 3xTF32 x-part MMAs (2 k-tiles x 9 n-tiles) once per frame instead of once per scan step.
@@ -627,7 +697,7 @@ template <int F>
 __global__ void __launch_bounds__(PROJ_THREADS, 6)
 input_proj_kernel(const float4* __restrict__ bfrag, const float* __restrict__ bias, const long long* __restrict__ n_samples,
                   const int* __restrict__ ids, int n, int chunk, int need, int hop, int max_new,
-                  float* __restrict__ ring, int ring_rows, int row_stride, int proj_off) {
+                  const float* __restrict__ ring, int ring_rows, int row_stride, float* __restrict__ proj) {
     __shared__ float4 sB[2 * MMA_NT * 32];
     __shared__ float sBias[PROJ_COLS];
     for (int e = threadIdx.x; e < 2 * MMA_NT * 32; e += blockDim.x) sB[e] = __ldg(bfrag + e);
@@ -637,12 +707,13 @@ input_proj_kernel(const float4* __restrict__ bfrag, const float* __restrict__ bi
     const long long items = (long long)n * max_new;
     const long long base = ((long long)blockIdx.x * (PROJ_THREADS / 32) + (threadIdx.x >> 5)) * 32;
     if (base >= items) return;
-    float* rows[MMA_MB][2];
+    const float* rows[MMA_MB][2];
+    float* prow[MMA_MB][2];
 #pragma unroll
     for (int mb = 0; mb < MMA_MB; ++mb)
 #pragma unroll
         for (int hf = 0; hf < 2; ++hf) {
-            rows[mb][hf] = nullptr;
+            rows[mb][hf] = nullptr; prow[mb][hf] = nullptr;
             const long long item = base + 16 * mb + g + 8 * hf;
             if (item < items) {
                 const int j = (int)(item / n);
@@ -650,7 +721,11 @@ input_proj_kernel(const float4* __restrict__ bfrag, const float* __restrict__ bi
                 const int sid = ids ? ids[i] : (int)i;
                 const long long n1 = n_samples[sid], n0 = n1 - chunk;
                 const long long c0 = n0 >= need ? (n0 - need) / hop + 1 : 0, c1 = n1 >= need ? (n1 - need) / hop + 1 : 0;
-                if (j < c1 - c0) rows[mb][hf] = ring + ((long long)sid * ring_rows + (int)((c0 + j) % ring_rows)) * row_stride;
+                if (j < c1 - c0) {
+                    const long long r = (long long)sid * ring_rows + (int)((c0 + j) % ring_rows);
+                    rows[mb][hf] = ring + r * row_stride;
+                    prow[mb][hf] = proj + r * PROJ_STRIDE;
+                }
             }
         }
     uint32_t ah[2][MMA_MB][4], al[2][MMA_MB][4];
@@ -699,10 +774,11 @@ input_proj_kernel(const float4* __restrict__ bfrag, const float* __restrict__ bi
         for (int mb = 0; mb < MMA_MB; ++mb)
 #pragma unroll
             for (int hf = 0; hf < 2; ++hf)
-                if (rows[mb][hf] != nullptr) {
+                if (prow[mb][hf] != nullptr) {
 #pragma unroll
                     for (int q = 0; q < 3; ++q)
-                        *reinterpret_cast<float2*>(rows[mb][hf] + proj_off + 8 * (ng + q) + 2 * t) = make_float2(acc[mb][q][2 * hf], acc[mb][q][2 * hf + 1]);
+                        if (q < 2 || t < 2)                          // ng is a multiple of 3: q == 2 is the half-empty tile of the gate
+                            *reinterpret_cast<float2*>(prow[mb][hf] + proj_col(ng + q, t)) = make_float2(acc[mb][q][2 * hf], acc[mb][q][2 * hf + 1]);
                 }
     }
 }
@@ -710,19 +786,21 @@ input_proj_kernel(const float4* __restrict__ bfrag, const float* __restrict__ bi
 // Same projection for EVERY ring row of every stream: run once after the weights change or after ticks that skipped the
 // per-tick projection (small batches served by the warp-per-stream kernel), so that cached projections are always valid.
 template <int F>
-__global__ void __launch_bounds__(PROJ_COLS * PROJ_FRAMES_PER_CTA)
+__global__ void __launch_bounds__(64 * PROJ_FRAMES_PER_CTA)
 input_proj_all_kernel(const float* __restrict__ wx, const float* __restrict__ bias, long long total_rows,
-                      float* __restrict__ ring, int row_stride, int proj_off) {
+                      const float* __restrict__ ring, int row_stride, float* __restrict__ proj) {
     __shared__ float sW[F * PROJ_COLS];
     for (int e = threadIdx.x; e < F * PROJ_COLS; e += blockDim.x) sW[e] = __ldg(wx + e);
     __syncthreads();
-    const int col = threadIdx.x % PROJ_COLS, fl = threadIdx.x / PROJ_COLS;
+    const int c = threadIdx.x & 63, fl = threadIdx.x >> 6;          // c: stored column 20 * gate + unit
+    if (c >= PROJ_STRIDE) return;
+    const int col = c + 4 * (c / 20);                                // padded column 24 * gate + unit
     for (long long r = (long long)blockIdx.x * PROJ_FRAMES_PER_CTA + fl; r < total_rows; r += (long long)gridDim.x * PROJ_FRAMES_PER_CTA) {
-        float* row = ring + r * row_stride;
+        const float* row = ring + r * row_stride;
         float a = __ldg(bias + col);
 #pragma unroll
         for (int f = 0; f < F; ++f) a = fmaf(row[f], sW[f * PROJ_COLS + col], a);
-        row[proj_off + col] = a;
+        proj[r * PROJ_STRIDE + c] = a;
     }
 }
 

@@ -166,9 +166,11 @@ __device__ __forceinline__ void fast_pass(K1FWarp& ws, int stage, uint32_t parit
     cpx z[16];
 #pragma unroll
     for (int n1 = 0; n1 < 16; ++n1) {
-        const int v = active ? in[16 * n1 + l16] : 0;
-        z[n1].x = (float)(short)(v & 0xffff);
-        z[n1].y = (float)(short)(v >> 16);
+        // int16 pair -> two floats without I2F (quarter-rate pipe): flip the sign bits (u = v + 32768), drop each half
+        // into the mantissa of 2^23 and subtract 2^23 + 32768; exact.
+        const unsigned v = (active ? (unsigned)in[16 * n1 + l16] : 0u) ^ 0x80008000u;
+        z[n1].x = __uint_as_float(__byte_perm(v, 0x4b000000u, 0x7610)) - 8421376.f;
+        z[n1].y = __uint_as_float(__byte_perm(v, 0x4b000000u, 0x7632)) - 8421376.f;
     }
     __syncwarp();                                  // all lanes have read the staged samples: the buffer becomes scratch
     float* P = reinterpret_cast<float*>(ws.buf[stage][half]);
