@@ -47,5 +47,96 @@ def load_weights(path: str) -> GruModel:
     if path.endswith('.pb'):
         from .pb_import import load_pb
         return load_pb(path)
-    raise ValueError('File extension of ' + path + " must be: ['.npz', '.pb'] "
-                     '(Keras .net / HDF5 import is not implemented: convert with precise-convert)')
+    if path.endswith('.net'):
+        return load_net(path)
+    raise ValueError('File extension of ' + path + " must be: ['.npz', '.pb', '.net']")
+
+
+def _as_str(v):
+    if isinstance(v, bytes):
+        return v.decode('utf-8')
+    if isinstance(v, np.ndarray) and v.shape == ():
+        return _as_str(v.item())
+    return str(v)
+
+
+def model_from_keras_h5(f) -> GruModel:
+    """Weights of the reference network from an open Keras HDF5 model file (``create_model``, precise/model.py:72-82:
+    ``GRU(units, name='net', activation='linear', ...)`` then ``Dense(1, activation='sigmoid')``; what ``model.save`` wrote,
+    precise/model.py:55-57 / scripts/train.py).  ``f`` is an ``h5py.File`` or anything with the same mapping interface:
+    ``f.attrs['model_config']`` (JSON) and ``f['model_weights'][layer][<weight names>]`` (``model_weights`` is absent in
+    weight-only files, where the layer groups sit at the root)."""
+    import json
+    root = f['model_weights'] if 'model_weights' in f else f
+    act, ract = 'linear', 'hard_sigmoid'
+    gru_name, dense_name = 'net', None
+    if 'model_config' in f.attrs:
+        cfg = json.loads(_as_str(f.attrs['model_config']))
+        layers = cfg.get('config', cfg)
+        layers = layers.get('layers', layers) if isinstance(layers, dict) else layers
+        for ly in layers:
+            c = ly.get('config', {})
+            if ly.get('class_name') == 'GRU':
+                gru_name = c.get('name', gru_name)
+                act = c.get('activation', act)
+                ract = c.get('recurrent_activation', ract)
+                if c.get('reset_after', False):
+                    raise ValueError('GRU(reset_after=True) is not the reference network (precise/model.py:77-80)')
+            elif ly.get('class_name') == 'Dense':
+                dense_name = c.get('name', dense_name)
+                if c.get('activation', 'sigmoid') != 'sigmoid':
+                    raise ValueError('the output layer must be Dense(1, activation="sigmoid")')
+
+    def datasets(group):
+        out = {}
+
+        def walk(g, prefix):
+            for k in g.keys():
+                v = g[k]
+                if hasattr(v, 'keys'):
+                    walk(v, prefix + k + '/')
+                else:
+                    out[prefix + k] = np.asarray(v)
+        walk(group, '')
+        return out
+
+    if dense_name is None:
+        cands = [k for k in root.keys() if k.startswith('dense')]
+        if len(cands) != 1:
+            raise ValueError('cannot identify the Dense layer among %r' % list(root.keys()))
+        dense_name = cands[0]
+    g = datasets(root[gru_name])
+    d = datasets(root[dense_name])
+
+    def pick(ds, stem):
+        hits = [v for k, v in ds.items() if k.split('/')[-1].split(':')[0] == stem]
+        if len(hits) != 1:
+            raise ValueError('expected one %r among %r' % (stem, sorted(ds)))
+        return hits[0]
+    return GruModel(pick(g, 'kernel'), pick(g, 'recurrent_kernel'), pick(g, 'bias'),
+                    pick(d, 'kernel').reshape(-1), pick(d, 'bias'), act, ract)
+
+
+def load_net(path: str) -> GruModel:
+    """Keras ``.net`` (HDF5) model file.  Needs ``h5py`` -- present wherever the reference itself runs (Keras depends on
+    it); this build image has none, so here ``.net`` files must first be converted where h5py exists:
+    ``python -m mycroft_precise_b200.model_io model.net model.npz``."""
+    try:
+        import h5py
+    except ImportError as e:
+        raise ImportError('reading Keras .net (HDF5) files needs h5py; convert on a machine that has it with '
+                          '`python -m mycroft_precise_b200.model_io model.net model.npz`, or use the frozen .pb') from e
+    with h5py.File(path, 'r') as f:
+        return model_from_keras_h5(f)
+
+
+if __name__ == '__main__':
+    import shutil
+    import sys
+    if len(sys.argv) != 3:
+        sys.exit('usage: python -m mycroft_precise_b200.model_io <model.net|model.pb|model.npz> <out.npz>')
+    save_weights(sys.argv[2], load_weights(sys.argv[1]))
+    import os
+    if os.path.isfile(sys.argv[1] + '.params'):
+        shutil.copyfile(sys.argv[1] + '.params', sys.argv[2] + '.params')
+    print('wrote', sys.argv[2])

@@ -246,7 +246,8 @@ def test_cached_projection_path_large_batch():
     model = m.GruModel.random(13, 20, seed=8, scale=0.1)
     model.dense_b = 3.0
     res = []
-    for mode in (0, 4, 1):                                           # 0: cp.async-prefetched scan, 4: plain loads, 1: CUDA cores
+    # 0: projection fused into the MFCC kernel + cp.async-prefetched scan, 4: plain loads, 5: separate input_proj_kernel, 1: CUDA cores
+    for mode in (0, 4, 5, 1):
         sb = m.StreamBatch(model, S, chunk_samples=chunk)
         sb.core.gru_mode(mode)
         raws = []

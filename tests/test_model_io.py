@@ -69,4 +69,59 @@ def test_npz_roundtrip_and_params_file(tmp_path):
     assert load_params(path).vectorizer == Vectorizer.speechpy_mfccs
     assert load_params(str(tmp_path / 'missing.npz')).to_dict() == ListenerParams().to_dict()
     with pytest.raises(ValueError):
-        load_weights(str(tmp_path / 'model.net'))
+        load_weights(str(tmp_path / 'model.h5x'))
+
+
+class _FakeH5Group(dict):
+    """Mapping with the part of the h5py Group / File interface that model_from_keras_h5 uses."""
+    def __init__(self, *a, **k):
+        super().__init__(*a, **k)
+        self.attrs = {}
+
+
+def _keras_like_file(m, with_model_weights=True, ract='hard_sigmoid'):
+    """Layout written by Keras 2.x model.save for precise/model.py:72-82 (layer 'net' = GRU, 'dense_1' = Dense)."""
+    import json
+    net = _FakeH5Group({'net': _FakeH5Group({'kernel:0': m.kernel, 'recurrent_kernel:0': m.recurrent, 'bias:0': m.bias})})
+    dense = _FakeH5Group({'dense_1': _FakeH5Group({'kernel:0': m.dense_w.reshape(-1, 1), 'bias:0': np.array([m.dense_b], np.float32)})})
+    weights = _FakeH5Group({'net': net, 'dense_1': dense})
+    f = _FakeH5Group({'model_weights': weights, 'optimizer_weights': _FakeH5Group()}) if with_model_weights else weights
+    cfg = {'class_name': 'Sequential', 'config': [
+        {'class_name': 'GRU', 'config': {'name': 'net', 'units': m.hidden, 'activation': 'linear',
+                                         'recurrent_activation': ract, 'dropout': 0.2}},
+        {'class_name': 'Dense', 'config': {'name': 'dense_1', 'units': 1, 'activation': 'sigmoid'}}]}
+    if with_model_weights:
+        f.attrs['model_config'] = json.dumps(cfg).encode('utf-8')
+    return f
+
+
+def test_keras_h5_layout_extraction():
+    from mycroft_precise_b200.model_io import GruModel, model_from_keras_h5
+    m = GruModel.random(13, 20, seed=4)
+    for full in (True, False):
+        got = model_from_keras_h5(_keras_like_file(m, with_model_weights=full))
+        for k in ('kernel', 'recurrent', 'bias', 'dense_w'):
+            assert np.array_equal(getattr(got, k), getattr(m, k))
+        assert got.dense_b == m.dense_b and got.activation == 'linear' and got.recurrent_activation == 'hard_sigmoid'
+    got = model_from_keras_h5(_keras_like_file(m, ract='sigmoid'))
+    assert got.recurrent_activation == 'sigmoid'
+    # Keras >= 2.2 nests the layer list one level deeper
+    f = _keras_like_file(m)
+    import json
+    cfg = json.loads(f.attrs['model_config'])
+    cfg['config'] = {'name': 'sequential_1', 'layers': cfg['config']}
+    f.attrs['model_config'] = json.dumps(cfg)
+    assert model_from_keras_h5(f).hidden == 20
+
+
+def test_net_file_without_h5py_fails_loudly(tmp_path):
+    from mycroft_precise_b200.model_io import load_weights
+    try:
+        import h5py  # noqa: F401
+        pytest.skip('h5py present')
+    except ImportError:
+        pass
+    p = tmp_path / 'm.net'
+    p.write_bytes(b'\x89HDF\r\n\x1a\n')
+    with pytest.raises(ImportError, match='h5py'):
+        load_weights(str(p))
