@@ -62,7 +62,7 @@ struct pb_handle {
     bool has_proj = false;           // default network: a second ring caches the input projections (gru_kernels.cuh)
     float* d_proj_ring = nullptr;
     bool proj_dirty = true;          // some ring rows lack a valid cached projection (weights changed / projection skipped)
-    float *d_proj_w = nullptr, *d_proj_b = nullptr, *d_proj_wq = nullptr;
+    float *d_proj_w = nullptr, *d_proj_b = nullptr;
     size_t k1_batch_smem = 0, k1_stream_smem = 0, k1_fast_smem = 0;
     bool force_generic = false;      // tests: exercise the generic kernels on the aligned geometry
     bool fast_ok = false;            // aligned geometry: warp-autonomous kernels (mfcc_fast.cuh)
@@ -93,7 +93,7 @@ struct pb_handle {
     bool tcb_ok = false;
     int tcb_kx = 0;
     float *d_tc5 = nullptr;           // tcgen05 GRU: [b1_hi | b1_lo | b2_hi | b2_lo | bias(80) | wd(24)]
-    int gru_mode = 0;                // 0 = auto, 1 = force CUDA-core small kernel, 2 = force tensor-core kernel, 3 = tcgen05 scan, 4 = tensor-core kernel without the cp.async prefetch, 5 = separate input_proj_kernel instead of the projection fused into K1
+    int gru_mode = 0;                // 0 = auto, 1 = force CUDA-core small kernel, 2 = force tensor-core kernel, 3 = tcgen05 scan, 7 = tensor-core kernel with 32-stream warp tiles
     float bd = 0.f;
     // host pipeline
     cudaStream_t pipe[HOST_PIPE] = {nullptr, nullptr, nullptr};
@@ -228,7 +228,7 @@ PB_API void pb_destroy(pb_handle* h) {
     cudaFree(h->d_tw_stage); cudaFree(h->d_tw_post); cudaFree(h->d_tw_any); cudaFree(h->d_cd); cudaFree(h->d_ptab); cudaFree(h->d_ctab); cudaFree(h->d_dct_t);
     cudaFree(h->st.n_samples); cudaFree(h->st.tail); cudaFree(h->st.ring); cudaFree(h->st.trig);
     cudaFree(h->d_wcat); cudaFree(h->d_bias); cudaFree(h->d_wd); cudaFree(h->d_count);
-    cudaFree(h->d_bfrag); cudaFree(h->d_mma_bias); cudaFree(h->d_mma_wd); cudaFree(h->d_proj_w); cudaFree(h->d_proj_b); cudaFree(h->d_proj_wq); cudaFree(h->d_proj_ring); cudaFree(h->d_tc5); cudaFree(h->d_tcb); cudaFree(h->d_dbg);
+    cudaFree(h->d_bfrag); cudaFree(h->d_mma_bias); cudaFree(h->d_mma_wd); cudaFree(h->d_proj_w); cudaFree(h->d_proj_b); cudaFree(h->d_proj_ring); cudaFree(h->d_tc5); cudaFree(h->d_tcb); cudaFree(h->d_dbg);
     if (h->h_count_pinned) cudaFreeHost(h->h_count_pinned);
     for (int i = 0; i < HOST_PIPE; ++i) {
         cudaFree(h->d_stage_pcm[i]); cudaFree(h->d_stage_ids[i]); cudaFree(h->d_stage_raw[i]);
@@ -485,16 +485,6 @@ PB_API int pb_load_weights(pb_handle* h, const float* kernel, const float* recur
             cudaFree(h->d_proj_w); cudaFree(h->d_proj_b); h->d_proj_w = h->d_proj_b = nullptr;
             CK(upload(&h->d_proj_w, pw));
             CK(upload(&h->d_proj_b, pbias));
-            // same weights for the projection fused into the MFCC kernel (mfcc_fast.cuh ProjFuse): wq[c][16], c = gate * 20 + unit
-            std::vector<float> wq((size_t)PROJ_STRIDE * 16, 0.f);
-            for (int gate = 0; gate < 3; ++gate)
-                for (int u = 0; u < H; ++u) {
-                    float* q = &wq[(size_t)(gate * H + u) * 16];
-                    for (int f = 0; f < F; ++f) q[f] = kernel[(size_t)f * H3 + gate * H + u];
-                    q[13] = bias[gate * H + u];
-                }
-            cudaFree(h->d_proj_wq); h->d_proj_wq = nullptr;
-            CK(upload(&h->d_proj_wq, wq));
         }
         std::vector<float> mb(72, 0.f), mw(24, 0.f);
         for (int gate = 0; gate < 3; ++gate)
@@ -530,7 +520,6 @@ PB_API int pb_load_weights(pb_handle* h, const float* kernel, const float* recur
             for (int u = 0; u < H; ++u) { tb[u] = bias[u]; tb[24 + u] = bias[H + u]; tb[48 + u] = bias[2 * H + u]; tw[u] = dense_w[u]; }
             cudaFree(h->d_tc5); h->d_tc5 = nullptr;
             CK(upload(&h->d_tc5, t));
-            CK(cudaFuncSetAttribute(gru_mma_kernel<20, 13, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MMA_PRE_SMEM));
             CK(cudaFuncSetAttribute(gru_tc5_kernel<20, 13, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Tc5Smem) + 128));
             CK(cudaFuncSetAttribute(gru_tc5_kernel<20, 13, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Tc5Smem) + 128));
         }
@@ -737,8 +726,13 @@ static int launch_gru(pb_handle* h, const K2In& in, bool ring, int64_t n, const 
         w.bfrag = h->d_bfrag; w.bias = h->d_mma_bias; w.wd = h->d_mma_wd; w.bd = h->bd;
         const int per_cta = (MMA_THREADS / 32) * 16 * MMA_MB;
         const int grid = (int)((n + per_cta - 1) / per_cta);
-        if (ring && in.proj != nullptr && h->gru_mode != 4) gru_mma_kernel<20, 13, true, true, true><<<grid, MMA_THREADS, MMA_PRE_SMEM, s>>>(w, in, n, dp, o);
-        else if (ring && in.proj != nullptr) gru_mma_kernel<20, 13, true, true><<<grid, MMA_THREADS, 0, s>>>(w, in, n, dp, o);   // mode 4: no prefetch (A/B)
+        // Steady-state stream scan: 16-stream tiles (MB = 1) unless forced (gru_mode 7).  With 32-stream tiles 131 072 streams
+        // are 2.3 rounds of 3 CTAs/SM and the last, 31 % full round still costs most of a round (each warp's step is a
+        // dependent chain); 16-stream tiles fit 5 CTAs/SM and leave a much shorter tail.
+        if (ring && in.proj != nullptr && h->gru_mode != 7) {
+            const int per1 = (MMA_THREADS / 32) * 16;
+            gru_mma_kernel<20, 13, true, true, 1><<<(int)((n + per1 - 1) / per1), MMA_THREADS, 0, s>>>(w, in, n, dp, o);
+        } else if (ring && in.proj != nullptr) gru_mma_kernel<20, 13, true, true><<<grid, MMA_THREADS, 0, s>>>(w, in, n, dp, o);
         else if (ring) gru_mma_kernel<20, 13, true, false><<<grid, MMA_THREADS, 0, s>>>(w, in, n, dp, o);
         else gru_mma_kernel<20, 13, false, false><<<grid, MMA_THREADS, 0, s>>>(w, in, n, dp, o);
     } else if (h->small_path) {
@@ -804,10 +798,7 @@ static int check_tick(pb_handle* h, const void* pcm, int64_t n) {
     return PB_OK;
 }
 
-// fuse_proj: also write the GRU input projections of the new frames (fast kernel only); *fused reports whether it happened
-static int launch_stream_mfcc(pb_handle* h, const int16_t* d_pcm, const int32_t* d_ids, int64_t n, cudaStream_t s,
-                              bool fuse_proj = false, bool* fused = nullptr) {
-    if (fused) *fused = false;
+static int launch_stream_mfcc(pb_handle* h, const int16_t* d_pcm, const int32_t* d_ids, int64_t n, cudaStream_t s) {
     const bool pairs = (h->cfg.chunk_samples % 2 == 0) && (h->cfg.hop_samples % 2 == 0) && (h->used % 2 == 0) &&
                        ((uintptr_t)d_pcm % 4 == 0);
     const int64_t tiles = (n + K1_STREAMS_PER_CTA - 1) / K1_STREAMS_PER_CTA;
@@ -820,13 +811,8 @@ static int launch_stream_mfcc(pb_handle* h, const int16_t* d_pcm, const int32_t*
         const int spw = (int)std::max<int64_t>(1, std::min<int64_t>(K1F_STREAMS_PER_WARP, (n + warps_total - 1) / warps_total));
         const int64_t tilesf = (n + spw - 1) / spw;
         const int gridf = (int)std::min<int64_t>((tilesf + K1F_WARPS - 1) / K1F_WARPS, (int64_t)h->sm_count * 4);
-        ProjFuse pf{nullptr, nullptr};
-        if (fuse_proj && h->d_proj_wq && h->d_proj_ring) {
-            pf.wq = reinterpret_cast<const float4*>(h->d_proj_wq); pf.ring = h->d_proj_ring;
-            if (fused) *fused = true;
-        }
         mfcc_fast_stream_kernel<<<gridf, K1F_THREADS, h->k1_fast_smem, s>>>(d_pcm, d_ids, (int)n, h->cfg.chunk_samples, h->cfg.hop_samples, spw, scale,
-                                                                            mel_tables(h), fast_tables(h), h->st, pf);
+                                                                            mel_tables(h), fast_tables(h), h->st);
     } else if (pairs)
         mfcc_stream_kernel<true><<<grid, K1_THREADS, h->k1_stream_smem, s>>>(d_pcm, d_ids, (int)n, h->cfg.chunk_samples, h->cfg.hop_samples, h->used, scale, mel_tables(h), h->st);
     else
@@ -851,26 +837,18 @@ PB_API int pb_update(pb_handle* h, const int16_t* d_pcm, const int32_t* d_ids, i
     if (!d_conf) return fail(PB_ERR_INVALID, "null d_conf");
     CK(cudaSetDevice(h->cfg.device));
     cudaStream_t s = (cudaStream_t)stream;
-    // default network, large batch: the tensor-core scan reads cached input projections.  The fast MFCC kernel writes them
-    // for the frames it produces (gru_mode 5 keeps the separate input_proj_kernel for A/B runs and the generic MFCC kernels
-    // always need it); a dirty cache (weights changed, or ticks that skipped the projection) is rebuilt once for every row.
-    const bool want_proj = h->has_proj && h->small_path && n > K2_WARP_PATH_MAX &&
-                           (h->gru_mode == 0 || h->gru_mode == 2 || h->gru_mode == 4 || h->gru_mode == 5);
-    bool fused = false;
-    // fused for small ticks too (a few hundred extra instructions per frame): the cache then stays valid across batch sizes
-    rc = launch_stream_mfcc(h, d_pcm, d_ids, n, s, h->has_proj && h->small_path && h->gru_mode != 5, &fused);
+    rc = launch_stream_mfcc(h, d_pcm, d_ids, n, s);
     if (rc != PB_OK) return rc;
     bool use_proj = false;
     if (h->has_proj && h->small_path) {
-        if (want_proj) {
+        if (n > K2_WARP_PATH_MAX && (h->gru_mode == 0 || h->gru_mode == 2 || h->gru_mode == 7)) {
+            ProfScope ps(h, 3, s);
             if (h->proj_dirty) {                               // bring every ring row up to date once, then stay incremental
-                ProfScope ps(h, 3, s);
                 const long long rows = (long long)h->cfg.max_streams * h->ring_rows;
                 const int grid = (int)std::min<long long>((rows + PROJ_FRAMES_PER_CTA - 1) / PROJ_FRAMES_PER_CTA, (long long)h->sm_count * 16);
                 input_proj_all_kernel<13><<<grid, 64 * PROJ_FRAMES_PER_CTA, 0, s>>>(h->d_proj_w, h->d_proj_b, rows, h->st.ring, h->row_stride, h->d_proj_ring);
                 h->proj_dirty = false;
-            } else if (!fused) {
-                ProfScope ps(h, 3, s);
+            } else {
                 const long long items = (long long)n * h->max_new;
                 const int grid = (int)((items + PROJ_THREADS - 1) / PROJ_THREADS);     // 32 frames per warp
                 input_proj_kernel<13><<<grid, PROJ_THREADS, 0, s>>>(h->d_bfrag, h->d_proj_b, h->st.n_samples, d_ids, (int)n,
@@ -878,7 +856,7 @@ PB_API int pb_update(pb_handle* h, const int16_t* d_pcm, const int32_t* d_ids, i
             }
             CK(cudaGetLastError());
             use_proj = true;
-        } else if (!fused) {
+        } else {
             h->proj_dirty = true;                              // this tick's frames get no projection
         }
     }

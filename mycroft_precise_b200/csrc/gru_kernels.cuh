@@ -418,21 +418,21 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], 
 // 3xTF32: d += a_lo b_hi + a_hi b_lo + a_hi b_hi for a group of NG n-tiles and MB row blocks.  The three
 // terms are issued as three sweeps over the group so that consecutive MMAs never target the same
 // accumulator (dependent distance NG * MB instructions).
-template <int NG>
+template <int NG, int MB>
 __device__ __forceinline__ void mma3_group(float (*acc)[MMA_NT][4], int nt0, const uint32_t (*ah)[4], const uint32_t (*al)[4],
                                            const float4 (&w)[NG]) {
 #pragma unroll
     for (int q = 0; q < NG; ++q)
 #pragma unroll
-        for (int mb = 0; mb < MMA_MB; ++mb) mma_tf32(acc[mb][nt0 + q], al[mb], __float_as_uint(w[q].x), __float_as_uint(w[q].y));
+        for (int mb = 0; mb < MB; ++mb) mma_tf32(acc[mb][nt0 + q], al[mb], __float_as_uint(w[q].x), __float_as_uint(w[q].y));
 #pragma unroll
     for (int q = 0; q < NG; ++q)
 #pragma unroll
-        for (int mb = 0; mb < MMA_MB; ++mb) mma_tf32(acc[mb][nt0 + q], ah[mb], __float_as_uint(w[q].z), __float_as_uint(w[q].w));
+        for (int mb = 0; mb < MB; ++mb) mma_tf32(acc[mb][nt0 + q], ah[mb], __float_as_uint(w[q].z), __float_as_uint(w[q].w));
 #pragma unroll
     for (int q = 0; q < NG; ++q)
 #pragma unroll
-        for (int mb = 0; mb < MMA_MB; ++mb) mma_tf32(acc[mb][nt0 + q], ah[mb], __float_as_uint(w[q].x), __float_as_uint(w[q].y));
+        for (int mb = 0; mb < MB; ++mb) mma_tf32(acc[mb][nt0 + q], ah[mb], __float_as_uint(w[q].x), __float_as_uint(w[q].y));
 }
 
 // hi = a with the 13 low mantissa bits cleared (what the tensor core reads anyway), lo = a - hi (exact in
@@ -449,26 +449,12 @@ __device__ __forceinline__ void split_tf32(const float (&v)[4], uint32_t (&hi)[4
 // PROJ (stream mode): the input projection x_t.[Wz|Wr|Wh] + b of every frame was computed once when the frame was
 // produced (input_proj_kernel) and sits in the ring next to the MFCC row, so the scan only runs the recurrent products:
 // 162 instead of 270 HMMA per step on the pipe that bounds this kernel.
-// PRE (with PROJ): the projection rows of step s+1 are fetched with cp.async into per-thread shared-memory slots while
-// step s computes -- the loads are scattered 32-byte sectors whose loaded DRAM latency (several microseconds at 131 072
-// streams) is otherwise exposed at the top of every step (ncu: long_scoreboard was the first stall reason).
-constexpr int MMA_PRE_SLOTS = 2 * MMA_MB * MMA_NT;                      // float2 slots per thread
-constexpr int MMA_PRE_SMEM = (MMA_THREADS / 32) * MMA_PRE_SLOTS * 32 * 8;  // bytes of dynamic shared memory
-
-__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit_wait_all(bool wait) {
-    if (wait) asm volatile("cp.async.wait_all;" ::: "memory");
-    else asm volatile("cp.async.commit_group;" ::: "memory");
-}
-
-template <int H, int F, bool RING, bool PROJ, bool PRE = false>
-__global__ void __launch_bounds__(MMA_THREADS, 3)
+// MB = row blocks of 16 streams per warp.  2 halves the weight-fragment traffic per MMA; 1 halves the tile (and the
+// registers: 5 instead of 3 CTAs per SM), which matters for the tail of the grid -- see launch_gru.
+template <int H, int F, bool RING, bool PROJ, int MB = MMA_MB>
+__global__ void __launch_bounds__(MMA_THREADS, MB == 1 ? 5 : 3)
 gru_mma_kernel(GruMmaW W, K2In in, long long n, DecodeParams dp, K2Out out) {
     static_assert(H <= 24 && F <= 16, "tile counts are fixed");
-    static_assert(!PRE || PROJ, "the prefetch variant reads cached projections");
-    extern __shared__ __align__(16) unsigned char mma_dyn_smem[];
     __shared__ float4 sB[MMA_KT * MMA_NT * 32];
     __shared__ float sBias[3 * 24];
     __shared__ float sWd[24];
@@ -477,16 +463,16 @@ gru_mma_kernel(GruMmaW W, K2In in, long long n, DecodeParams dp, K2Out out) {
     for (int e = threadIdx.x; e < 24; e += blockDim.x) sWd[e] = __ldg(W.wd + e);
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
-    const long long base = ((long long)blockIdx.x * (MMA_THREADS / 32) + warp) * (16 * MMA_MB);
+    const long long base = ((long long)blockIdx.x * (MMA_THREADS / 32) + warp) * (16 * MB);
     if (base >= n) return;
     // rows of this thread: stream (mb, hf) = base + 16 mb + g + 8 hf
-    long long idx[MMA_MB][2];
-    int sid[MMA_MB][2];
-    long long rel[MMA_MB][2];
-    RingCursor cur[MMA_MB][2];
-    bool ok[MMA_MB][2];
+    long long idx[MB][2];
+    int sid[MB][2];
+    long long rel[MB][2];
+    RingCursor cur[MB][2];
+    bool ok[MB][2];
 #pragma unroll
-    for (int mb = 0; mb < MMA_MB; ++mb)
+    for (int mb = 0; mb < MB; ++mb)
 #pragma unroll
         for (int hf = 0; hf < 2; ++hf) {
             idx[mb][hf] = base + 16 * mb + g + 8 * hf;
@@ -501,61 +487,21 @@ gru_mma_kernel(GruMmaW W, K2In in, long long n, DecodeParams dp, K2Out out) {
             }
         }
     // h in accumulator layout: hreg[mb][tile][e], e = (row g: units 2t, 2t+1; row g+8: units 2t, 2t+1) of tile
-    float hreg[MMA_MB][3][4];
+    float hreg[MB][3][4];
 #pragma unroll
-    for (int mb = 0; mb < MMA_MB; ++mb)
+    for (int mb = 0; mb < MB; ++mb)
 #pragma unroll
         for (int nt = 0; nt < 3; ++nt)
 #pragma unroll
             for (int e = 0; e < 4; ++e) hreg[mb][nt][e] = 0.f;
 
-    // PRE: slot j = (2 mb + hf) * 9 + nt of this thread at pre[j * 32] (lanes interleaved: conflict-free LDS.64)
-    float2* pre = reinterpret_cast<float2*>(mma_dyn_smem) + (size_t)warp * MMA_PRE_SLOTS * 32 + lane;
-    unsigned vnext = 0;                                                  // bit (2 mb + hf): the prefetched row exists
-    auto prefetch = [&](int step) {
-        vnext = 0;
-#pragma unroll
-        for (int mb = 0; mb < MMA_MB; ++mb)
-#pragma unroll
-            for (int hf = 0; hf < 2; ++hf) {
-                const float* row = ok[mb][hf] ? cur[mb][hf].next(step) : nullptr;
-                if (row != nullptr) {
-                    vnext |= 1u << (2 * mb + hf);
-#pragma unroll
-                    for (int nt = 0; nt < MMA_NT; ++nt)
-                        if (nt % 3 != 2 || t < 2) cp_async8(pre + ((2 * mb + hf) * MMA_NT + nt) * 32, row + proj_col(nt, t));
-                }
-            }
-        cp_async_commit_wait_all(false);
-    };
-    if (PRE) prefetch(0);
-
 #pragma unroll 1
     for (int step = 0; step < in.T; ++step) {
-        float acc[MMA_MB][MMA_NT][4];
-        if (PRE) {
-            // ---- accumulators start from the prefetched projection; then the next step's rows start to stream in
-            cp_async_commit_wait_all(true);
-            const unsigned vcur = vnext;
-#pragma unroll
-            for (int mb = 0; mb < MMA_MB; ++mb)
-#pragma unroll
-                for (int hf = 0; hf < 2; ++hf) {
-                    const bool have = (vcur >> (2 * mb + hf)) & 1u;
-#pragma unroll
-                    for (int nt = 0; nt < MMA_NT; ++nt) {
-                        float2 v;
-                        if (!have) v = make_float2(sBias[8 * nt + 2 * t], sBias[8 * nt + 2 * t + 1]);
-                        else if (nt % 3 != 2 || t < 2) v = pre[((2 * mb + hf) * MMA_NT + nt) * 32];
-                        else v = make_float2(0.f, 0.f);
-                        acc[mb][nt][2 * hf] = v.x; acc[mb][nt][2 * hf + 1] = v.y;
-                    }
-                }
-            if (step + 1 < in.T) prefetch(step + 1);
-        } else if (PROJ) {
+        float acc[MB][MMA_NT][4];
+        if (PROJ) {
             // ---- accumulators start from the cached projection (bias included); rows before the stream's first frame: bias
 #pragma unroll
-            for (int mb = 0; mb < MMA_MB; ++mb)
+            for (int mb = 0; mb < MB; ++mb)
 #pragma unroll
                 for (int hf = 0; hf < 2; ++hf) {
                     const float* row = ok[mb][hf] ? cur[mb][hf].next(step) : nullptr;
@@ -570,9 +516,9 @@ gru_mma_kernel(GruMmaW W, K2In in, long long n, DecodeParams dp, K2Out out) {
                 }
         } else {
             // ---- A fragments of x_t: a0 = (row g, k 2t), a1 = (row g+8, k 2t), a2 = (row g, k 2t+1), a3 = (row g+8, k 2t+1)
-            uint32_t xh[MMA_MB][2][4], xl[MMA_MB][2][4];
+            uint32_t xh[MB][2][4], xl[MB][2][4];
 #pragma unroll
-            for (int mb = 0; mb < MMA_MB; ++mb) {
+            for (int mb = 0; mb < MB; ++mb) {
                 float xv[2][2][2];                               // [kt][hf][j]
 #pragma unroll
                 for (int hf = 0; hf < 2; ++hf) {
@@ -597,14 +543,14 @@ gru_mma_kernel(GruMmaW W, K2In in, long long n, DecodeParams dp, K2Out out) {
             for (int nt = 0; nt < MMA_NT; ++nt) {
                 const float b0 = sBias[8 * nt + 2 * t], b1 = sBias[8 * nt + 2 * t + 1];
 #pragma unroll
-                for (int mb = 0; mb < MMA_MB; ++mb) { acc[mb][nt][0] = b0; acc[mb][nt][1] = b1; acc[mb][nt][2] = b0; acc[mb][nt][3] = b1; }
+                for (int mb = 0; mb < MB; ++mb) { acc[mb][nt][0] = b0; acc[mb][nt][1] = b1; acc[mb][nt][2] = b0; acc[mb][nt][3] = b1; }
             }
             // ---- x part for all three gates
 #pragma unroll
             for (int kt = 0; kt < 2; ++kt) {
-                uint32_t ah[MMA_MB][4], al[MMA_MB][4];
+                uint32_t ah[MB][4], al[MB][4];
 #pragma unroll
-                for (int mb = 0; mb < MMA_MB; ++mb)
+                for (int mb = 0; mb < MB; ++mb)
 #pragma unroll
                     for (int e = 0; e < 4; ++e) { ah[mb][e] = xh[mb][kt][e]; al[mb][e] = xl[mb][kt][e]; }
 #pragma unroll
@@ -612,16 +558,16 @@ gru_mma_kernel(GruMmaW W, K2In in, long long n, DecodeParams dp, K2Out out) {
                     float4 w[3];
 #pragma unroll
                     for (int q = 0; q < 3; ++q) w[q] = sB[(kt * MMA_NT + ng + q) * 32 + lane];
-                    mma3_group<3>(acc, ng, ah, al, w);
+                    mma3_group<3, MB>(acc, ng, ah, al, w);
                 }
             }
         }
         // ---- h part for z and r
 #pragma unroll
         for (int kt = 0; kt < 3; ++kt) {
-            uint32_t ah[MMA_MB][4], al[MMA_MB][4];
+            uint32_t ah[MB][4], al[MB][4];
 #pragma unroll
-            for (int mb = 0; mb < MMA_MB; ++mb) {
+            for (int mb = 0; mb < MB; ++mb) {
                 const float v[4] = {hreg[mb][kt][0], hreg[mb][kt][2], hreg[mb][kt][1], hreg[mb][kt][3]};
                 split_tf32(v, ah[mb], al[mb]);
             }
@@ -630,15 +576,15 @@ gru_mma_kernel(GruMmaW W, K2In in, long long n, DecodeParams dp, K2Out out) {
                 float4 w[3];
 #pragma unroll
                 for (int q = 0; q < 3; ++q) w[q] = sB[((2 + kt) * MMA_NT + ng + q) * 32 + lane];
-                mma3_group<3>(acc, ng, ah, al, w);
+                mma3_group<3, MB>(acc, ng, ah, al, w);
             }
         }
         // ---- gates; r * h becomes the A operand of the candidate product
 #pragma unroll
         for (int kt = 0; kt < 3; ++kt) {
-            uint32_t ah[MMA_MB][4], al[MMA_MB][4];
+            uint32_t ah[MB][4], al[MB][4];
 #pragma unroll
-            for (int mb = 0; mb < MMA_MB; ++mb) {
+            for (int mb = 0; mb < MB; ++mb) {
                 float rh[4];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) rh[e] = hard_sigmoid(acc[mb][3 + kt][e]) * hreg[mb][kt][e];
@@ -649,11 +595,11 @@ gru_mma_kernel(GruMmaW W, K2In in, long long n, DecodeParams dp, K2Out out) {
                 float4 w[3];
 #pragma unroll
                 for (int q = 0; q < 3; ++q) w[q] = sB[((2 + kt) * MMA_NT + 6 + q) * 32 + lane];
-                mma3_group<3>(acc, 6, ah, al, w);
+                mma3_group<3, MB>(acc, 6, ah, al, w);
             }
         }
 #pragma unroll
-        for (int mb = 0; mb < MMA_MB; ++mb)
+        for (int mb = 0; mb < MB; ++mb)
 #pragma unroll
             for (int nt = 0; nt < 3; ++nt)
 #pragma unroll
@@ -664,7 +610,7 @@ gru_mma_kernel(GruMmaW W, K2In in, long long n, DecodeParams dp, K2Out out) {
     }
     // ---- Dense(1): per-thread partial over its 6 units per row, reduced over the quad
 #pragma unroll
-    for (int mb = 0; mb < MMA_MB; ++mb)
+    for (int mb = 0; mb < MB; ++mb)
 #pragma unroll
         for (int hf = 0; hf < 2; ++hf) {
             float part = 0.f;

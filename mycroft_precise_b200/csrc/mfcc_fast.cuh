@@ -68,15 +68,6 @@ struct FastTables {            // device copies built by the host (api.cu)
     int npl, maxc, nol;
 };
 
-// Fused input projection (default network, stream kernel only): the lanes that produced a frame's 13 MFCCs also compute the
-// GRU input projection b + x . [Wz|Wr|Wh] (60 columns, gru_kernels.cuh PROJ_STRIDE) and store it in the projection ring,
-// replacing the separate input_proj_kernel launch.  wq[c][16]: column c's 13 weights, the bias at [13], zeros after.
-struct ProjFuse {
-    const float4* wq;          // [60][4]; nullptr: no projection
-    float* ring;               // [max_streams][ring_rows][60]
-};
-constexpr int K1F_PROJ_COLS = 60;
-
 struct K1FWarp {               // per warp
     float2 buf[2][2][K1F_BUF_ELEMS];           // [stage][half]: input staging -> transpose scratch -> power bins
     float part[2][K1F_PART];
@@ -116,7 +107,7 @@ __device__ __forceinline__ K1FTab load_fast_tables(unsigned char* smem, const Me
 // All 32 lanes of the warp call this (the other half works on its own frame); `active` gates the store.
 __device__ __forceinline__ void mel16(const float* P, const K1FTab& tb, const FastTables& ft, const MelTables& t,
                                       float* part, float* mel, const int (&eoff)[8], int l16, bool active,
-                                      float* __restrict__ out, float* feat = nullptr) {
+                                      float* __restrict__ out) {
     const char* Pb = reinterpret_cast<const char*>(P);
     float tot = 0.f;
 #pragma unroll 1
@@ -161,7 +152,6 @@ __device__ __forceinline__ void mel16(const float* P, const K1FTab& tb, const Fa
             if (t.n_filt & 1) a0 = fmaf(d[(t.n_filt - 1) * ld], mel[t.n_filt - 1], a0);
             const float v = c == 0 ? logf(fmaxf(tot, K1_EPS)) : a0 + a1;
             if (active) out[c] = v;
-            if (feat != nullptr) feat[c] = v;          // disjoint from mel[]: see fast_pass
         }
     }
     __syncwarp();
@@ -170,8 +160,7 @@ __device__ __forceinline__ void mel16(const float* P, const K1FTab& tb, const Fa
 // One FFT + mel pass for the warp's two frames whose 1 KB inputs have landed in ws.buf[stage].
 __device__ __forceinline__ void fast_pass(K1FWarp& ws, int stage, uint32_t parity, const FftLaneConst& lc, const K1FTab& tb,
                                           const FastTables& ft, const MelTables& t, float scale, const int (&eoff)[8],
-                                          int l16, int half, bool active, float* __restrict__ out,
-                                          const float4* __restrict__ wq = nullptr, float* __restrict__ prow = nullptr) {
+                                          int l16, int half, bool active, float* __restrict__ out) {
     mbar_wait(&ws.bar[stage], parity);
     const int* in = reinterpret_cast<const int*>(ws.buf[stage][half]);
     cpx z[16];
@@ -188,28 +177,7 @@ __device__ __forceinline__ void fast_pass(K1FWarp& ws, int stage, uint32_t parit
     fft512_power(z, lc, ws.buf[stage][half], P, scale, l16, active);   // P aliases the scratch: written after the last scratch read
     if (l16 == 0) P[K1F_ZERO_BIN] = 0.f;           // padding entries of the piece table point here
     __syncwarp();
-    if (wq == nullptr) { mel16(P, tb, ft, t, ws.part[half], ws.mel[half], eoff, l16, active, out); return; }
-    // fused input projection: the frame's outputs are parked in the (now dead) rise partials, then lane l16 owns columns
-    // l16 + 16 q.  Weights come through L1 (3.8 KB, every warp reads the same lines).
-    float* feat = ws.part[half];
-    mel16(P, tb, ft, t, ws.part[half], ws.mel[half], eoff, l16, active, out, feat);
-    float x[13];
-#pragma unroll
-    for (int f = 0; f < 13; ++f) x[f] = feat[f];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        const int c = l16 + 16 * q;
-        if (c < K1F_PROJ_COLS) {
-            const float4 w0 = __ldg(wq + 4 * c), w1 = __ldg(wq + 4 * c + 1), w2 = __ldg(wq + 4 * c + 2), w3 = __ldg(wq + 4 * c + 3);
-            float a = w3.y;                                              // bias
-            a = fmaf(x[0], w0.x, a); a = fmaf(x[1], w0.y, a); a = fmaf(x[2], w0.z, a); a = fmaf(x[3], w0.w, a);
-            a = fmaf(x[4], w1.x, a); a = fmaf(x[5], w1.y, a); a = fmaf(x[6], w1.z, a); a = fmaf(x[7], w1.w, a);
-            a = fmaf(x[8], w2.x, a); a = fmaf(x[9], w2.y, a); a = fmaf(x[10], w2.z, a); a = fmaf(x[11], w2.w, a);
-            a = fmaf(x[12], w3.x, a);
-            if (active) prow[c] = a;
-        }
-    }
-    __syncwarp();                                                        // feat (= part) is reused by the next pass
+    mel16(P, tb, ft, t, ws.part[half], ws.mel[half], eoff, l16, active, out);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -264,7 +232,7 @@ mfcc_fast_batch_kernel(const int16_t* __restrict__ pcm, long long samples_per_st
 // Stateful tick (pb_update / pb_update_vectors on the aligned geometry): a warp owns 16 streams.
 __global__ void __launch_bounds__(K1F_THREADS, 4)
 mfcc_fast_stream_kernel(const int16_t* __restrict__ pcm, const int* __restrict__ ids, int n, int chunk, int hop, int spw,
-                        float scale, MelTables tab, FastTables ft, StreamState st, ProjFuse pf) {
+                        float scale, MelTables tab, FastTables ft, StreamState st) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     K1FWarp* wsm = reinterpret_cast<K1FWarp*>(smem_raw);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, l16 = lane & 15, half = lane >> 4;
@@ -337,16 +305,13 @@ mfcc_fast_stream_kernel(const int16_t* __restrict__ pcm, const int* __restrict__
             if (f0 + 2 < nf && lane == 0) issue(f0 + 2, stage ^ 1);
             const bool active = f0 + half < nf;
             float* row = st.ring;
-            float* prow = pf.ring;
             if (active) {
                 const int t = ws.fr_stream[f0 + half];
                 const long long k = ws.st_c0[t] + ws.fr_sub[f0 + half];
-                const long long r = (long long)ws.st_id[t] * st.ring_rows + (int)(k % st.ring_rows);
-                row = st.ring + r * st.row_stride;
-                prow = pf.ring + r * K1F_PROJ_COLS;
+                row = st.ring + ((long long)ws.st_id[t] * st.ring_rows + (int)(k % st.ring_rows)) * st.row_stride;
             }
             const uint32_t parity = (stage == 0 ? uses0 : uses1) & 1;
-            fast_pass(ws, stage, parity, lc, tb, ft, tab, scale, eoff, l16, half, active, row, pf.wq, prow);
+            fast_pass(ws, stage, parity, lc, tb, ft, tab, scale, eoff, l16, half, active, row);
             if (stage == 0) ++uses0; else ++uses1;
         }
         // ---- tail + sample counter.  Every old-tail read of this tile is complete (the bulk copies that read it

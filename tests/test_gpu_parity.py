@@ -246,8 +246,8 @@ def test_cached_projection_path_large_batch():
     model = m.GruModel.random(13, 20, seed=8, scale=0.1)
     model.dense_b = 3.0
     res = []
-    # 0: projection fused into the MFCC kernel + cp.async-prefetched scan, 4: plain loads, 5: separate input_proj_kernel, 1: CUDA cores
-    for mode in (0, 4, 5, 1):
+    # 0: tensor-core scan over cached projections, 16-stream warp tiles; 7: the same with 32-stream tiles; 1: CUDA cores
+    for mode in (0, 7, 1):
         sb = m.StreamBatch(model, S, chunk_samples=chunk)
         sb.core.gru_mode(mode)
         raws = []
@@ -268,7 +268,9 @@ def test_cached_projection_path_large_batch():
     for r, c in res[:-1]:
         assert np.max(np.abs(r - res[-1][0])) < 1e-5
         assert c > 0 and abs(c - res[-1][1]) <= 3
-    assert np.array_equal(res[0][0], res[1][0])                      # same arithmetic, different load path
+    a, b = res[0][0].copy(), res[1][0].copy()                        # same arithmetic per stream, different tiling ...
+    a[25, :5] = b[25, :5] = 0                                        # ... except the 5-stream tick (warp-per-stream kernel vs forced MMA)
+    assert np.array_equal(a, b)
 
 
 def _generic_case(pr_kw, H, act='linear', ract='hard_sigmoid', N=200, seed=5, mode=0):
