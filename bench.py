@@ -168,6 +168,12 @@ def run_reference(args, rank):
         if step >= args.warmup:
             rates.append(r)
     v = float(np.mean(rates))
+    try:                                           # extra evidence: the compiled scalar C restatement on the same cores
+        cc = cpu_c_port_rate()
+        cpu_c = {'value': cc[0], 'unit': 'stream-updates/s', 'cores': cc[1], 'kind': 'port', 'sample': cc[2]}
+    except Exception as e:
+        cpu_c = None
+        print('note: C port baseline skipped: %r' % (e,), file=sys.stderr)
     line = {
         'impl': 'reference', 'metric': 'stream-updates/s (16 kHz int16 PCM, 1024-sample chunk -> decoded confidence + trigger)',
         'value': v, 'unit': 'stream-updates/s', 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
@@ -180,6 +186,9 @@ def run_reference(args, rank):
         'cpu_baseline': {'value': v, 'unit': 'stream-updates/s', 'cores': cores, 'kind': 'port', 'sample': sample + ' per step'},
         'e2e': {'value': v, 'unit': 'stream-updates/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'realtime_streams': v / 15.625,
+        'cpu_baseline_c': cpu_c,
+        'note': 'value = numpy oracle port (the reference itself is Python + numpy + Keras/TF per Listener); cpu_baseline_c = the same '
+                'path as compiled scalar C, a stronger CPU baseline than the reference could reach',
     }
     print(json.dumps(line))
 
