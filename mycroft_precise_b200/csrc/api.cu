@@ -10,7 +10,10 @@
 #include <string.h>
 
 #include <algorithm>
+#include <map>
+#include <mutex>
 #include <new>
+#include <utility>
 #include <vector>
 
 #include "../../include/precise_b200.h"
@@ -62,6 +65,7 @@ struct pb_handle {
     bool has_proj = false;           // default network: a second ring caches the input projections (gru_kernels.cuh)
     float* d_proj_ring = nullptr;
     bool proj_dirty = true;          // some ring rows lack a valid cached projection (weights changed / projection skipped)
+    bool host_tick_proj = false;     // inside a pb_update_host tick whose sub-batches use the cache: short sub-batches keep it valid too
     float *d_proj_w = nullptr, *d_proj_b = nullptr;
     size_t k1_batch_smem = 0, k1_stream_smem = 0, k1_fast_smem = 0;
     bool force_generic = false;      // tests: exercise the generic kernels on the aligned geometry
@@ -185,6 +189,23 @@ static cudaError_t upload(T** dst, const std::vector<T>& v) {
 }
 
 static bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize belongs to the kernel, not to a handle: handles with different geometries
+// (n_filt, hidden, ...) coexist in one process, so only ever raise it -- to the largest size any handle has asked for.
+template <typename K>
+static cudaError_t ensure_dyn_smem(K kernel, size_t bytes) {
+    static std::mutex mu;
+    static std::map<std::pair<int, const void*>, size_t> granted;     // per (device, kernel): the attribute lives in the context
+    int dev = 0;
+    cudaError_t e0 = cudaGetDevice(&dev);
+    if (e0 != cudaSuccess) return e0;
+    std::lock_guard<std::mutex> lock(mu);
+    size_t& cur = granted[std::make_pair(dev, (const void*)kernel)];
+    if (bytes <= cur) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e == cudaSuccess) cur = bytes;
+    return e;
+}
 
 // ------------------------------------------------------------------------------------------------
 #define PB_API extern "C" __attribute__((visibility("default")))
@@ -393,14 +414,14 @@ PB_API int pb_create(const pb_config* cfg, pb_handle** out) {
     CKH(cudaMemset(h->st.trig, 0, S * sizeof(int)));
     CKH(cudaMalloc((void**)&h->d_count, sizeof(unsigned long long)));
     CKH(cudaMemset(h->d_count, 0, sizeof(unsigned long long)));
-    CKH(cudaFuncSetAttribute(mfcc_batch_kernel<int16_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->k1_batch_smem));
-    CKH(cudaFuncSetAttribute(mfcc_batch_kernel<int16_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->k1_batch_smem));
-    CKH(cudaFuncSetAttribute(mfcc_batch_kernel<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->k1_batch_smem));
-    CKH(cudaFuncSetAttribute(mfcc_batch_kernel<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->k1_batch_smem));
-    CKH(cudaFuncSetAttribute(mfcc_fast_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->k1_fast_smem));
-    CKH(cudaFuncSetAttribute(mfcc_fast_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->k1_fast_smem));
-    CKH(cudaFuncSetAttribute(mfcc_stream_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->k1_stream_smem));
-    CKH(cudaFuncSetAttribute(mfcc_stream_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->k1_stream_smem));
+    CKH(ensure_dyn_smem(mfcc_batch_kernel<int16_t, true>, (size_t)(h->k1_batch_smem)));
+    CKH(ensure_dyn_smem(mfcc_batch_kernel<int16_t, false>, (size_t)(h->k1_batch_smem)));
+    CKH(ensure_dyn_smem(mfcc_batch_kernel<float, true>, (size_t)(h->k1_batch_smem)));
+    CKH(ensure_dyn_smem(mfcc_batch_kernel<float, false>, (size_t)(h->k1_batch_smem)));
+    CKH(ensure_dyn_smem(mfcc_fast_batch_kernel, (size_t)(h->k1_fast_smem)));
+    CKH(ensure_dyn_smem(mfcc_fast_stream_kernel, (size_t)(h->k1_fast_smem)));
+    CKH(ensure_dyn_smem(mfcc_stream_kernel<true>, (size_t)(h->k1_stream_smem)));
+    CKH(ensure_dyn_smem(mfcc_stream_kernel<false>, (size_t)(h->k1_stream_smem)));
 #undef CKH
     *out = h;
     return PB_OK;
@@ -520,8 +541,8 @@ PB_API int pb_load_weights(pb_handle* h, const float* kernel, const float* recur
             for (int u = 0; u < H; ++u) { tb[u] = bias[u]; tb[24 + u] = bias[H + u]; tb[48 + u] = bias[2 * H + u]; tw[u] = dense_w[u]; }
             cudaFree(h->d_tc5); h->d_tc5 = nullptr;
             CK(upload(&h->d_tc5, t));
-            CK(cudaFuncSetAttribute(gru_tc5_kernel<20, 13, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Tc5Smem) + 128));
-            CK(cudaFuncSetAttribute(gru_tc5_kernel<20, 13, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Tc5Smem) + 128));
+            CK(ensure_dyn_smem(gru_tc5_kernel<20, 13, true>, (size_t)(sizeof(Tc5Smem) + 128)));
+            CK(ensure_dyn_smem(gru_tc5_kernel<20, 13, false>, (size_t)(sizeof(Tc5Smem) + 128)));
         }
         memcpy(h->w_small.W, kernel, sizeof(h->w_small.W));
         memcpy(h->w_small.U, recurrent, sizeof(h->w_small.U));
@@ -562,13 +583,13 @@ PB_API int pb_load_weights(pb_handle* h, const float* kernel, const float* recur
             for (int u = 0; u < H; ++u) tw[u] = dense_w[u];
             cudaFree(h->d_tcb); h->d_tcb = nullptr;
             CK(upload(&h->d_tcb, t));
-            CK(cudaFuncSetAttribute(gru_tcb_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TcbSmem) + 128));
-            CK(cudaFuncSetAttribute(gru_tcb_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TcbSmem) + 128));
+            CK(ensure_dyn_smem(gru_tcb_kernel<true>, (size_t)(sizeof(TcbSmem) + 128)));
+            CK(ensure_dyn_smem(gru_tcb_kernel<false>, (size_t)(sizeof(TcbSmem) + 128)));
         }
         size_t smem = (size_t)(F + 3 * H) * K2_TILE_STREAMS * sizeof(float);
         if (smem > 200 * 1024) return fail(PB_ERR_UNSUPPORTED, "feature_size + 3*hidden = %d is too large for the tiled GRU kernel", F + 3 * H);
-        CK(cudaFuncSetAttribute(gru_tiled_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CK(cudaFuncSetAttribute(gru_tiled_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CK(ensure_dyn_smem(gru_tiled_kernel<true>, (size_t)(smem)));
+        CK(ensure_dyn_smem(gru_tiled_kernel<false>, (size_t)(smem)));
     }
     h->have_weights = true;
     h->proj_dirty = true;
@@ -829,6 +850,23 @@ PB_API int pb_update_vectors(pb_handle* h, const int16_t* d_pcm, const int32_t* 
     return launch_stream_mfcc(h, d_pcm, d_ids, n, (cudaStream_t)stream);
 }
 
+// Does a tick of n streams run the scan that reads cached input projections (gru_mma_kernel<.., PROJ>)?
+static bool wants_projection(const pb_handle* h, int64_t n) {
+    return h->has_proj && h->small_path && n > K2_WARP_PATH_MAX && (h->gru_mode == 0 || h->gru_mode == 2 || h->gru_mode == 7);
+}
+
+// Recompute the projection of every ring row once (all streams), then the cache is maintained incrementally.
+static int rebuild_projections_if_dirty(pb_handle* h, cudaStream_t s) {
+    if (!h->proj_dirty) return PB_OK;
+    ProfScope ps(h, 3, s);
+    const long long rows = (long long)h->cfg.max_streams * h->ring_rows;
+    const int grid = (int)std::min<long long>((rows + PROJ_FRAMES_PER_CTA - 1) / PROJ_FRAMES_PER_CTA, (long long)h->sm_count * 16);
+    input_proj_all_kernel<13><<<grid, 64 * PROJ_FRAMES_PER_CTA, 0, s>>>(h->d_proj_w, h->d_proj_b, rows, h->st.ring, h->row_stride, h->d_proj_ring);
+    CK(cudaGetLastError());
+    h->proj_dirty = false;
+    return PB_OK;
+}
+
 PB_API int pb_update(pb_handle* h, const int16_t* d_pcm, const int32_t* d_ids, int64_t n, float* d_raw, double* d_conf,
               uint8_t* d_fired, unsigned long long* d_count, void* stream) {
     int rc = check_tick(h, d_pcm, n);
@@ -837,29 +875,25 @@ PB_API int pb_update(pb_handle* h, const int16_t* d_pcm, const int32_t* d_ids, i
     if (!d_conf) return fail(PB_ERR_INVALID, "null d_conf");
     CK(cudaSetDevice(h->cfg.device));
     cudaStream_t s = (cudaStream_t)stream;
+    // Default network, large batch: the tensor-core scan reads cached input projections.  A stale cache (weights changed,
+    // or ticks that skipped the projection) is rebuilt for every existing row BEFORE this tick's MFCC kernel runs -- the
+    // host-buffer path calls this up front on its first pipe, see pb_update_host -- and the rows the tick adds are projected
+    // right after it, so the rebuild never reads or writes a row that another sub-batch of the same tick is producing.
+    const bool want_proj = wants_projection(h, n);
+    if (want_proj) { rc = rebuild_projections_if_dirty(h, s); if (rc != PB_OK) return rc; }
     rc = launch_stream_mfcc(h, d_pcm, d_ids, n, s);
     if (rc != PB_OK) return rc;
-    bool use_proj = false;
-    if (h->has_proj && h->small_path) {
-        if (n > K2_WARP_PATH_MAX && (h->gru_mode == 0 || h->gru_mode == 2 || h->gru_mode == 7)) {
-            ProfScope ps(h, 3, s);
-            if (h->proj_dirty) {                               // bring every ring row up to date once, then stay incremental
-                const long long rows = (long long)h->cfg.max_streams * h->ring_rows;
-                const int grid = (int)std::min<long long>((rows + PROJ_FRAMES_PER_CTA - 1) / PROJ_FRAMES_PER_CTA, (long long)h->sm_count * 16);
-                input_proj_all_kernel<13><<<grid, 64 * PROJ_FRAMES_PER_CTA, 0, s>>>(h->d_proj_w, h->d_proj_b, rows, h->st.ring, h->row_stride, h->d_proj_ring);
-                h->proj_dirty = false;
-            } else {
-                const long long items = (long long)n * h->max_new;
-                const int grid = (int)((items + PROJ_THREADS - 1) / PROJ_THREADS);     // 32 frames per warp
-                input_proj_kernel<13><<<grid, PROJ_THREADS, 0, s>>>(h->d_bfrag, h->d_proj_b, h->st.n_samples, d_ids, (int)n,
-                    h->cfg.chunk_samples, h->used, h->cfg.hop_samples, h->max_new, h->st.ring, h->ring_rows, h->row_stride, h->d_proj_ring);
-            }
-            CK(cudaGetLastError());
-            use_proj = true;
-        } else {
-            h->proj_dirty = true;                              // this tick's frames get no projection
-        }
+    if (want_proj || (h->host_tick_proj && !h->proj_dirty)) {    // the second case: a short sub-batch of a large host tick
+        ProfScope ps(h, 3, s);
+        const long long items = (long long)n * h->max_new;
+        const int grid = (int)((items + PROJ_THREADS - 1) / PROJ_THREADS);     // 32 frames per warp
+        input_proj_kernel<13><<<grid, PROJ_THREADS, 0, s>>>(h->d_bfrag, h->d_proj_b, h->st.n_samples, d_ids, (int)n,
+            h->cfg.chunk_samples, h->used, h->cfg.hop_samples, h->max_new, h->st.ring, h->ring_rows, h->row_stride, h->d_proj_ring);
+        CK(cudaGetLastError());
+    } else if (h->has_proj && h->small_path) {
+        h->proj_dirty = true;                                  // this tick's frames get no projection
     }
+    const bool use_proj = want_proj;
     K2In in{};
     in.ring = h->st.ring; in.n_samples = h->st.n_samples; in.ids = d_ids;
     in.ring_rows = h->ring_rows; in.row_stride = h->row_stride; in.window = h->cfg.window_samples; in.hop = h->cfg.hop_samples;
@@ -989,14 +1023,24 @@ PB_API int pb_update_host(pb_handle* h, const int16_t* h_pcm, const int32_t* h_i
     // the counter is zeroed on pipe 0; the other pipes wait for that, pipe 0 waits for them at the end,
     // so the whole tick costs one host synchronisation
     CK(cudaMemsetAsync(h->d_count, 0, sizeof(unsigned long long), h->pipe[0]));
-    const int used_pipes = (int)std::min<int64_t>(HOST_PIPE, (n + sb - 1) / sb);
+    // equal sub-batches (a short last one would drop below the size at which the tick uses the projection cache and
+    // invalidate it every tick); step <= sb, a multiple of 32 except when one sub-batch takes everything
+    const int64_t n_sub = (n + sb - 1) / sb;
+    const int64_t step = n_sub == 1 ? n : std::min(sb, ((n + n_sub - 1) / n_sub + 31) & ~(int64_t)31);
+    struct TickFlag { bool& f; ~TickFlag() { f = false; } } tick_flag{h->host_tick_proj};
+    if (wants_projection(h, std::min(step, n))) {
+        rc = rebuild_projections_if_dirty(h, h->pipe[0]);
+        if (rc != PB_OK) return rc;
+        h->host_tick_proj = true;
+    }
+    const int used_pipes = (int)std::min<int64_t>(HOST_PIPE, (n + step - 1) / step);
     if (used_pipes > 1) {
         CK(cudaEventRecord(h->pipe_ev[0], h->pipe[0]));
         for (int i = 1; i < used_pipes; ++i) CK(cudaStreamWaitEvent(h->pipe[i], h->pipe_ev[0], 0));
     }
     int p = 0;
-    for (int64_t off = 0; off < n; off += sb, p = (p + 1) % HOST_PIPE) {
-        const int64_t m = std::min(sb, n - off);
+    for (int64_t off = 0; off < n; off += step, p = (p + 1) % HOST_PIPE) {
+        const int64_t m = std::min(step, n - off);
         cudaStream_t s = h->pipe[p];
         CK(cudaMemcpyAsync(h->d_stage_pcm[p], h_pcm + off * chunk, m * chunk * sizeof(int16_t), cudaMemcpyHostToDevice, s));
         if (h_ids) CK(cudaMemcpyAsync(h->d_stage_ids[p], h_ids + off, m * sizeof(int), cudaMemcpyHostToDevice, s));

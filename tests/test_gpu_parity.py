@@ -435,6 +435,64 @@ def test_stream_host_path_equals_device_path():
         assert a[4] == b[4] and a[4] > 0
 
 
+def test_host_path_sub_batches_keep_projection_cache():
+    """pb_update_host on 16 400 streams = two pipelined sub-batches (8 224 + 8 176: the second is below the size at which a
+    tick uses the cached input projections) with a weight reload in between: must equal the single-launch device path."""
+    m = _mod()
+    S, K, chunk = 16400, 32, 1024
+    pcm = noise(64, K * chunk, seed=41)
+    pcm = np.tile(pcm, (S // 64 + 1, 1))[:S].copy()
+    pcm[::5] = np.roll(pcm[::5], 321, axis=1)
+    model = m.GruModel.random(13, 20, seed=12, scale=0.1)
+    model.dense_b = 3.0
+    dev = m.StreamBatch(model, S, chunk_samples=chunk)
+    host = m.StreamBatch(model, S, chunk_samples=chunk)
+    conf = np.zeros(S); raw = np.zeros(S, np.float32); fired = np.zeros(S, np.uint8)
+    total = 0
+    for k in range(K):
+        c = np.ascontiguousarray(pcm[:, k * chunk:(k + 1) * chunk])
+        if k == 27:
+            for sb in (dev, host):
+                sb.core.load_weights(model.kernel, model.recurrent, model.bias, model.dense_w, model.dense_b)
+        o = dev.update(cuda(c))
+        total += host.update_host(c, conf, raw, fired)
+        assert np.max(np.abs(o['raw'].cpu().numpy() - raw)) < 1e-6, k
+        assert np.array_equal(o['fired'].cpu().numpy().astype(bool), fired.astype(bool)), k
+    assert total == int(dev.count.item()) > 0
+    dev.core.close(); host.core.close()
+
+
+def test_handles_with_different_geometries_coexist():
+    """Kernel attributes (dynamic shared memory limits) are per kernel, not per handle: creating a small-geometry handle
+    after a large one must not break the large one's launches."""
+    m = _mod()
+    chunk = 1024
+    pcm = noise(6, 40 * chunk, seed=43)
+    pr_big = m.ListenerParams(n_filt=40, n_mfcc=40)
+    big_model = m.GruModel.random(40, 128, seed=2, scale=0.1 / np.sqrt(128 / 20.0))
+    tiled_model = m.GruModel.random(26, 64, seed=3, scale=0.1 / np.sqrt(64 / 20.0))     # tiled kernel, 56 KB of dynamic smem
+    big = m.StreamBatch(big_model, 6, params=pr_big, chunk_samples=chunk)
+    tiled = m.StreamBatch(tiled_model, 6, params=m.ListenerParams(use_delta=True), chunk_samples=chunk)
+    small = m.StreamBatch(m.GruModel.random(13, 20, seed=4, scale=0.1), 6, chunk_samples=chunk)      # created last
+    tiny = m.StreamBatch(m.GruModel.random(26, 8, seed=5, scale=0.1), 6, params=m.ListenerParams(use_delta=True),
+                         chunk_samples=chunk)                                                        # tiled kernel again, 13 KB
+    outs = {}
+    for k in range(40):
+        c = cuda(pcm[:, k * chunk:(k + 1) * chunk])
+        for name, sb in (('big', big), ('tiled', tiled), ('small', small), ('tiny', tiny)):
+            outs.setdefault(name, []).append(sb.update(c)['raw'].cpu().numpy().copy())
+    w = og.GruWeights(big_model.kernel, big_model.recurrent, big_model.bias, big_model.dense_w, big_model.dense_b)
+    oraw, _, _ = run_streams(w, pcm, chunk, pr=OracleParams(**pr_big.to_dict()))
+    assert np.max(np.abs(np.array(outs['big']).T - oraw)) < 1e-4
+    w = og.GruWeights(tiled_model.kernel, tiled_model.recurrent, tiled_model.bias, tiled_model.dense_w, tiled_model.dense_b)
+    oraw, _, _ = run_streams(w, pcm, chunk, pr=OracleParams(**m.ListenerParams(use_delta=True).to_dict()))
+    assert np.max(np.abs(np.array(outs['tiled']).T - oraw)) < 1e-4
+    got = big.core.mfcc(cuda(pcm[:, :8000])).cpu().numpy()                 # batch MFCC kernels of the large geometry as well
+    assert got.shape[-1] == 40 and np.isfinite(got).all()
+    for sb in (big, tiled, small, tiny):
+        sb.core.close()
+
+
 def test_stream_ids_subset_and_clear():
     m = _mod()
     S, chunk = 16, 1024
