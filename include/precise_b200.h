@@ -192,8 +192,16 @@ int pb_set_cdf(pb_handle* h, const double* h_cd, int64_t len);
  * instead of the warp-autonomous fast kernels, so both implementations are covered by parity tests. */
 int pb_debug_force_generic(pb_handle* h, int on);
 /* Test hook for the default network (H=20, F=13): 0 = automatic choice (warp-per-stream kernel for small
- * batches, tensor-core scan otherwise), 1 = CUDA-core thread-per-stream kernel, 2 = tensor-core kernel. */
+ * batches, tensor-core scan otherwise), 1 = CUDA-core thread-per-stream kernel, 2 = tensor-core kernel,
+ * 3 = tcgen05 scan, 7 = tensor-core kernel with 32-stream warp tiles. */
 int pb_debug_gru_mode(pb_handle* h, int mode);
+/* Experimental (opt-in, default 0): 1 routes the stateful tick's MFCC through the tensor-core DFT kernel
+ * (csrc/mfcc_tc.cuh: radix-16 butterflies on the CUDA cores + fp16x3 GEMM blocks on tcgen05).  Its host-side tables
+ * are CPU-verified; the kernel itself has not been validated on hardware yet -- do not enable in production. */
+int pb_debug_k1_mode(pb_handle* h, int mode);
+/* CPU model of that kernel's DFT for one frame of 512 int16 samples -> |X[k]|^2, k = 0..256 (same butterfly, operand tables
+ * and layout arithmetic; no device needed).  Test hook. */
+int pb_debug_tc_dft_power(const int16_t* x512, double* power257);
 /* Test/profiling hook: the first call arms, later calls read four device-side cycle counters of the wide-network
  * tensor-core kernel's MMA-issuer thread (operand wait, weight-tile wait, issue, total) for CTA 0. */
 int pb_debug_counters(pb_handle* h, long long out[4]);

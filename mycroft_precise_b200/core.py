@@ -63,6 +63,8 @@ SYMBOLS = {
     'pb_set_cdf': (C.c_int, [_VP, _VP, _I64]),
     'pb_debug_force_generic': (C.c_int, [_VP, C.c_int]),
     'pb_debug_gru_mode': (C.c_int, [_VP, C.c_int]),
+    'pb_debug_k1_mode': (C.c_int, [_VP, C.c_int]),
+    'pb_debug_tc_dft_power': (C.c_int, [_VP, _VP]),
     'pb_debug_counters': (C.c_int, [_VP, C.POINTER(C.c_longlong)]),
     'pb_last_error': (C.c_char_p, []),
     'pb_abi_version': (C.c_int, []),
@@ -310,6 +312,10 @@ class PreciseB200:
 
     def force_generic(self, on=True):
         check(self.lib.pb_debug_force_generic(self._h, int(on)))
+
+    def k1_mode(self, mode):
+        """1 = experimental tensor-core DFT tick (csrc/mfcc_tc.cuh, not yet validated on hardware), 0 = default kernels."""
+        check(self.lib.pb_debug_k1_mode(self._h, int(mode)))
 
     # ---- profiling / introspection
     def profile(self, on=True):

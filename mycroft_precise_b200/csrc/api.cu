@@ -22,6 +22,7 @@
 #include "mfcc_fast.cuh"
 #include "gru_tc5.cuh"
 #include "gru_tc5_big.cuh"
+#include "mfcc_tc.cuh"
 
 using namespace pb;
 
@@ -69,6 +70,10 @@ struct pb_handle {
     float *d_proj_w = nullptr, *d_proj_b = nullptr;
     size_t k1_batch_smem = 0, k1_stream_smem = 0, k1_fast_smem = 0;
     bool force_generic = false;      // tests: exercise the generic kernels on the aligned geometry
+    int k1_mode = 0;                 // 0 = default kernels, 1 = experimental tensor-core DFT tick (mfcc_tc.cuh; opt-in, see its header)
+    bool tcd_ok = false;             // geometry supported by mfcc_tc_stream_kernel
+    std::vector<float> h_wrise, h_wfall; std::vector<int> h_grid;      // host copies for the lazily built tcd tables
+    uint4* d_tcd_b = nullptr; float4* d_tcd_etab = nullptr; float* d_tcd_dct = nullptr;
     bool fast_ok = false;            // aligned geometry: warp-autonomous kernels (mfcc_fast.cuh)
     int npl = 0, maxc = 0, nol = 0;
     float4* d_ptab = nullptr;
@@ -246,6 +251,7 @@ PB_API void pb_destroy(pb_handle* h) {
     if (!h) return;
     cudaSetDevice(h->cfg.device);
     cudaFree(h->d_wrise); cudaFree(h->d_wfall); cudaFree(h->d_dct); cudaFree(h->d_grid);
+    cudaFree(h->d_tcd_b); cudaFree(h->d_tcd_etab); cudaFree(h->d_tcd_dct);
     cudaFree(h->d_tw_stage); cudaFree(h->d_tw_post); cudaFree(h->d_tw_any); cudaFree(h->d_cd); cudaFree(h->d_ptab); cudaFree(h->d_ctab); cudaFree(h->d_dct_t);
     cudaFree(h->st.n_samples); cudaFree(h->st.tail); cudaFree(h->st.ring); cudaFree(h->st.trig);
     cudaFree(h->d_wcat); cudaFree(h->d_bias); cudaFree(h->d_wd); cudaFree(h->d_count);
@@ -350,6 +356,9 @@ PB_API int pb_create(const pb_config* cfg, pb_handle** out) {
         for (int pp = seg_first[j + 1]; pp < seg_first[j + 2]; ++pp) ctab[(size_t)j * h->maxc + w++] = (unsigned char)(64 + pp);
     }
     h->fast_ok = c.n_fft == 512 && h->used == 512 && c.hop_samples % 8 == 0 && n_pieces <= 64 && h->npl <= 4;
+    h->h_wrise = wrise; h->h_wfall = wfall; h->h_grid = grid;
+    h->tcd_ok = h->fast_ok && c.vectorizer == PB_VEC_MFCCS && c.n_filt <= TCD_MAX_FILT && h->n_out <= TCD_MAX_OUT &&
+                c.chunk_samples % 8 == 0 && c.chunk_samples >= 512 && (c.chunk_samples + c.hop_samples - 1) / c.hop_samples <= TCD_MAX_NEW;
     h->k1_fast_smem = K1F_WARPS * sizeof(K1FWarp) + (size_t)h->npl * 128 * sizeof(float4) +
                       (size_t)c.n_filt * 16 * h->nol * sizeof(float) + (((size_t)c.n_filt * h->maxc + 15) & ~(size_t)15);
     // DCT-II, norm='ortho' (scipy.fftpack.dct as sonopy.mfcc_spec calls it), first n_out rows
@@ -631,6 +640,22 @@ PB_API int pb_debug_counters(pb_handle* h, long long out[4]) {
 
 PB_API int pb_debug_gru_mode(pb_handle* h, int mode) { if (!h) return fail(PB_ERR_INVALID, "null handle"); h->gru_mode = mode; return PB_OK; }
 
+PB_API int pb_debug_k1_mode(pb_handle* h, int mode) {
+    if (!h) return fail(PB_ERR_INVALID, "null handle");
+    if (mode != 0 && mode != 1) return fail(PB_ERR_INVALID, "k1 mode must be 0 (default kernels) or 1 (experimental tensor-core DFT)");
+    if (mode == 1 && !h->tcd_ok) return fail(PB_ERR_UNSUPPORTED, "the tensor-core MFCC tick needs n_fft 512, chunk >= 512 and a multiple of 8, n_filt <= %d, MFCC vectorizer", TCD_MAX_FILT);
+    h->k1_mode = mode;
+    return PB_OK;
+}
+
+// CPU model of the tensor-core DFT for one 512-sample frame (mfcc_tc.cuh: same butterfly, same operand tables and layout
+// arithmetic as the kernel).  No device needed; used by the CPU tests to pin the host-side half of that design.
+PB_API int pb_debug_tc_dft_power(const int16_t* x512, double* power257) {
+    if (!x512 || !power257) return fail(PB_ERR_INVALID, "null argument");
+    tcd_host_power(x512, power257);
+    return PB_OK;
+}
+
 PB_API int pb_debug_force_generic(pb_handle* h, int on) { if (!h) return fail(PB_ERR_INVALID, "null handle"); h->force_generic = on != 0; return PB_OK; }
 
 PB_API int pb_profile_enable(pb_handle* h, int on) { if (!h) return fail(PB_ERR_INVALID, "null handle"); h->profiling = on != 0; return PB_OK; }
@@ -819,6 +844,31 @@ static int check_tick(pb_handle* h, const void* pcm, int64_t n) {
     return PB_OK;
 }
 
+// tables of the experimental tensor-core MFCC tick, built on first use (never on the default path)
+static int ensure_tcd_tables(pb_handle* h) {
+    if (h->d_tcd_b) return PB_OK;
+    std::vector<__half> bh, bl;
+    tcd_build_b(bh, bl);
+    std::vector<__half> both(bh);
+    both.insert(both.end(), bl.begin(), bl.end());
+    const float inv = 1.0f / 32768.0f, pscale = inv * inv / (float)h->cfg.n_fft / (TCD_A_SCALE * TCD_A_SCALE);
+    std::vector<float4> etab;
+    tcd_build_etab(etab, h->h_wrise, h->h_wfall, h->h_grid, h->cfg.n_filt, pscale);
+    std::vector<float> dct((size_t)TCD_MAX_OUT * 24, 0.f);
+    for (int k = 0; k < h->n_out; ++k)
+        for (int j = 0; j < h->cfg.n_filt; ++j) {
+            double v = cos(M_PI * k * (2 * j + 1) / (2.0 * h->cfg.n_filt)) * sqrt(2.0 / h->cfg.n_filt);
+            if (k == 0) v *= sqrt(0.5);
+            dct[(size_t)k * 24 + j] = (float)v;
+        }
+    CK(cudaMalloc((void**)&h->d_tcd_b, both.size() * sizeof(__half)));
+    CK(cudaMemcpy(h->d_tcd_b, both.data(), both.size() * sizeof(__half), cudaMemcpyHostToDevice));
+    CK(upload(&h->d_tcd_etab, etab));
+    CK(upload(&h->d_tcd_dct, dct));
+    CK(ensure_dyn_smem(mfcc_tc_stream_kernel, sizeof(TcdSmem) + 128));
+    return PB_OK;
+}
+
 static int launch_stream_mfcc(pb_handle* h, const int16_t* d_pcm, const int32_t* d_ids, int64_t n, cudaStream_t s) {
     const bool pairs = (h->cfg.chunk_samples % 2 == 0) && (h->cfg.hop_samples % 2 == 0) && (h->used % 2 == 0) &&
                        ((uintptr_t)d_pcm % 4 == 0);
@@ -826,7 +876,16 @@ static int launch_stream_mfcc(pb_handle* h, const int16_t* d_pcm, const int32_t*
     const int grid = (int)std::min<int64_t>(tiles, (int64_t)h->sm_count * 4);
     const float inv = 1.0f / 32768.0f, scale = inv * inv / (float)h->cfg.n_fft;
     ProfScope ps(h, 0, s);
-    if (h->fast_ok && h->cfg.chunk_samples % 8 == 0 && (uintptr_t)d_pcm % 16 == 0 && !h->force_generic) {
+    if (h->k1_mode == 1 && h->tcd_ok && (uintptr_t)d_pcm % 16 == 0 && !h->force_generic) {
+        int rc = ensure_tcd_tables(h);
+        if (rc != PB_OK) return rc;
+        TcdTables t;
+        t.b = h->d_tcd_b; t.etab = h->d_tcd_etab; t.dct = h->d_tcd_dct; t.n_filt = h->cfg.n_filt; t.n_out = h->n_out;
+        t.tot_scale = scale / (TCD_A_SCALE * TCD_A_SCALE);
+        const int groups = (int)((n + TCD_GROUP - 1) / TCD_GROUP);
+        mfcc_tc_stream_kernel<<<std::min(groups, h->sm_count), TCD_THREADS, sizeof(TcdSmem) + 128, s>>>(d_pcm, d_ids, (int)n, h->cfg.chunk_samples,
+                                                                                                    h->cfg.hop_samples, t, h->st);
+    } else if (h->fast_ok && h->cfg.chunk_samples % 8 == 0 && (uintptr_t)d_pcm % 16 == 0 && !h->force_generic) {
         // streams per warp tile: 16 at scale; fewer when the batch cannot fill the machine's warps
         const int64_t warps_total = (int64_t)h->sm_count * 4 * K1F_WARPS;
         const int spw = (int)std::max<int64_t>(1, std::min<int64_t>(K1F_STREAMS_PER_WARP, (n + warps_total - 1) / warps_total));

@@ -8,6 +8,8 @@ Tolerances
     when CUDA's log() and libm's differ in the last ulp (rate reported, must be < 0.2 %).
   * trigger / count: exact.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -625,3 +627,24 @@ def test_runner_plugin_predict_shape():
     p = r.predict(x)
     assert p.shape == (9, 1) and p.dtype == np.float32
     assert abs(r.run(x[2]) - p[2, 0]) < 1e-7
+
+
+@pytest.mark.skipif(os.environ.get('PB_TEST_TC_K1') != '1',
+                    reason='experimental tensor-core MFCC tick (csrc/mfcc_tc.cuh): not yet validated on hardware; set PB_TEST_TC_K1=1')
+def test_experimental_tensor_core_mfcc_tick():
+    """pb_debug_k1_mode(1): windows produced by the tcgen05 DFT kernel vs the default kernels and the oracle."""
+    m = _mod()
+    chunk, S, K = 1024, 300, 40
+    pcm = noise(S, K * chunk, seed=51)
+    pcm[0] = 0; pcm[1] = 32767; pcm[2] = -32768
+    model = m.GruModel.random(13, 20, seed=9, scale=0.1)
+    ref = m.StreamBatch(model, S, chunk_samples=chunk)
+    tc = m.StreamBatch(model, S, chunk_samples=chunk)
+    tc.core.k1_mode(1)
+    for k in range(K):
+        c = cuda(pcm[:, k * chunk:(k + 1) * chunk])
+        a, b = ref.update(c), tc.update(c)
+        wa, wb = ref.core.read_window(S).cpu().numpy(), tc.core.read_window(S).cpu().numpy()
+        assert np.max(np.abs(wa - wb)) < 2e-4, k
+        assert np.max(np.abs(a['raw'].cpu().numpy() - b['raw'].cpu().numpy())) < 1e-4, k
+    ref.core.close(); tc.core.close()

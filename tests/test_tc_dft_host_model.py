@@ -1,0 +1,45 @@
+"""CPU: the host-side half of the experimental tensor-core MFCC kernel (csrc/mfcc_tc.cuh) -- the 16-point real-DFT butterfly,
+the fp16 hi/lo twiddle operands in the UMMA K-major layout (with the K permutation the producer threads write) and the
+accumulator-column -> bin map -- reproduces a float64 power spectrum.  The library exports a CPU model built from exactly
+those pieces (pb_debug_tc_dft_power); no device is needed."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from mycroft_precise_b200.core import get_lib
+
+
+def _power(x):
+    lib = get_lib()
+    x = np.ascontiguousarray(x, dtype=np.int16)
+    out = np.zeros(257, np.float64)
+    rc = lib.pb_debug_tc_dft_power(x.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
+    assert rc == 0
+    return out
+
+
+def _cases():
+    rs = np.random.RandomState(7)
+    yield 'noise', np.clip(rs.randn(512) * 3000, -32768, 32767)
+    yield 'quiet', np.round(rs.randn(512) * 2)
+    yield 'max dc', np.full(512, 32767)
+    yield 'min dc', np.full(512, -32768)
+    yield 'nyquist', np.where(np.arange(512) % 2 == 0, 32767, -32768)
+    yield 'impulse', np.eye(1, 512, 137).ravel() * 30000
+    yield 'tone', 32000 * np.sin(2 * np.pi * 1000 / 16000 * np.arange(512) + 0.3)
+    for k in (1, 7, 8, 9, 15, 16, 17, 100, 129, 255):                 # one bin from every GEMM block / column quarter
+        yield 'bin %d' % k, 20000 * np.cos(2 * np.pi * k * np.arange(512) / 512 + 0.1 * k)
+
+
+@pytest.mark.parametrize('name,x', list(_cases()), ids=[n for n, _ in _cases()])
+def test_host_model_matches_float64_fft(name, x):
+    x = np.asarray(x).astype(np.int16)
+    ref = np.abs(np.fft.rfft(x.astype(np.float64))) ** 2
+    got = _power(x)
+    peak = max(ref.max(), 1.0)
+    assert np.max(np.abs(got - ref)) / peak < 3e-6, name
+
+
+def test_silence_is_exactly_zero():
+    assert np.all(_power(np.zeros(512, np.int16)) == 0.0)
