@@ -202,6 +202,9 @@ int pb_debug_k1_mode(pb_handle* h, int mode);
 /* CPU model of that kernel's DFT for one frame of 512 int16 samples -> |X[k]|^2, k = 0..256 (same butterfly, operand tables
  * and layout arithmetic; no device needed).  Test hook. */
 int pb_debug_tc_dft_power(const int16_t* x512, double* power257);
+/* ... and of the whole kernel for one frame (accumulators + mel / log / DCT epilogue with the tables this configuration
+ * would upload) -> out[min(n_filt, n_mfcc)].  No device needed.  Test hook. */
+int pb_debug_tc_mfcc_frame(const pb_config* cfg, const int16_t* x512, float* out);
 /* Test/profiling hook: the first call arms, later calls read four device-side cycle counters of the wide-network
  * tensor-core kernel's MMA-issuer thread (operand wait, weight-tile wait, issue, total) for CTA 0. */
 int pb_debug_counters(pb_handle* h, long long out[4]);

@@ -65,6 +65,7 @@ SYMBOLS = {
     'pb_debug_gru_mode': (C.c_int, [_VP, C.c_int]),
     'pb_debug_k1_mode': (C.c_int, [_VP, C.c_int]),
     'pb_debug_tc_dft_power': (C.c_int, [_VP, _VP]),
+    'pb_debug_tc_mfcc_frame': (C.c_int, [_VP, _VP, _VP]),
     'pb_debug_counters': (C.c_int, [_VP, C.POINTER(C.c_longlong)]),
     'pb_last_error': (C.c_char_p, []),
     'pb_abi_version': (C.c_int, []),

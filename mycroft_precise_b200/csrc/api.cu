@@ -74,6 +74,7 @@ struct pb_handle {
     bool tcd_ok = false;             // geometry supported by mfcc_tc_stream_kernel
     std::vector<float> h_wrise, h_wfall; std::vector<int> h_grid;      // host copies for the lazily built tcd tables
     uint4* d_tcd_b = nullptr; float4* d_tcd_etab = nullptr; float* d_tcd_dct = nullptr;
+    float tcd_tot_scale = 0.f;
     bool fast_ok = false;            // aligned geometry: warp-autonomous kernels (mfcc_fast.cuh)
     int npl = 0, maxc = 0, nol = 0;
     float4* d_ptab = nullptr;
@@ -656,6 +657,33 @@ PB_API int pb_debug_tc_dft_power(const int16_t* x512, double* power257) {
     return PB_OK;
 }
 
+static void tcd_host_tables(const pb_handle* h, std::vector<float4>& etab, std::vector<float>& dct, float* tot_scale);
+
+// CPU model of the whole experimental kernel for one frame: accumulator row (as above) + the epilogue (mel, log, DCT, c0) with
+// the tables a handle of this configuration would upload.  Needs no device: only the mel-table part of pb_create runs.
+PB_API int pb_debug_tc_mfcc_frame(const pb_config* cfg, const int16_t* x512, float* out) {
+    if (!cfg || !x512 || !out) return fail(PB_ERR_INVALID, "null argument");
+    if (cfg->n_fft != 512 || cfg->n_filt < 1 || cfg->n_filt > TCD_MAX_FILT || cfg->vectorizer != PB_VEC_MFCCS)
+        return fail(PB_ERR_UNSUPPORTED, "the tensor-core MFCC model covers n_fft 512, n_filt <= %d, MFCC vectorizer", TCD_MAX_FILT);
+    pb_handle* h = new (std::nothrow) pb_handle();
+    if (!h) return fail(PB_ERR_CUDA, "out of host memory");
+    h->cfg = *cfg;
+    h->n_bins = cfg->n_fft / 2 + 1;
+    h->n_out = std::min(cfg->n_filt, cfg->n_mfcc);
+    int rc = h->n_out > TCD_MAX_OUT ? fail(PB_ERR_UNSUPPORTED, "n_mfcc > %d", TCD_MAX_OUT) : build_mel(h, h->h_wrise, h->h_wfall, h->h_grid);
+    if (rc == PB_OK) {
+        std::vector<float4> etab;
+        std::vector<float> dct;
+        float tot_scale = 0.f;
+        tcd_host_tables(h, etab, dct, &tot_scale);
+        float d[512], acc[TCD_MAX_FILT + 2];
+        tcd_host_accumulators(x512, d);
+        tcd_host_epilogue(d, etab.data(), dct.data(), cfg->n_filt, h->n_out, tot_scale, acc, out);
+    }
+    delete h;
+    return rc;
+}
+
 PB_API int pb_debug_force_generic(pb_handle* h, int on) { if (!h) return fail(PB_ERR_INVALID, "null handle"); h->force_generic = on != 0; return PB_OK; }
 
 PB_API int pb_profile_enable(pb_handle* h, int on) { if (!h) return fail(PB_ERR_INVALID, "null handle"); h->profiling = on != 0; return PB_OK; }
@@ -844,23 +872,30 @@ static int check_tick(pb_handle* h, const void* pcm, int64_t n) {
     return PB_OK;
 }
 
-// tables of the experimental tensor-core MFCC tick, built on first use (never on the default path)
-static int ensure_tcd_tables(pb_handle* h) {
-    if (h->d_tcd_b) return PB_OK;
-    std::vector<__half> bh, bl;
-    tcd_build_b(bh, bl);
-    std::vector<__half> both(bh);
-    both.insert(both.end(), bl.begin(), bl.end());
-    const float inv = 1.0f / 32768.0f, pscale = inv * inv / (float)h->cfg.n_fft / (TCD_A_SCALE * TCD_A_SCALE);
-    std::vector<float4> etab;
+// tables of the experimental tensor-core MFCC tick (host part: shared by the device upload and the CPU model)
+static void tcd_host_tables(const pb_handle* h, std::vector<float4>& etab, std::vector<float>& dct, float* tot_scale) {
+    const float inv = 1.0f / 32768.0f, scale = inv * inv / (float)h->cfg.n_fft, pscale = scale / (TCD_A_SCALE * TCD_A_SCALE);
     tcd_build_etab(etab, h->h_wrise, h->h_wfall, h->h_grid, h->cfg.n_filt, pscale);
-    std::vector<float> dct((size_t)TCD_MAX_OUT * 24, 0.f);
+    dct.assign((size_t)TCD_MAX_OUT * 24, 0.f);
     for (int k = 0; k < h->n_out; ++k)
         for (int j = 0; j < h->cfg.n_filt; ++j) {
             double v = cos(M_PI * k * (2 * j + 1) / (2.0 * h->cfg.n_filt)) * sqrt(2.0 / h->cfg.n_filt);
             if (k == 0) v *= sqrt(0.5);
             dct[(size_t)k * 24 + j] = (float)v;
         }
+    *tot_scale = pscale;
+}
+
+// ... built on first use (never on the default path)
+static int ensure_tcd_tables(pb_handle* h) {
+    if (h->d_tcd_b) return PB_OK;
+    std::vector<__half> bh, bl;
+    tcd_build_b(bh, bl);
+    std::vector<__half> both(bh);
+    both.insert(both.end(), bl.begin(), bl.end());
+    std::vector<float4> etab;
+    std::vector<float> dct;
+    tcd_host_tables(h, etab, dct, &h->tcd_tot_scale);
     CK(cudaMalloc((void**)&h->d_tcd_b, both.size() * sizeof(__half)));
     CK(cudaMemcpy(h->d_tcd_b, both.data(), both.size() * sizeof(__half), cudaMemcpyHostToDevice));
     CK(upload(&h->d_tcd_etab, etab));
@@ -881,7 +916,7 @@ static int launch_stream_mfcc(pb_handle* h, const int16_t* d_pcm, const int32_t*
         if (rc != PB_OK) return rc;
         TcdTables t;
         t.b = h->d_tcd_b; t.etab = h->d_tcd_etab; t.dct = h->d_tcd_dct; t.n_filt = h->cfg.n_filt; t.n_out = h->n_out;
-        t.tot_scale = scale / (TCD_A_SCALE * TCD_A_SCALE);
+        t.tot_scale = h->tcd_tot_scale;
         const int groups = (int)((n + TCD_GROUP - 1) / TCD_GROUP);
         mfcc_tc_stream_kernel<<<std::min(groups, h->sm_count), TCD_THREADS, sizeof(TcdSmem) + 128, s>>>(d_pcm, d_ids, (int)n, h->cfg.chunk_samples,
                                                                                                     h->cfg.hop_samples, t, h->st);

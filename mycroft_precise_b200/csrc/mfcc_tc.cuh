@@ -1,8 +1,9 @@
 // mfcc_tc.cuh -- EXPERIMENTAL K1 variant: the 512-point real DFT on the 5th-generation tensor cores (tcgen05 + TMEM).
 //
 // Status: written at the end of round 1 after the GPU budget was spent.  The host-side parts (twiddle tables in the UMMA
-// operand layout, accumulator-column -> bin map, the 16-point real-DFT butterfly) are verified on the CPU
-// (pb_debug_tc_dft_power, tests/test_abi.py); the kernel itself compiles for sm_100a but has NOT run on hardware yet.  It is
+// operand layout, accumulator-column -> bin map, the 16-point real-DFT butterfly, the mel / DCT tables and the epilogue's
+// arithmetic) are verified on the CPU (pb_debug_tc_dft_power, pb_debug_tc_mfcc_frame, tests/test_tc_dft_host_model.py); the
+// kernel itself compiles for sm_100a but has NOT run on hardware yet.  It is
 // therefore opt-in only (pb_debug_k1_mode(h, 1)); the default MFCC kernels are untouched.  Design and numbers: DESIGN.md
 // section 6 ("Round-2 plan for K1"), numerical study: scripts/proto_tc_dft.py.
 //
@@ -176,8 +177,9 @@ static inline void tcd_build_etab(std::vector<float4>& etab, const std::vector<f
 }
 
 // CPU model of the tensor-core path for ONE frame of 512 int16 samples: the same butterfly, the same tables read through the
-// same layout arithmetic, fp16 products accumulated in fp32.  Returns |X[k]|^2 of the raw samples, k = 0..256.
-static inline void tcd_host_power(const int16_t* x, double* power) {
+// same layout arithmetic, fp16 products accumulated in fp32.  d[512] = the frame's accumulator row (TMEM lane) as the
+// epilogue sees it.
+static inline void tcd_host_accumulators(const int16_t* x, float* d) {
     static std::vector<__half> b_hi, b_lo;
     if (b_hi.empty()) tcd_build_b(b_hi, b_lo);
     std::vector<float> a((size_t)TCD_BLOCKS * 64);
@@ -190,7 +192,6 @@ static inline void tcd_host_power(const int16_t* x, double* power) {
             a[0 * 64 + 8 * g + j] = yr[0]; a[0 * 64 + 8 * g + 4 + j] = yr[8];
             for (int r = 1; r < 8; ++r) { a[r * 64 + 8 * g + j] = yr[r]; a[r * 64 + 8 * g + 4 + j] = yi[r]; }
         }
-    std::vector<float> d(512, 0.f);
     for (int b = 0; b < TCD_BLOCKS; ++b)
         for (int n = 0; n < 64; ++n) {
             float acc = 0.f;
@@ -205,6 +206,12 @@ static inline void tcd_host_power(const int16_t* x, double* power) {
                 }
             d[64 * b + n] = acc;
         }
+}
+
+// |X[k]|^2 of the raw samples, k = 0..256
+static inline void tcd_host_power(const int16_t* x, double* power) {
+    float d[512];
+    tcd_host_accumulators(x, d);
     const double inv = 1.0 / ((double)TCD_A_SCALE * (double)TCD_A_SCALE);
     for (int c = 0; c < 16; ++c)
         for (int m = 0; m < 16; ++m) {
@@ -213,6 +220,49 @@ static inline void tcd_host_power(const int16_t* x, double* power) {
             if (c == 0 && m == 0) { power[0] = re * re * inv; power[256] = im * im * inv; }
             else power[k] = (re * re + im * im) * inv;
         }
+}
+
+// The epilogue of mfcc_tc_stream_kernel for one accumulator row, statement for statement (fp32): table-driven mel sums with
+// the run-length flush, log, DCT, c0.  acc: (n_filt + 2) floats of scratch.
+static inline void tcd_host_epilogue(const float* d, const float4* etab, const float* dct, int n_filt, int n_out, float tot_scale,
+                                     float* acc, float* out) {
+    for (int j = 0; j < n_filt + 2; ++j) acc[j] = 0.f;
+    float tot = 0.f, a_r = 0.f, a_f = 0.f, p256 = 0.f;
+    int s_cur = 0;
+    for (int c = 0; c < 16; ++c)
+        for (int m = 0; m < 16; ++m) {
+            const float re = d[32 * c + m], im = d[32 * c + 16 + m];
+            float p = re * re;
+            if (c == 0 && m == 0) p256 = im * im;
+            else p = fmaf(im, im, p);
+            const float4 e = etab[16 * c + m];
+            int s;
+            memcpy(&s, &e.z, 4);
+            if (s != s_cur) { acc[s_cur + 1] += a_r; acc[s_cur] += a_f; s_cur = s; a_r = 0.f; a_f = 0.f; }
+            tot += p;
+            a_r = fmaf(e.x, p, a_r);
+            a_f = fmaf(e.y, p, a_f);
+        }
+    {
+        const float4 e = etab[256];
+        int s;
+        memcpy(&s, &e.z, 4);
+        if (s != s_cur) { acc[s_cur + 1] += a_r; acc[s_cur] += a_f; s_cur = s; a_r = 0.f; a_f = 0.f; }
+        tot += p256;
+        a_r = fmaf(e.x, p256, a_r);
+        a_f = fmaf(e.y, p256, a_f);
+        acc[s_cur + 1] += a_r; acc[s_cur] += a_f;
+    }
+    const float eps = 2.220446049250313e-16f;
+    for (int j = 0; j < n_filt; ++j) acc[j + 1] = logf(fmaxf(acc[j + 1], eps));
+    for (int o = 0; o < n_out; ++o) {
+        float v0 = 0.f, v1 = 0.f;
+        const float* dr = dct + (size_t)o * 24;
+        int j = 0;
+        for (; j + 1 < n_filt; j += 2) { v0 = fmaf(dr[j], acc[j + 1], v0); v1 = fmaf(dr[j + 1], acc[j + 2], v1); }
+        if (j < n_filt) v0 = fmaf(dr[j], acc[j + 1], v0);
+        out[o] = o == 0 ? logf(fmaxf(tot * tot_scale, eps)) : v0 + v1;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------------

@@ -43,3 +43,31 @@ def test_host_model_matches_float64_fft(name, x):
 
 def test_silence_is_exactly_zero():
     assert np.all(_power(np.zeros(512, np.int16)) == 0.0)
+
+
+def _mfcc_frame(pr, x512):
+    from mycroft_precise_b200.core import make_config
+    lib = get_lib()
+    cfg = make_config(pr)
+    x = np.ascontiguousarray(x512, dtype=np.int16)
+    out = np.zeros(min(pr.n_filt, pr.n_mfcc), np.float32)
+    rc = lib.pb_debug_tc_mfcc_frame(C.byref(cfg), x.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
+    assert rc == 0, lib.pb_last_error()
+    return out
+
+
+@pytest.mark.parametrize('kw', [dict(), dict(n_filt=16, n_mfcc=10), dict(sample_rate=8000), dict(n_filt=22, n_mfcc=16)])
+def test_full_frame_model_matches_oracle_mfcc(kw):
+    """Accumulators + the kernel's epilogue (table-driven mel sums, log, DCT, c0) against the float64 oracle MFCC row."""
+    from mycroft_precise_b200 import ListenerParams
+    from oracle import mfcc as om
+    pr = ListenerParams(**kw)
+    rs = np.random.RandomState(11)
+    sigs = [np.clip(rs.randn(1600) * 3000, -32768, 32767), np.zeros(1600), np.full(1600, 32767.0),
+            20000 * np.sin(2 * np.pi * 700 / pr.sample_rate * np.arange(1600)), np.round(rs.randn(1600) * 3)]
+    for sig in sigs:
+        x = sig.astype(np.int16)
+        want = om.mfcc_spec(x.astype(np.float32) / 32768.0, pr.sample_rate, 1600, 800, 512, pr.n_filt, pr.n_mfcc)[0]
+        got = _mfcc_frame(pr, x[:512])
+        assert got.shape == want.shape
+        assert np.max(np.abs(got - want)) < 2e-4, (kw, np.max(np.abs(got - want)))
