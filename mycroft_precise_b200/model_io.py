@@ -118,14 +118,17 @@ def model_from_keras_h5(f) -> GruModel:
 
 
 def load_net(path: str) -> GruModel:
-    """Keras ``.net`` (HDF5) model file.  Needs ``h5py`` -- present wherever the reference itself runs (Keras depends on
-    it); this build image has none, so here ``.net`` files must first be converted where h5py exists:
+    """Keras ``.net`` (HDF5) model file: through ``h5py`` where it is installed (wherever the reference itself runs -- Keras
+    depends on it), otherwise through the built-in reader for h5py's default file format (``h5_import.py``; written from the
+    HDF5 specification, not validated against Keras-written files in this build image).  A file the built-in reader refuses
+    (``libver='latest'``, compression) can be converted where h5py exists:
     ``python -m mycroft_precise_b200.model_io model.net model.npz``."""
     try:
         import h5py
-    except ImportError as e:
-        raise ImportError('reading Keras .net (HDF5) files needs h5py; convert on a machine that has it with '
-                          '`python -m mycroft_precise_b200.model_io model.net model.npz`, or use the frozen .pb') from e
+    except ImportError:
+        from .h5_import import H5File
+        with H5File(path) as f:
+            return model_from_keras_h5(f)
     with h5py.File(path, 'r') as f:
         return model_from_keras_h5(f)
 

@@ -114,14 +114,60 @@ def test_keras_h5_layout_extraction():
     assert model_from_keras_h5(f).hidden == 20
 
 
-def test_net_file_without_h5py_fails_loudly(tmp_path):
+def test_net_file_that_is_not_hdf5_fails_loudly(tmp_path):
     from mycroft_precise_b200.model_io import load_weights
+    p = tmp_path / 'm.net'
+    p.write_bytes(b'\x89HDF\r\n\x1a\n')                      # signature only: truncated
+    with pytest.raises(Exception):
+        load_weights(str(p))
+
+
+def _model_config(ract='hard_sigmoid'):
+    return json.dumps({'class_name': 'Sequential', 'config': [
+        {'class_name': 'GRU', 'config': {'name': 'net', 'units': 20, 'activation': 'linear', 'recurrent_activation': ract}},
+        {'class_name': 'Dense', 'config': {'name': 'dense_1', 'units': 1, 'activation': 'sigmoid'}}]})
+
+
+@pytest.mark.parametrize('split', [False, True])
+def test_builtin_hdf5_reader_on_keras_layout(tmp_path, split):
+    """mycroft_precise_b200/h5_import.py against a file written from the same format specification by tests/h5_writer.py
+    (groups, nested groups, float datasets, string / string-array attributes, continuation blocks)."""
+    import sys
+    sys.path.insert(0, os.path.dirname(__file__))
+    from h5_writer import keras_model_file
+    from mycroft_precise_b200.h5_import import H5File, H5FormatError
+    from mycroft_precise_b200.model_io import model_from_keras_h5
+    m = GruModel.random(13, 20, seed=6)
+    data = keras_model_file(m.kernel, m.recurrent, m.bias, m.dense_w, m.dense_b, _model_config('sigmoid'), split_headers=split)
+    p = tmp_path / 'model.net'
+    p.write_bytes(data)
+    with H5File(str(p)) as f:
+        assert sorted(f.keys()) == ['model_weights', 'optimizer_weights']
+        assert bytes(f.attrs['keras_version']) == b'2.1.5'
+        assert list(f['model_weights'].attrs['layer_names']) == [b'net', b'dense_1']
+        assert f['model_weights/net/net/kernel:0'].shape == (13, 60)
+        assert f['optimizer_weights'].keys() == []
+        got = model_from_keras_h5(f)
+    for k in ('kernel', 'recurrent', 'bias', 'dense_w'):
+        assert np.array_equal(getattr(got, k), getattr(m, k))
+    assert got.dense_b == m.dense_b and got.recurrent_activation == 'sigmoid' and got.activation == 'linear'
+    with pytest.raises(H5FormatError):
+        H5File(data=b'not an hdf5 file' * 64)
+    with pytest.raises(H5FormatError):
+        H5File(data=data[:8] + b'\x02' + data[9:])           # superblock version 2 (libver='latest'): refused, not misparsed
+
+
+def test_load_weights_net_without_h5py_uses_builtin_reader(tmp_path):
+    import sys
+    sys.path.insert(0, os.path.dirname(__file__))
+    from h5_writer import keras_model_file
     try:
         import h5py  # noqa: F401
-        pytest.skip('h5py present')
+        pytest.skip('h5py present: load_net prefers it')
     except ImportError:
         pass
+    m = GruModel.random(13, 20, seed=7)
     p = tmp_path / 'm.net'
-    p.write_bytes(b'\x89HDF\r\n\x1a\n')
-    with pytest.raises(ImportError, match='h5py'):
-        load_weights(str(p))
+    p.write_bytes(keras_model_file(m.kernel, m.recurrent, m.bias, m.dense_w, m.dense_b, _model_config()))
+    got = load_weights(str(p))
+    assert np.array_equal(got.kernel, m.kernel) and got.recurrent_activation == 'hard_sigmoid'
