@@ -195,9 +195,10 @@ int pb_debug_force_generic(pb_handle* h, int on);
  * batches, tensor-core scan otherwise), 1 = CUDA-core thread-per-stream kernel, 2 = tensor-core kernel,
  * 3 = tcgen05 scan, 7 = tensor-core kernel with 32-stream warp tiles. */
 int pb_debug_gru_mode(pb_handle* h, int mode);
-/* Experimental (opt-in, default 0): 1 routes the stateful tick's MFCC through the tensor-core DFT kernel
+/* Experimental (opt-in, default 0): 2 = the fast MFCC tick kernel with its per-pass set-up in 32-bit arithmetic;
+ * 1 routes the stateful tick's MFCC through the tensor-core DFT kernel
  * (csrc/mfcc_tc.cuh: radix-16 butterflies on the CUDA cores + fp16x3 GEMM blocks on tcgen05).  Its host-side tables
- * are CPU-verified; the kernel itself has not been validated on hardware yet -- do not enable in production. */
+ * are CPU-verified.  Neither variant has been validated on hardware yet -- do not enable in production. */
 int pb_debug_k1_mode(pb_handle* h, int mode);
 /* CPU model of that kernel's DFT for one frame of 512 int16 samples -> |X[k]|^2, k = 0..256 (same butterfly, operand tables
  * and layout arithmetic; no device needed).  Test hook. */

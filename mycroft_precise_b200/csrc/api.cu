@@ -70,7 +70,7 @@ struct pb_handle {
     float *d_proj_w = nullptr, *d_proj_b = nullptr;
     size_t k1_batch_smem = 0, k1_stream_smem = 0, k1_fast_smem = 0;
     bool force_generic = false;      // tests: exercise the generic kernels on the aligned geometry
-    int k1_mode = 0;                 // 0 = default kernels, 1 = experimental tensor-core DFT tick (mfcc_tc.cuh; opt-in, see its header)
+    int k1_mode = 0;                 // 0 = default kernels, 1 = experimental tensor-core DFT tick (mfcc_tc.cuh; opt-in, see its header), 2 = fast kernel, lean set-up (opt-in)
     bool tcd_ok = false;             // geometry supported by mfcc_tc_stream_kernel
     std::vector<float> h_wrise, h_wfall; std::vector<int> h_grid;      // host copies for the lazily built tcd tables
     uint4* d_tcd_b = nullptr; float4* d_tcd_etab = nullptr; float* d_tcd_dct = nullptr;
@@ -429,7 +429,8 @@ PB_API int pb_create(const pb_config* cfg, pb_handle** out) {
     CKH(ensure_dyn_smem(mfcc_batch_kernel<float, true>, (size_t)(h->k1_batch_smem)));
     CKH(ensure_dyn_smem(mfcc_batch_kernel<float, false>, (size_t)(h->k1_batch_smem)));
     CKH(ensure_dyn_smem(mfcc_fast_batch_kernel, (size_t)(h->k1_fast_smem)));
-    CKH(ensure_dyn_smem(mfcc_fast_stream_kernel, (size_t)(h->k1_fast_smem)));
+    CKH(ensure_dyn_smem(mfcc_fast_stream_kernel<false>, (size_t)(h->k1_fast_smem)));
+    CKH(ensure_dyn_smem(mfcc_fast_stream_kernel<true>, (size_t)(h->k1_fast_smem)));
     CKH(ensure_dyn_smem(mfcc_stream_kernel<true>, (size_t)(h->k1_stream_smem)));
     CKH(ensure_dyn_smem(mfcc_stream_kernel<false>, (size_t)(h->k1_stream_smem)));
 #undef CKH
@@ -643,7 +644,8 @@ PB_API int pb_debug_gru_mode(pb_handle* h, int mode) { if (!h) return fail(PB_ER
 
 PB_API int pb_debug_k1_mode(pb_handle* h, int mode) {
     if (!h) return fail(PB_ERR_INVALID, "null handle");
-    if (mode != 0 && mode != 1) return fail(PB_ERR_INVALID, "k1 mode must be 0 (default kernels) or 1 (experimental tensor-core DFT)");
+    if (mode < 0 || mode > 2) return fail(PB_ERR_INVALID, "k1 mode must be 0 (default kernels), 1 (experimental tensor-core DFT) or 2 (fast kernel with the lean per-pass set-up)");
+    if (mode == 2 && !h->fast_ok) return fail(PB_ERR_UNSUPPORTED, "k1 mode 2 needs the aligned geometry of the fast MFCC kernels");
     if (mode == 1 && !h->tcd_ok) return fail(PB_ERR_UNSUPPORTED, "the tensor-core MFCC tick needs n_fft 512, chunk >= 512 and a multiple of 8, n_filt <= %d, MFCC vectorizer", TCD_MAX_FILT);
     h->k1_mode = mode;
     return PB_OK;
@@ -926,8 +928,12 @@ static int launch_stream_mfcc(pb_handle* h, const int16_t* d_pcm, const int32_t*
         const int spw = (int)std::max<int64_t>(1, std::min<int64_t>(K1F_STREAMS_PER_WARP, (n + warps_total - 1) / warps_total));
         const int64_t tilesf = (n + spw - 1) / spw;
         const int gridf = (int)std::min<int64_t>((tilesf + K1F_WARPS - 1) / K1F_WARPS, (int64_t)h->sm_count * 4);
-        mfcc_fast_stream_kernel<<<gridf, K1F_THREADS, h->k1_fast_smem, s>>>(d_pcm, d_ids, (int)n, h->cfg.chunk_samples, h->cfg.hop_samples, spw, scale,
-                                                                            mel_tables(h), fast_tables(h), h->st);
+        if (h->k1_mode == 2)
+            mfcc_fast_stream_kernel<true><<<gridf, K1F_THREADS, h->k1_fast_smem, s>>>(d_pcm, d_ids, (int)n, h->cfg.chunk_samples, h->cfg.hop_samples, spw, scale,
+                                                                                      mel_tables(h), fast_tables(h), h->st);
+        else
+            mfcc_fast_stream_kernel<false><<<gridf, K1F_THREADS, h->k1_fast_smem, s>>>(d_pcm, d_ids, (int)n, h->cfg.chunk_samples, h->cfg.hop_samples, spw, scale,
+                                                                                       mel_tables(h), fast_tables(h), h->st);
     } else if (pairs)
         mfcc_stream_kernel<true><<<grid, K1_THREADS, h->k1_stream_smem, s>>>(d_pcm, d_ids, (int)n, h->cfg.chunk_samples, h->cfg.hop_samples, h->used, scale, mel_tables(h), h->st);
     else

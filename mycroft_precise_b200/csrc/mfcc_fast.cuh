@@ -230,6 +230,11 @@ mfcc_fast_batch_kernel(const int16_t* __restrict__ pcm, long long samples_per_st
 
 // ------------------------------------------------------------------------------------------------
 // Stateful tick (pb_update / pb_update_vectors on the aligned geometry): a warp owns 16 streams.
+// LEAN (opt-in, pb_debug_k1_mode 2; not yet validated on hardware): the per-pass set-up in 32-bit arithmetic.  The profile
+// shows 16 % of this kernel's executed instructions in that set-up (a 64-bit modulo for the ring slot and 64-bit products
+// for the source offsets, per frame); LEAN derives both from two per-stream ints computed once per tile
+// (slot of the stream's first new frame, offset of that frame's first sample relative to the chunk).
+template <bool LEAN>
 __global__ void __launch_bounds__(K1F_THREADS, 4)
 mfcc_fast_stream_kernel(const int16_t* __restrict__ pcm, const int* __restrict__ ids, int n, int chunk, int hop, int spw,
                         float scale, MelTables tab, FastTables ft, StreamState st) {
@@ -269,6 +274,8 @@ mfcc_fast_stream_kernel(const int16_t* __restrict__ pcm, const int* __restrict__
                 c0 = frames_ready(n0, used, hop);
                 cnt = (int)(frames_ready(n0 + chunk, used, hop) - c0);
                 ts0 = c0 * hop < n0 ? c0 * hop : n0;
+                // LEAN: st_ts0 carries (ring slot of frame c0) << 32 | (c0 * hop - n0) instead; -512 < c0 * hop - n0 <= hop - 512
+                if (LEAN) ts0 = ((long long)(int)(c0 % st.ring_rows) << 32) | (long long)(unsigned)(int)(c0 * hop - n0);
             }
             if (lane < spw) {
                 ws.st_id[lane] = sid; ws.st_n0[lane] = n0; ws.st_ts0[lane] = ts0; ws.st_cnt[lane] = cnt; ws.st_c0[lane] = c0;
@@ -287,9 +294,21 @@ mfcc_fast_stream_kernel(const int16_t* __restrict__ pcm, const int* __restrict__
             mbar_expect_tx(&ws.bar[stage], 1024u * nfr);
             for (int hf = 0; hf < nfr; ++hf) {
                 const int t = ws.fr_stream[f0 + hf];
-                const long long a0 = (ws.st_c0[t] + ws.fr_sub[f0 + hf]) * hop, n0 = ws.st_n0[t];
                 const int16_t* chunk_p = pcm + (long long)(base + t) * chunk;
                 char* dst = reinterpret_cast<char*>(ws.buf[stage][hf]);
+                if (LEAN) {
+                    const int sub_off = ws.fr_sub[f0 + hf] * hop;
+                    const int rel = (int)(unsigned)(ws.st_ts0[t] & 0xffffffffll) + sub_off;        // first sample of the frame, relative to the chunk
+                    if (rel >= 0) {
+                        bulk_g2s(dst, chunk_p + rel, 1024u, &ws.bar[stage]);
+                    } else {                                  // rel < 0 implies the tail starts at frame c0: offset in the tail = sub * hop
+                        const int len0 = min(used, -rel);
+                        bulk_g2s(dst, st.tail + (long long)ws.st_id[t] * st.tail_cap + sub_off, 2u * len0, &ws.bar[stage]);
+                        if (len0 < used) bulk_g2s(dst + 2 * len0, chunk_p, 2u * (used - len0), &ws.bar[stage]);
+                    }
+                    continue;
+                }
+                const long long a0 = (ws.st_c0[t] + ws.fr_sub[f0 + hf]) * hop, n0 = ws.st_n0[t];
                 if (a0 >= n0) {
                     bulk_g2s(dst, chunk_p + (a0 - n0), 1024u, &ws.bar[stage]);
                 } else {
@@ -307,8 +326,14 @@ mfcc_fast_stream_kernel(const int16_t* __restrict__ pcm, const int* __restrict__
             float* row = st.ring;
             if (active) {
                 const int t = ws.fr_stream[f0 + half];
-                const long long k = ws.st_c0[t] + ws.fr_sub[f0 + half];
-                row = st.ring + ((long long)ws.st_id[t] * st.ring_rows + (int)(k % st.ring_rows)) * st.row_stride;
+                if (LEAN) {
+                    int slot = (int)(ws.st_ts0[t] >> 32) + ws.fr_sub[f0 + half];                 // fr_sub < ring_rows
+                    if (slot >= st.ring_rows) slot -= st.ring_rows;
+                    row = st.ring + ((long long)ws.st_id[t] * st.ring_rows + slot) * st.row_stride;
+                } else {
+                    const long long k = ws.st_c0[t] + ws.fr_sub[f0 + half];
+                    row = st.ring + ((long long)ws.st_id[t] * st.ring_rows + (int)(k % st.ring_rows)) * st.row_stride;
+                }
             }
             const uint32_t parity = (stage == 0 ? uses0 : uses1) & 1;
             fast_pass(ws, stage, parity, lc, tb, ft, tab, scale, eoff, l16, half, active, row);

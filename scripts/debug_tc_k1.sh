@@ -3,16 +3,16 @@
 set -x
 mkdir -p gpurun_out
 # 1. parity of the windows against the default kernels (small batch: 300 streams, 40 ticks)
-timeout 120 env PB_TEST_TC_K1=1 python -m pytest tests/test_gpu_parity.py -m gpu -k tensor_core -x -q 2>&1 | tail -15 | tee gpurun_out/tc_k1_test.log
+timeout 120 env PB_TEST_TC_K1=1 python -m pytest tests/test_gpu_parity.py -m gpu -k experimental_mfcc -x -q 2>&1 | tail -15 | tee gpurun_out/tc_k1_test.log
 # 2. memory checker on a tiny run (only if step 1 did not hang)
-timeout 200 compute-sanitizer --tool memcheck --print-limit 5 env PB_TEST_TC_K1=1 python -m pytest tests/test_gpu_parity.py -m gpu -k tensor_core -x -q 2>&1 | tail -20 | tee gpurun_out/tc_k1_memcheck.log
+timeout 200 compute-sanitizer --tool memcheck --print-limit 5 env PB_TEST_TC_K1=1 python -m pytest tests/test_gpu_parity.py -m gpu -k experimental_mfcc -x -q 2>&1 | tail -20 | tee gpurun_out/tc_k1_memcheck.log
 # 3. timing against the default kernel at the bench size
 timeout 200 python - <<'PY' 2>&1 | tee gpurun_out/tc_k1_time.log
 import numpy as np, torch, mycroft_precise_b200 as m
 S = 131072
 model = m.GruModel.random(13, 20, seed=0, scale=0.1)
 pcm = torch.from_numpy((np.random.RandomState(0).randn(S, 1024) * 3000).astype(np.int16)).cuda()
-for mode in (0, 1):
+for mode in (0, 2, 1):
     sb = m.StreamBatch(model, S, chunk_samples=1024)
     sb.core.k1_mode(mode)
     for _ in range(30):

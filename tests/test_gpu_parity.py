@@ -630,9 +630,11 @@ def test_runner_plugin_predict_shape():
 
 
 @pytest.mark.skipif(os.environ.get('PB_TEST_TC_K1') != '1',
-                    reason='experimental tensor-core MFCC tick (csrc/mfcc_tc.cuh): not yet validated on hardware; set PB_TEST_TC_K1=1')
-def test_experimental_tensor_core_mfcc_tick():
-    """pb_debug_k1_mode(1): windows produced by the tcgen05 DFT kernel vs the default kernels and the oracle."""
+                    reason='opt-in MFCC kernels (tensor-core DFT, lean set-up): not yet validated on hardware; set PB_TEST_TC_K1=1')
+@pytest.mark.parametrize('k1_mode', [2, 1], ids=['lean_setup', 'tensor_core'])
+def test_experimental_mfcc_tick(k1_mode):
+    """pb_debug_k1_mode: 1 = windows produced by the tcgen05 DFT kernel, 2 = fast kernel with the 32-bit per-pass set-up,
+    against the default kernels (mode 2 must be bit-identical: same arithmetic, different address computation)."""
     m = _mod()
     chunk, S, K = 1024, 300, 40
     pcm = noise(S, K * chunk, seed=51)
@@ -640,11 +642,13 @@ def test_experimental_tensor_core_mfcc_tick():
     model = m.GruModel.random(13, 20, seed=9, scale=0.1)
     ref = m.StreamBatch(model, S, chunk_samples=chunk)
     tc = m.StreamBatch(model, S, chunk_samples=chunk)
-    tc.core.k1_mode(1)
+    tc.core.k1_mode(k1_mode)
     for k in range(K):
         c = cuda(pcm[:, k * chunk:(k + 1) * chunk])
         a, b = ref.update(c), tc.update(c)
         wa, wb = ref.core.read_window(S).cpu().numpy(), tc.core.read_window(S).cpu().numpy()
         assert np.max(np.abs(wa - wb)) < 2e-4, k
+        if k1_mode == 2:
+            assert np.array_equal(wa, wb), k
         assert np.max(np.abs(a['raw'].cpu().numpy() - b['raw'].cpu().numpy())) < 1e-4, k
     ref.core.close(); tc.core.close()
