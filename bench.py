@@ -266,6 +266,8 @@ def run_b200(args):
     core = sb.core
     if args.gru_mode:
         core.gru_mode(args.gru_mode)
+    if args.k1_mode:
+        core.k1_mode(args.k1_mode)
 
     # ---- synthetic PCM: NT distinct ticks resident in HBM (each tick 2 KB x S > L2 at the default S)
     NT = args.ticks_resident
@@ -495,7 +497,8 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-latency', dest='latency', action='store_false')
     ap.add_argument('--no-config3', dest='config3', action='store_false')
-    ap.add_argument('--gru-mode', type=int, default=0, help='debug: 0 auto, 1 CUDA-core, 2 mma.sync, 3 tcgen05')
+    ap.add_argument('--gru-mode', type=int, default=0, help='debug: 0 auto, 1 CUDA-core, 2 mma.sync, 3 tcgen05, 7 mma.sync with 32-stream tiles')
+    ap.add_argument('--k1-mode', type=int, default=0, help='debug (A/B runs only): 0 default MFCC kernels, 1 tensor-core DFT, 2 lean set-up')
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
