@@ -103,7 +103,7 @@ struct pb_handle {
     bool tcb_ok = false;
     int tcb_kx = 0;
     float *d_tc5 = nullptr;           // tcgen05 GRU: [b1_hi | b1_lo | b2_hi | b2_lo | bias(80) | wd(24)]
-    int gru_mode = 0;                // 0 = auto, 1 = force CUDA-core small kernel, 2 = force tensor-core kernel, 3 = tcgen05 scan, 7 = tensor-core kernel with 32-stream warp tiles
+    int gru_mode = 0;                // 0 = auto, 1 = force CUDA-core small kernel, 2 = force tensor-core kernel, 3 = tcgen05 scan, 7 = tensor-core kernel with 32-stream warp tiles, 8 = tcgen05 scan over cached projections (opt-in, unvalidated)
     float bd = 0.f;
     // host pipeline
     cudaStream_t pipe[HOST_PIPE] = {nullptr, nullptr, nullptr};
@@ -554,6 +554,7 @@ PB_API int pb_load_weights(pb_handle* h, const float* kernel, const float* recur
             CK(upload(&h->d_tc5, t));
             CK(ensure_dyn_smem(gru_tc5_kernel<20, 13, true>, (size_t)(sizeof(Tc5Smem) + 128)));
             CK(ensure_dyn_smem(gru_tc5_kernel<20, 13, false>, (size_t)(sizeof(Tc5Smem) + 128)));
+            CK(ensure_dyn_smem(gru_tc5_kernel<20, 13, true, true>, (size_t)(sizeof(Tc5Smem) + 128)));
         }
         memcpy(h->w_small.W, kernel, sizeof(h->w_small.W));
         memcpy(h->w_small.U, recurrent, sizeof(h->w_small.U));
@@ -788,14 +789,15 @@ static int launch_gru(pb_handle* h, const K2In& in, bool ring, int64_t n, const 
         const int grid = (int)((n + 3) / 4);
         if (ring) gru_warp_kernel<20, 13, true><<<grid, 128, 0, s>>>(h->w_small, in, n, dp, o);
         else gru_warp_kernel<20, 13, false><<<grid, 128, 0, s>>>(h->w_small, in, n, dp, o);
-    } else if (h->small_path && h->gru_mode == 3) {               // tcgen05 + TMEM scan
+    } else if (h->small_path && (h->gru_mode == 3 || h->gru_mode == 8)) {   // tcgen05 + TMEM scan (8: over cached projections, opt-in)
         GruTc5W w;
         const int sz1 = 10 * TC5_N1 * 4, sz2 = 10 * TC5_N2 * 4;
         w.b1_hi = h->d_tc5; w.b1_lo = w.b1_hi + sz1; w.b2_hi = w.b1_lo + sz1; w.b2_lo = w.b2_hi + sz2;
         w.bias = w.b2_lo + sz2; w.wd = w.bias + 80; w.bd = h->bd;
         const int grid = (int)((n + TC5_THREADS - 1) / TC5_THREADS);
         const size_t smem = sizeof(Tc5Smem) + 128;
-        if (ring) gru_tc5_kernel<20, 13, true><<<grid, TC5_BLOCK, smem, s>>>(w, in, n, dp, o);
+        if (ring && in.proj != nullptr && h->gru_mode == 8) gru_tc5_kernel<20, 13, true, true><<<grid, TC5_BLOCK, smem, s>>>(w, in, n, dp, o);
+        else if (ring) gru_tc5_kernel<20, 13, true><<<grid, TC5_BLOCK, smem, s>>>(w, in, n, dp, o);
         else gru_tc5_kernel<20, 13, false><<<grid, TC5_BLOCK, smem, s>>>(w, in, n, dp, o);
     } else if (h->small_path && h->gru_mode != 1) {               // tensor-core scan (mma.sync TF32 x3)
         GruMmaW w;
@@ -952,7 +954,7 @@ PB_API int pb_update_vectors(pb_handle* h, const int16_t* d_pcm, const int32_t* 
 
 // Does a tick of n streams run the scan that reads cached input projections (gru_mma_kernel<.., PROJ>)?
 static bool wants_projection(const pb_handle* h, int64_t n) {
-    return h->has_proj && h->small_path && n > K2_WARP_PATH_MAX && (h->gru_mode == 0 || h->gru_mode == 2 || h->gru_mode == 7);
+    return h->has_proj && h->small_path && n > K2_WARP_PATH_MAX && (h->gru_mode == 0 || h->gru_mode == 2 || h->gru_mode == 7 || h->gru_mode == 8);
 }
 
 // Recompute the projection of every ring row once (all streams), then the cache is maintained incrementally.

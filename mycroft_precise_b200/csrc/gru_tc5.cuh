@@ -95,9 +95,14 @@ __device__ __forceinline__ void tc5_put4(float (*hi)[4], float (*lo)[4], int row
     *reinterpret_cast<float4*>(lo[row]) = make_float4(l[0], l[1], l[2], l[3]);
 }
 
-template <int H, int F, bool RING>
+// PROJ (opt-in, pb_debug_gru_mode 8; written after round 1's GPU budget was spent -- not yet validated on hardware): the
+// input projection x_t.[Wz|Wr|Wh] + b comes from the cache that input_proj_kernel maintains (gru_kernels.cuh), so the
+// tensor core only runs the recurrent products: 18 instead of 30 MMAs per step, no x operand tiles.  The row threads fetch
+// their 60 cached values while the MMAs run and add them where the non-PROJ kernel adds the bias.
+template <int H, int F, bool RING, bool PROJ = false>
 __global__ void __launch_bounds__(TC5_BLOCK)
 gru_tc5_kernel(GruTc5W W, K2In in, long long n, DecodeParams dp, K2Out out) {
+    static_assert(!PROJ || (RING && H == 20), "the cached projection rows hold 3 x 20 columns");
     static_assert(H <= 24 && F <= 16, "operand tiles are sized for the default network");
     extern __shared__ __align__(128) unsigned char tc5_raw[];
     Tc5Smem& sm = *reinterpret_cast<Tc5Smem*>(tc5_raw);
@@ -129,20 +134,20 @@ gru_tc5_kernel(GruTc5W W, K2In in, long long n, DecodeParams dp, K2Out out) {
             for (int step = 0; step < in.T; ++step) {
                 mbar_wait(&sm.ready[0], step & 1);
                 tc5_fence_after();
-                // D1 = [x|h] . [Wz|Wr]
+                // D1 = [x|h] . [Wz|Wr]   (PROJ: h part only)
 #pragma unroll 1
-                for (int s = 0; s < 5; ++s) {
+                for (int s = PROJ ? 2 : 0; s < 5; ++s) {
                     const float* a_hi = s < 2 ? &sm.ax_hi[2 * s][0][0] : &sm.ah_hi[2 * (s - 2)][0][0];
                     const float* a_lo = s < 2 ? &sm.ax_lo[2 * s][0][0] : &sm.ah_lo[2 * (s - 2)][0][0];
                     const uint64_t dah = tc5_desc(a_hi, 2048, 128), dal = tc5_desc(a_lo, 2048, 128);
                     const uint64_t dbh = tc5_desc(sm.b1_hi[2 * s], TC5_N1 * 16, 128), dbl = tc5_desc(sm.b1_lo[2 * s], TC5_N1 * 16, 128);
-                    tc5_mma(tmem, dal, dbh, idesc1, s > 0);
+                    tc5_mma(tmem, dal, dbh, idesc1, s > (PROJ ? 2 : 0));
                     tc5_mma(tmem, dah, dbl, idesc1, 1);
                     tc5_mma(tmem, dah, dbh, idesc1, 1);
                 }
-                // D2 = x . Wh
+                // D2 = x . Wh   (PROJ: nothing, the candidate product starts fresh in the second phase)
 #pragma unroll 1
-                for (int s = 0; s < 2; ++s) {
+                for (int s = 0; s < (PROJ ? 0 : 2); ++s) {
                     const uint64_t dah = tc5_desc(sm.ax_hi[2 * s], 2048, 128), dal = tc5_desc(sm.ax_lo[2 * s], 2048, 128);
                     const uint64_t dbh = tc5_desc(sm.b2_hi[2 * s], TC5_N2 * 16, 128), dbl = tc5_desc(sm.b2_lo[2 * s], TC5_N2 * 16, 128);
                     tc5_mma(tmem + TC5_N1, dal, dbh, idesc2, s > 0);
@@ -156,7 +161,7 @@ gru_tc5_kernel(GruTc5W W, K2In in, long long n, DecodeParams dp, K2Out out) {
                 for (int s = 2; s < 5; ++s) {
                     const uint64_t dah = tc5_desc(sm.ah_hi[2 * (s - 2)], 2048, 128), dal = tc5_desc(sm.ah_lo[2 * (s - 2)], 2048, 128);
                     const uint64_t dbh = tc5_desc(sm.b2_hi[2 * s], TC5_N2 * 16, 128), dbl = tc5_desc(sm.b2_lo[2 * s], TC5_N2 * 16, 128);
-                    tc5_mma(tmem + TC5_N1, dal, dbh, idesc2, 1);
+                    tc5_mma(tmem + TC5_N1, dal, dbh, idesc2, PROJ ? (s > 2) : 1);
                     tc5_mma(tmem + TC5_N1, dah, dbl, idesc2, 1);
                     tc5_mma(tmem + TC5_N1, dah, dbh, idesc2, 1);
                 }
@@ -174,7 +179,9 @@ gru_tc5_kernel(GruTc5W W, K2In in, long long n, DecodeParams dp, K2Out out) {
     if (RING && valid) {
         sid = in.ids ? in.ids[i] : (int)i;
         const long long ns = in.n_samples[sid];
-        cur.init(in, sid, ns >= in.window ? (ns - in.window) / in.hop + 1 : 0);
+        const long long rel = ns >= in.window ? (ns - in.window) / in.hop + 1 : 0;
+        if (PROJ) cur.init_proj(in, sid, rel, PROJ_STRIDE);
+        else cur.init(in, sid, rel);
     }
     float h[24];
 #pragma unroll
@@ -182,24 +189,44 @@ gru_tc5_kernel(GruTc5W W, K2In in, long long n, DecodeParams dp, K2Out out) {
 
 #pragma unroll 1
     for (int step = 0; step < in.T; ++step) {
-        // ---- this row's x_t and h as A operands
-        float x[16];
+        // ---- this row's x_t and h as A operands (PROJ: h only; the cached projection row is fetched below, under the MMAs)
+        const float* prow = nullptr;
+        if (PROJ) {
+            if (valid) prow = cur.next(step);
+        } else {
+            float x[16];
 #pragma unroll
-        for (int f = 0; f < 16; ++f) x[f] = 0.f;
-        if (valid) {
-            const float* row = RING ? cur.next(step) : in.inputs + (i * in.T + step) * F;
-            if (row != nullptr) {
+            for (int f = 0; f < 16; ++f) x[f] = 0.f;
+            if (valid) {
+                const float* row = RING ? cur.next(step) : in.inputs + (i * in.T + step) * F;
+                if (row != nullptr) {
 #pragma unroll
-                for (int f = 0; f < F; ++f) x[f] = __ldg(row + f);
+                    for (int f = 0; f < F; ++f) x[f] = __ldg(row + f);
+                }
             }
-        }
 #pragma unroll
-        for (int c = 0; c < TC5_KXC; ++c) tc5_put4(sm.ax_hi[c], sm.ax_lo[c], tid, x[4 * c], x[4 * c + 1], x[4 * c + 2], x[4 * c + 3]);
+            for (int c = 0; c < TC5_KXC; ++c) tc5_put4(sm.ax_hi[c], sm.ax_lo[c], tid, x[4 * c], x[4 * c + 1], x[4 * c + 2], x[4 * c + 3]);
+        }
 #pragma unroll
         for (int c = 0; c < TC5_KHC; ++c) tc5_put4(sm.ah_hi[c], sm.ah_lo[c], tid, h[4 * c], h[4 * c + 1], h[4 * c + 2], h[4 * c + 3]);
         fence_proxy_async();
         tc5_fence_before();
         mbar_arrive(&sm.ready[0]);
+        // additive terms of the three gates: the cached projection (bias included) or, for rows before the stream's first
+        // frame and in the non-PROJ kernel, the bias
+        float pz[24], pr[24], ph[24];
+#pragma unroll
+        for (int j = 0; j < 24; ++j) { pz[j] = sm.bias[j]; pr[j] = sm.bias[24 + j]; ph[j] = sm.bias[TC5_N1 + j]; }
+        if (PROJ && prow != nullptr) {
+#pragma unroll
+            for (int q = 0; q < 5; ++q) {
+                const float4 a = __ldg(reinterpret_cast<const float4*>(prow) + q), b = __ldg(reinterpret_cast<const float4*>(prow + 20) + q),
+                             c = __ldg(reinterpret_cast<const float4*>(prow + 40) + q);
+                pz[4 * q] = a.x; pz[4 * q + 1] = a.y; pz[4 * q + 2] = a.z; pz[4 * q + 3] = a.w;
+                pr[4 * q] = b.x; pr[4 * q + 1] = b.y; pr[4 * q + 2] = b.z; pr[4 * q + 3] = b.w;
+                ph[4 * q] = c.x; ph[4 * q + 1] = c.y; ph[4 * q + 2] = c.z; ph[4 * q + 3] = c.w;
+            }
+        }
         mbar_wait(&sm.bar[0], step & 1);
         tc5_fence_after();
         float z[24];
@@ -214,8 +241,8 @@ gru_tc5_kernel(GruTc5W W, K2In in, long long n, DecodeParams dp, K2Out out) {
             }
 #pragma unroll
             for (int j = 0; j < 24; ++j) {
-                z[j] = hard_sigmoid(zr[j] + sm.bias[j]);
-                const float r = hard_sigmoid(zr[24 + j] + sm.bias[24 + j]);
+                z[j] = hard_sigmoid(zr[j] + pz[j]);
+                const float r = hard_sigmoid(zr[24 + j] + pr[j]);
                 zr[j] = r * h[j];                                    // r * h, reusing the array
             }
 #pragma unroll
@@ -235,7 +262,7 @@ gru_tc5_kernel(GruTc5W W, K2In in, long long n, DecodeParams dp, K2Out out) {
                 for (int e = 0; e < 16; ++e) hh[16 * q + e] = d[e];
             }
 #pragma unroll
-            for (int j = 0; j < 24; ++j) h[j] = j < H ? z[j] * h[j] + (1.f - z[j]) * (hh[j] + sm.bias[TC5_N1 + j]) : 0.f;
+            for (int j = 0; j < 24; ++j) h[j] = j < H ? z[j] * h[j] + (1.f - z[j]) * (hh[j] + ph[j]) : 0.f;
         }
     }
     float logit = W.bd;

@@ -652,3 +652,23 @@ def test_experimental_mfcc_tick(k1_mode):
             assert np.array_equal(wa, wb), k
         assert np.max(np.abs(a['raw'].cpu().numpy() - b['raw'].cpu().numpy())) < 1e-4, k
     ref.core.close(); tc.core.close()
+
+
+@pytest.mark.skipif(os.environ.get('PB_TEST_TC_K1') != '1',
+                    reason='opt-in tcgen05 scan over cached projections (pb_debug_gru_mode 8): not yet validated on hardware')
+def test_experimental_tcgen05_scan_over_cached_projections():
+    m = _mod()
+    S, K, chunk = 9000, 36, 1024
+    pcm = noise(64, K * chunk, seed=61)
+    pcm = np.tile(pcm, (S // 64 + 1, 1))[:S].copy()
+    model = m.GruModel.random(13, 20, seed=8, scale=0.1)
+    model.dense_b = 3.0
+    res = []
+    for mode in (8, 1):
+        sb = m.StreamBatch(model, S, chunk_samples=chunk)
+        sb.core.gru_mode(mode)
+        raws = [sb.update(cuda(pcm[:, k * chunk:(k + 1) * chunk]))['raw'].cpu().numpy().copy() for k in range(K)]
+        res.append((np.array(raws), int(sb.count.item())))
+        sb.core.close()
+    assert np.max(np.abs(res[0][0] - res[1][0])) < 1e-5
+    assert res[0][1] > 0 and abs(res[0][1] - res[1][1]) <= 3
