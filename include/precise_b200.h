@@ -84,7 +84,11 @@ typedef struct pb_config {
     /* ---- TriggerDetector ---- */
     double sensitivity;        /* 0.5 */
     int32_t trigger_level;     /* 3   */
-    int32_t reserved;
+    int32_t decode_legacy_f64; /* 0 (default): asigmoid's `1 / x - 1` in float32, what the reference computes for the
+                                * np.float32 that Runner.run returns (network_runner.py:73-74, functions.py:99-101) under
+                                * NumPy >= 2 scalar promotion -- the behaviour of the reference run in this image;
+                                * 1: the same expression in float64, what NumPy 1.16 (the reference's own pin, setup.py:74)
+                                * evaluates, because legacy promotion makes `1 / np.float32` a float64 */
 } pb_config;
 
 typedef struct pb_handle pb_handle;

@@ -30,7 +30,7 @@ class pb_config(C.Structure):
         ('n_thresholds', C.c_int32),
         ('threshold_mu', C.c_double * PB_MAX_THRESHOLDS), ('threshold_std', C.c_double * PB_MAX_THRESHOLDS),
         ('threshold_center', C.c_double),
-        ('sensitivity', C.c_double), ('trigger_level', C.c_int32), ('reserved', C.c_int32),
+        ('sensitivity', C.c_double), ('trigger_level', C.c_int32), ('decode_legacy_f64', C.c_int32),
     ]
 
 
@@ -109,7 +109,7 @@ def check(rc: int):
 
 def make_config(pr: ListenerParams, hidden=20, max_streams=1, chunk_samples=1024, device=0,
                 sensitivity=0.5, trigger_level=3, activation='linear',
-                recurrent_activation='hard_sigmoid') -> pb_config:
+                recurrent_activation='hard_sigmoid', decode_legacy_f64=False) -> pb_config:
     cfg = pb_config()
     check(get_lib().pb_config_default(C.byref(cfg)))
     cfg.device = device
@@ -137,6 +137,7 @@ def make_config(pr: ListenerParams, hidden=20, max_streams=1, chunk_samples=1024
     cfg.threshold_center = pr.threshold_center
     cfg.sensitivity = sensitivity
     cfg.trigger_level = trigger_level
+    cfg.decode_legacy_f64 = int(bool(decode_legacy_f64))
     return cfg
 
 
@@ -164,6 +165,21 @@ def _ptr(t):
     return None if t is None else C.c_void_p(t.data_ptr())
 
 
+def _np_ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _check_np(name, a, dtype, shape, optional=True):
+    """The C ABI takes raw host pointers: refuse anything whose dtype / shape / layout it would misread."""
+    if a is None:
+        if optional:
+            return
+        raise ValueError('%s is required' % name)
+    if not isinstance(a, np.ndarray) or a.dtype != np.dtype(dtype) or not a.flags.c_contiguous or tuple(a.shape) != tuple(shape):
+        raise ValueError('%s must be a C-contiguous %s array of shape %s, got %s %s' % (
+            name, np.dtype(dtype).name, tuple(shape), getattr(a, 'dtype', type(a)), getattr(a, 'shape', None)))
+
+
 class PreciseB200:
     """One library handle: tables + per-stream state for ``max_streams`` streams on one GPU.
 
@@ -173,7 +189,7 @@ class PreciseB200:
 
     def __init__(self, params: ListenerParams = None, hidden=20, max_streams=1, chunk_samples=1024,
                  device=0, sensitivity=0.5, trigger_level=3, activation='linear',
-                 recurrent_activation='hard_sigmoid'):
+                 recurrent_activation='hard_sigmoid', decode_legacy_f64=False, check_ids=False):
         import torch
         self.torch = torch
         self.lib = get_lib()
@@ -182,7 +198,8 @@ class PreciseB200:
             raise PBError('no CUDA device: mycroft_precise_b200 has no CPU path')
         self.device = torch.device('cuda', device)
         self.cfg = make_config(self.params, hidden, max_streams, chunk_samples, device, sensitivity,
-                               trigger_level, activation, recurrent_activation)
+                               trigger_level, activation, recurrent_activation, decode_legacy_f64)
+        self.check_ids = bool(check_ids)      # debug: also verify 0 <= ids < max_streams and uniqueness (a device sync)
         h = C.c_void_p()
         check(self.lib.pb_create(C.byref(self.cfg), C.byref(h)))
         self._h = h
@@ -265,13 +282,47 @@ class PreciseB200:
         check(self.lib.pb_decode(self._h, _ptr(raw), raw.numel(), _ptr(out), self._stream()))
         return out.view(raw.shape)
 
+    # ---- argument checks: the C ABI reads raw device pointers, so dtype / device / size / layout are verified here
+    def _check_t(self, name, t, dtype, numel, optional=True):
+        if t is None:
+            if optional:
+                return
+            raise ValueError('%s is required' % name)
+        if (not isinstance(t, self.torch.Tensor) or t.dtype != dtype or t.device != self.device
+                or t.numel() != numel or not t.is_contiguous()):
+            raise ValueError('%s must be a contiguous %s tensor with %d elements on %s, got %s %s on %s' % (
+                name, dtype, numel, self.device, getattr(t, 'dtype', type(t)), tuple(getattr(t, 'shape', ())),
+                getattr(t, 'device', None)))
+
+    def _check_ids(self, ids, n):
+        self._check_t('ids', ids, self.torch.int32, n)
+        if ids is not None and self.check_ids and n:
+            lo, hi = int(ids.min()), int(ids.max())
+            if lo < 0 or hi >= self.max_streams:
+                raise ValueError('stream ids must lie in [0, %d), got [%d, %d]' % (self.max_streams, lo, hi))
+            if int(self.torch.unique(ids).numel()) != n:
+                raise ValueError('stream ids must be unique within a tick')
+
+    def _check_pcm(self, pcm):
+        torch = self.torch
+        if (not isinstance(pcm, torch.Tensor) or pcm.dtype != torch.int16 or pcm.dim() != 2 or pcm.shape[1] != self.chunk_samples
+                or not pcm.is_contiguous() or pcm.device != self.device):
+            raise ValueError('pcm must be a contiguous int16 [n, %d] tensor on %s' % (self.chunk_samples, self.device))
+        if pcm.shape[0] > self.max_streams:
+            raise ValueError('n = %d exceeds max_streams = %d' % (pcm.shape[0], self.max_streams))
+        return pcm.shape[0]
+
     # ---- stateful tick
     def update(self, pcm, ids=None, out=None, count=None):
         """pcm [n, chunk_samples] int16 CUDA.  Returns dict(raw, conf, fired) (+ count accumulates)."""
         torch = self.torch
-        n = pcm.shape[0]
-        if pcm.dtype != torch.int16 or pcm.dim() != 2 or pcm.shape[1] != self.chunk_samples or not pcm.is_contiguous():
-            raise ValueError('pcm must be a contiguous int16 [n, %d] tensor' % self.chunk_samples)
+        n = self._check_pcm(pcm)
+        self._check_ids(ids, n)
+        if out is not None:
+            self._check_t("out['raw']", out.get('raw'), torch.float32, n)
+            self._check_t("out['conf']", out.get('conf'), torch.float64, n, optional=False)
+            self._check_t("out['fired']", out.get('fired'), torch.uint8, n)
+        self._check_t('count', count, torch.int64, 1)
         if out is None:
             out = dict(raw=torch.empty(n, dtype=torch.float32, device=self.device),
                        conf=torch.empty(n, dtype=torch.float64, device=self.device),
@@ -281,24 +332,38 @@ class PreciseB200:
         return out
 
     def update_vectors(self, pcm, ids=None):
-        check(self.lib.pb_update_vectors(self._h, _ptr(pcm), _ptr(ids), pcm.shape[0], self._stream()))
+        n = self._check_pcm(pcm)
+        self._check_ids(ids, n)
+        check(self.lib.pb_update_vectors(self._h, _ptr(pcm), _ptr(ids), n, self._stream()))
 
     def read_window(self, n=None, ids=None):
         torch = self.torch
         n = (ids.numel() if ids is not None else (self.max_streams if n is None else n))
+        self._check_ids(ids, n)
         out = torch.empty((n, self.n_features, self.mfcc_width), dtype=torch.float32, device=self.device)
         check(self.lib.pb_read_window(self._h, _ptr(ids), n, _ptr(out), self._stream()))
         return out
 
     def clear(self, n=None, ids=None):
         n = (ids.numel() if ids is not None else (self.max_streams if n is None else n))
+        self._check_ids(ids, n)
         check(self.lib.pb_clear(self._h, _ptr(ids), n, self._stream()))
 
     def update_host(self, pcm_np, conf_np, raw_np=None, fired_np=None, ids_np=None) -> int:
         """Host-buffer tick (numpy arrays, ideally backed by pinned memory).  Returns this tick's count."""
+        if not isinstance(pcm_np, np.ndarray) or pcm_np.ndim != 2:
+            raise ValueError('pcm_np must be an int16 array of shape (n, %d)' % self.chunk_samples)
         n = pcm_np.shape[0]
+        _check_np('pcm_np', pcm_np, np.int16, (n, self.chunk_samples), optional=False)
+        _check_np('conf_np', conf_np, np.float64, (n,), optional=False)
+        _check_np('raw_np', raw_np, np.float32, (n,))
+        _check_np('fired_np', fired_np, np.uint8, (n,))
+        _check_np('ids_np', ids_np, np.int32, (n,))
+        if ids_np is not None and self.check_ids and n:
+            if ids_np.min() < 0 or ids_np.max() >= self.max_streams or len(np.unique(ids_np)) != n:
+                raise ValueError('stream ids must be unique and lie in [0, %d)' % self.max_streams)
         cnt = C.c_uint64(0)
-        vp = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
+        vp = _np_ptr
         check(self.lib.pb_update_host(self._h, vp(pcm_np), vp(ids_np), n, vp(raw_np), vp(conf_np), vp(fired_np),
                                       C.cast(C.byref(cnt), C.c_void_p)))
         return int(cnt.value)

@@ -23,6 +23,7 @@
 #include "gru_tc5.cuh"
 #include "gru_tc5_big.cuh"
 #include "mfcc_tc.cuh"
+#include "mfcc_tc2.cuh"
 
 using namespace pb;
 
@@ -71,7 +72,8 @@ struct pb_handle {
     size_t k1_batch_smem = 0, k1_stream_smem = 0, k1_fast_smem = 0;
     bool force_generic = false;      // tests: exercise the generic kernels on the aligned geometry
     int k1_mode = 0;                 // 0 = default kernels, 1 = experimental tensor-core DFT tick (mfcc_tc.cuh; opt-in, see its header), 2 = fast kernel, lean set-up (opt-in)
-    bool tcd_ok = false;             // geometry supported by mfcc_tc_stream_kernel
+    bool tcd_ok = false;             // geometry the tensor-core DFT tables cover (CPU model + kernel)
+    bool tc2_ok = false;             // ... and by mfcc_tc2_stream_kernel<Tc2Geo20> (run-time mel tables equal its compile-time ones)
     std::vector<float> h_wrise, h_wfall; std::vector<int> h_grid;      // host copies for the lazily built tcd tables
     uint4* d_tcd_b = nullptr; float4* d_tcd_etab = nullptr; float* d_tcd_dct = nullptr;
     float tcd_tot_scale = 0.f;
@@ -359,7 +361,10 @@ PB_API int pb_create(const pb_config* cfg, pb_handle** out) {
     h->fast_ok = c.n_fft == 512 && h->used == 512 && c.hop_samples % 8 == 0 && n_pieces <= 64 && h->npl <= 4;
     h->h_wrise = wrise; h->h_wfall = wfall; h->h_grid = grid;
     h->tcd_ok = h->fast_ok && c.vectorizer == PB_VEC_MFCCS && c.n_filt <= TCD_MAX_FILT && h->n_out <= TCD_MAX_OUT &&
-                c.chunk_samples % 8 == 0 && c.chunk_samples >= 512 && (c.chunk_samples + c.hop_samples - 1) / c.hop_samples <= TCD_MAX_NEW;
+                c.chunk_samples % 8 == 0 && c.chunk_samples >= 512 && (c.chunk_samples + c.hop_samples - 1) / c.hop_samples <= TC2_MAX_NEW;
+    h->tc2_ok = h->tcd_ok && c.hop_samples <= 16384 && h->ring_rows <= 255 && h->n_out >= 1 &&
+                (c.chunk_samples + c.hop_samples - 1) / c.hop_samples <= TC2_MAX_NEW &&
+                tc2_geo_matches<Tc2Geo20>(c.n_filt, h->n_bins, grid, wrise, wfall);
     h->k1_fast_smem = K1F_WARPS * sizeof(K1FWarp) + (size_t)h->npl * 128 * sizeof(float4) +
                       (size_t)c.n_filt * 16 * h->nol * sizeof(float) + (((size_t)c.n_filt * h->maxc + 15) & ~(size_t)15);
     // DCT-II, norm='ortho' (scipy.fftpack.dct as sonopy.mfcc_spec calls it), first n_out rows
@@ -645,9 +650,9 @@ PB_API int pb_debug_gru_mode(pb_handle* h, int mode) { if (!h) return fail(PB_ER
 
 PB_API int pb_debug_k1_mode(pb_handle* h, int mode) {
     if (!h) return fail(PB_ERR_INVALID, "null handle");
-    if (mode < 0 || mode > 2) return fail(PB_ERR_INVALID, "k1 mode must be 0 (default kernels), 1 (experimental tensor-core DFT) or 2 (fast kernel with the lean per-pass set-up)");
+    if (mode < 0 || mode > 4 || mode == 1) return fail(PB_ERR_INVALID, "k1 mode must be 0 (automatic), 2 (FFT kernel, lean set-up), 3 (FFT kernel) or 4 (tensor-core DFT kernel)");
+    if (mode == 4 && !h->tc2_ok) return fail(PB_ERR_UNSUPPORTED, "the tensor-core MFCC tick needs the default mel geometry (20 filters, 16 kHz, n_fft 512), chunk >= 512 and a multiple of 8");
     if (mode == 2 && !h->fast_ok) return fail(PB_ERR_UNSUPPORTED, "k1 mode 2 needs the aligned geometry of the fast MFCC kernels");
-    if (mode == 1 && !h->tcd_ok) return fail(PB_ERR_UNSUPPORTED, "the tensor-core MFCC tick needs n_fft 512, chunk >= 512 and a multiple of 8, n_filt <= %d, MFCC vectorizer", TCD_MAX_FILT);
     h->k1_mode = mode;
     return PB_OK;
 }
@@ -742,6 +747,7 @@ static DecodeParams decode_params(const pb_handle* h) {
     long long q = -(8 * 2048) / bytes;                            // C truncates toward zero ...
     if ((-(8 * 2048)) % bytes != 0) q -= 1;                       // ... python floors
     d.trigger_reset = (int)q;
+    d.legacy_f64 = h->cfg.decode_legacy_f64 != 0;
     return d;
 }
 
@@ -904,7 +910,7 @@ static int ensure_tcd_tables(pb_handle* h) {
     CK(cudaMemcpy(h->d_tcd_b, both.data(), both.size() * sizeof(__half), cudaMemcpyHostToDevice));
     CK(upload(&h->d_tcd_etab, etab));
     CK(upload(&h->d_tcd_dct, dct));
-    CK(ensure_dyn_smem(mfcc_tc_stream_kernel, sizeof(TcdSmem) + 128));
+    CK(ensure_dyn_smem(mfcc_tc2_stream_kernel<Tc2Geo20>, sizeof(Tc2Smem) + 128));
     return PB_OK;
 }
 
@@ -915,15 +921,17 @@ static int launch_stream_mfcc(pb_handle* h, const int16_t* d_pcm, const int32_t*
     const int grid = (int)std::min<int64_t>(tiles, (int64_t)h->sm_count * 4);
     const float inv = 1.0f / 32768.0f, scale = inv * inv / (float)h->cfg.n_fft;
     ProfScope ps(h, 0, s);
-    if (h->k1_mode == 1 && h->tcd_ok && (uintptr_t)d_pcm % 16 == 0 && !h->force_generic) {
+    if (h->k1_mode == 4 && h->tc2_ok && (uintptr_t)d_pcm % 16 == 0 && !h->force_generic) {
         int rc = ensure_tcd_tables(h);
         if (rc != PB_OK) return rc;
-        TcdTables t;
-        t.b = h->d_tcd_b; t.etab = h->d_tcd_etab; t.dct = h->d_tcd_dct; t.n_filt = h->cfg.n_filt; t.n_out = h->n_out;
-        t.tot_scale = h->tcd_tot_scale;
-        const int groups = (int)((n + TCD_GROUP - 1) / TCD_GROUP);
-        mfcc_tc_stream_kernel<<<std::min(groups, h->sm_count), TCD_THREADS, sizeof(TcdSmem) + 128, s>>>(d_pcm, d_ids, (int)n, h->cfg.chunk_samples,
-                                                                                                    h->cfg.hop_samples, t, h->st);
+        Tc2Tables t;
+        t.b = h->d_tcd_b; t.dct = h->d_tcd_dct; t.n_out = h->n_out; t.pscale = h->tcd_tot_scale;
+        // super-groups: one per SM where the batch allows it, a multiple of 32 streams, at most TC2_SG_MAX
+        int sg = (int)((n + h->sm_count - 1) / h->sm_count);
+        sg = std::min(TC2_SG_MAX, std::max(128, (sg + 31) & ~31));
+        const int groups = (int)((n + sg - 1) / sg);
+        mfcc_tc2_stream_kernel<Tc2Geo20><<<std::min(groups, h->sm_count), TC2_THREADS, sizeof(Tc2Smem) + 128, s>>>(
+            d_pcm, d_ids, (int)n, sg, h->cfg.chunk_samples, h->cfg.hop_samples, t, h->st);
     } else if (h->fast_ok && h->cfg.chunk_samples % 8 == 0 && (uintptr_t)d_pcm % 16 == 0 && !h->force_generic) {
         // streams per warp tile: 16 at scale; fewer when the batch cannot fill the machine's warps
         const int64_t warps_total = (int64_t)h->sm_count * 4 * K1F_WARPS;

@@ -26,6 +26,7 @@ struct DecodeParams {
     double hot_threshold;    // 1.0 - sensitivity
     int trigger_level;
     int trigger_reset;       // -(8*2048) // chunk_bytes  (python floor division)
+    int legacy_f64;          // pb_config.decode_legacy_f64
 };
 
 struct K2Out {
@@ -58,7 +59,10 @@ __device__ __forceinline__ float ract(float x) { return RACT == 0 ? hard_sigmoid
 template <int ACT>
 __device__ __forceinline__ float act(float x) { return ACT == 0 ? x : tanhf(x); }
 
-// ThresholdDecoder.decode on a float32 network output, in float64 like the reference.
+// ThresholdDecoder.decode on a float32 network output.  Runner.run hands the decoder an np.float32
+// (network_runner.py:73-74, :94-95), so functions.asigmoid (functions.py:99-101) evaluates `1 / x - 1` in float32 under
+// NumPy >= 2 promotion rules and only math.log in double; under NumPy 1.16 the same expression is float64
+// (d.legacy_f64).  Everything after the logarithm is Python float (double) arithmetic in both cases.
 __device__ __forceinline__ double decode_one(float raw, const DecodeParams& d) {
     const double r = (double)raw;
     if (raw == 1.0f || raw == 0.0f) return r;
@@ -66,7 +70,8 @@ __device__ __forceinline__ double decode_one(float raw, const DecodeParams& d) {
     if (d.out_range == 0) {
         cp = r > (double)d.min_out ? 1.0 : 0.0;
     } else {
-        double lg = -log(1.0 / r - 1.0);                               // functions.asigmoid
+        const double t = d.legacy_f64 ? 1.0 / r - 1.0 : (double)__fsub_rn(__fdiv_rn(1.0f, raw), 1.0f);
+        double lg = -log(t);                                           // functions.asigmoid
         double ratio = (lg - (double)d.min_out) / (double)d.out_range;
         ratio = fmin(fmax(ratio, 0.0), 1.0);
         int idx = (int)__dadd_rn(__dmul_rn(ratio, (double)(d.cd_len - 1)), 0.5);

@@ -1,11 +1,4 @@
-// mfcc_tc.cuh -- EXPERIMENTAL K1 variant: the 512-point real DFT on the 5th-generation tensor cores (tcgen05 + TMEM).
-//
-// Status: written at the end of round 1 after the GPU budget was spent.  The host-side parts (twiddle tables in the UMMA
-// operand layout, accumulator-column -> bin map, the 16-point real-DFT butterfly, the mel / DCT tables and the epilogue's
-// arithmetic) are verified on the CPU (pb_debug_tc_dft_power, pb_debug_tc_mfcc_frame, tests/test_tc_dft_host_model.py); the
-// kernel itself compiles for sm_100a but has NOT run on hardware yet.  It is
-// therefore opt-in only (pb_debug_k1_mode(h, 1)); the default MFCC kernels are untouched.  Design and numbers: DESIGN.md
-// section 6 ("Round-2 plan for K1"), numerical study: scripts/proto_tc_dft.py.
+// mfcc_tc.cuh -- host tables, CPU model and device helpers of the tensor-core MFCC tick (the kernel itself: mfcc_tc2.cuh).
 //
 // Replaces, per frame, np.fft.rfft(frame, n=512), the power spectrum, the mel filterbank, log, DCT and c0 of
 // sonopy.mfcc_spec as the reference calls it (precise/vectorization.py:36-39), for the stateful tick
@@ -17,12 +10,8 @@
 // Block 0 takes [Y_0 | Y_8] (both real), block r = 1..7 takes [Re Y_r | Im Y_r] and also yields X[16 m + 16 - r] from
 // conj(Y_r) = Y_(16-r).  Operands are fp16 hi + lo pieces, three passes (a_lo b_hi + a_hi b_lo + a_hi b_hi, fp32
 // accumulate): 6e-7 of the peak bin against a float64 FFT, the accuracy of the fp32 FFT kernels.
-//
-// Mapping.  A CTA owns groups of 128 streams; the frames a tick releases in a group are processed in tiles of 128 frames =
-// the 128 TMEM lanes.  Warps 0-3: epilogue, thread <-> frame (TMEM lane): tcgen05.ld -> power -> mel (table driven) -> log
-// -> DCT -> ring row.  Warps 4-11: producers, thread <-> (frame, four n2): 16 x LDG.64 of PCM, four real DFT-16s, fp16
-// split, sixteen 16-byte stores into the K-major canonical A tiles.  Warp 12: one lane issues the 96 MMAs of a tile
-// (4 K-steps x 8 blocks x 3 passes, M = 128, N = 64, K = 16).  Hand-offs are mbarriers only inside a group.
+// The CPU model below (same butterfly, same operand tables read through the same layout arithmetic) is what
+// tests/test_tc_dft_host_model.py checks without a device.
 #pragma once
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
@@ -39,14 +28,16 @@ namespace pb {
 
 constexpr int TCD_BLOCKS = 8;                 // GEMM blocks per frame
 constexpr int TCD_KSTEPS = 4;                 // K = 64 per block = 4 MMA K-steps of 16
-constexpr int TCD_EPI_WARPS = 4, TCD_PROD_WARPS = 8;
-constexpr int TCD_THREADS = (TCD_EPI_WARPS + TCD_PROD_WARPS + 1) * 32;     // 416
-constexpr int TCD_GROUP = 128;                // streams per group
 constexpr int TCD_MAX_NEW = 4;                // frames a stream may release per tick
 constexpr int TCD_MAX_FILT = 22;              // n_filt + 2 accumulator slots of 128 floats must fit
 constexpr int TCD_MAX_OUT = 16;
-constexpr float TCD_IN_SCALE = 0.03125f;      // 2^-5 folded into the int16 -> float conversion; the butterfly returns 2 Y
-constexpr float TCD_A_SCALE = 0.0625f;        // => A operands hold Y * 2^-4: |A| <= 32768 < fp16 max
+constexpr float TCD_IN_SCALE = 0.015625f;     // 2^-6 folded into the int16 -> float conversion; the butterfly returns 2 Y
+constexpr float TCD_A_SCALE = 0.03125f;       // => A operands hold Y * 2^-5: |A| <= 16384, and <= 32768 < fp16 max after the shift below
+// The kernel transforms x - x[0] (a constant only moves X[0]; constant input then gives exact zeros everywhere else, like the
+// float64 reference and the FFT kernels): Y_0 loses 16 x[0], i.e. the butterfly output 2 * 16 * IN_SCALE * x[0], and the
+// X[0] accumulator gets 32 times that back.
+constexpr float TCD_X0_Y = 32.f * TCD_IN_SCALE;          // 0.5
+constexpr float TCD_X0_D = 32.f * TCD_X0_Y;              // 16
 
 // ---------------------------------------------------------------------------------------------------------------------
 // 16-point DFT of real data, outputs scaled by 2: yr[k] + i yi[k] = 2 * sum_q x[q] w16^(q k), k = 0..8 (yi[0] = yi[8] = 0).
@@ -100,8 +91,10 @@ __host__ __device__ __forceinline__ void rdft16_x2(const float (&x)[16], float (
 // ---------------------------------------------------------------------------------------------------------------------
 // Host tables.
 //   B operand of block b, piece hi / lo: fp16 [kgroup 8][n 64][8]  (K-major canonical, no swizzle: element (n, k) at
-//   ((k / 8) * 64 + n) * 8 + k % 8).  k = 8 g + e: e < 4 -> first input half, n2 = 4 g + e; e >= 4 -> second half,
-//   n2 = 4 g + e - 4  (the producer task (frame, g) writes exactly one 16-byte K-group per block).
+//   ((k / 8) * 64 + n) * 8 + k % 8).  K-group g holds the inputs n2 = 4 g .. 4 g + 3 (the four samples one producer lane
+//   loads per 32-sample row), first and second input half of the block; element order inside the 16-byte group:
+//   tcd_kslot(j, second, g) -- two 8-byte halves, one per sample pair (j >> 1), swapped for odd g so that the two lanes
+//   that share a frame row store to different bank halves.
 //   Output column c of block b (accumulator column 64 b + c):
 //     block 0: [Re X[16m] | Im X[16m] (m = 0 carries X[256]) | Re X[16m+8] | Im X[16m+8]],   m = c % 16
 //     block r: [Re X[16m+r] | Im X[16m+r] | Re X[16m+16-r] | Im X[16m+16-r]]
@@ -111,7 +104,13 @@ struct TcdHostTables {
     std::vector<float> dct;                    // [TCD_MAX_OUT][24]
 };
 
+// position (0..7) inside K-group g of input n2 = 4 g + j, first (second = 0) or second (second = 1) input half of the block
+__host__ __device__ constexpr int tcd_kslot(int j, int second, int g) { return 4 * ((j >> 1) ^ (g & 1)) + 2 * second + (j & 1); }
+
 // bin held by element m of 32-column chunk c = 2 b + h (16 re columns then 16 im columns)
+__host__ __device__ constexpr int tcd_chunk_bin_c(int c, int m) {
+    return (c >> 1) == 0 ? ((c & 1) == 0 ? 16 * m : 16 * m + 8) : ((c & 1) == 0 ? 16 * m + (c >> 1) : 16 * m + 16 - (c >> 1));
+}
 static inline int tcd_chunk_bin(int c, int m) {
     const int b = c >> 1, h = c & 1;
     if (b == 0) return h == 0 ? 16 * m : 16 * m + 8;
@@ -125,7 +124,8 @@ static inline void tcd_build_b(std::vector<__half>& b_hi, std::vector<__half>& b
     for (int b = 0; b < TCD_BLOCKS; ++b)
         for (int k = 0; k < 64; ++k)
             for (int n = 0; n < 64; ++n) {
-                const int g = k >> 3, e = k & 7, n2 = 4 * g + (e & 3), second = e >> 2;      // which input this row multiplies
+                const int g = k >> 3, e = k & 7;                                             // which input this row multiplies:
+                const int second = (e >> 1) & 1, n2 = 4 * g + 2 * ((e >> 2) ^ (g & 1)) + (e & 1);   // inverse of tcd_kslot
                 const int quarter = n >> 4, m = n & 15;
                 double v = 0.0;
                 if (b == 0) {
@@ -177,8 +177,8 @@ static inline void tcd_build_etab(std::vector<float4>& etab, const std::vector<f
 }
 
 // CPU model of the tensor-core path for ONE frame of 512 int16 samples: the same butterfly, the same tables read through the
-// same layout arithmetic, fp16 products accumulated in fp32.  d[512] = the frame's accumulator row (TMEM lane) as the
-// epilogue sees it.
+// same layout arithmetic, fp16 products accumulated in fp32, the frame's first sample removed from Y_0 and restored in X[0].
+// d[512] = the frame's accumulator row (TMEM lane) as the epilogue sees it after that correction.
 static inline void tcd_host_accumulators(const int16_t* x, float* d) {
     static std::vector<__half> b_hi, b_lo;
     if (b_hi.empty()) tcd_build_b(b_hi, b_lo);
@@ -189,8 +189,8 @@ static inline void tcd_host_accumulators(const int16_t* x, float* d) {
             float in[16], yr[9], yi[9];
             for (int q = 0; q < 16; ++q) in[q] = (float)x[n2 + 32 * q] * TCD_IN_SCALE;
             rdft16_x2(in, yr, yi);
-            a[0 * 64 + 8 * g + j] = yr[0]; a[0 * 64 + 8 * g + 4 + j] = yr[8];
-            for (int r = 1; r < 8; ++r) { a[r * 64 + 8 * g + j] = yr[r]; a[r * 64 + 8 * g + 4 + j] = yi[r]; }
+            a[0 * 64 + 8 * g + tcd_kslot(j, 0, g)] = yr[0] - TCD_X0_Y * (float)x[0]; a[0 * 64 + 8 * g + tcd_kslot(j, 1, g)] = yr[8];
+            for (int r = 1; r < 8; ++r) { a[r * 64 + 8 * g + tcd_kslot(j, 0, g)] = yr[r]; a[r * 64 + 8 * g + tcd_kslot(j, 1, g)] = yi[r]; }
         }
     for (int b = 0; b < TCD_BLOCKS; ++b)
         for (int n = 0; n < 64; ++n) {
@@ -206,6 +206,7 @@ static inline void tcd_host_accumulators(const int16_t* x, float* d) {
                 }
             d[64 * b + n] = acc;
         }
+    d[0] += TCD_X0_D * (float)x[0];            // the kernel transforms x - x[0] (exact zeros for constant input) and restores X[0] here
 }
 
 // |X[k]|^2 of the raw samples, k = 0..256
@@ -266,31 +267,6 @@ static inline void tcd_host_epilogue(const float* d, const float4* etab, const f
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-struct TcdTables {               // device pointers
-    const uint4* b;              // [2][8][8][64] x 16 bytes: hi then lo
-    const float4* etab;          // [257]
-    const float* dct;            // [TCD_MAX_OUT][24]
-    int n_filt, n_out;
-    float tot_scale;             // pscale for the total power (c0)
-};
-
-struct TcdSmem {
-    __half b_hi[TCD_BLOCKS][8][64][8];
-    __half b_lo[TCD_BLOCKS][8][64][8];
-    __half a_hi[TCD_BLOCKS][2][128][8];          // the current K-step: two 16-byte K-groups per block
-    __half a_lo[TCD_BLOCKS][2][128][8];
-    float acc[TCD_MAX_FILT + 2][128];            // mel accumulators, slot j + 1 = filter j, own column per epilogue thread
-    float4 etab[257];
-    float dct[TCD_MAX_OUT][24];
-    long long st_n0[TCD_GROUP], st_c0[TCD_GROUP], st_ts0[TCD_GROUP];
-    int st_id[TCD_GROUP], st_cnt[TCD_GROUP];
-    short fr_stream[TCD_GROUP * TCD_MAX_NEW], fr_sub[TCD_GROUP * TCD_MAX_NEW];
-    int warp_tot[4];
-    int n_frames;
-    unsigned long long a_full, a_empty, d_full, d_empty;
-    uint32_t tmem_base;
-};
-
 // instruction descriptor: kind::f16, A and B fp16 K-major, fp32 accumulate, M = 128
 __device__ __forceinline__ uint32_t tcd_idesc(int n) {
     return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
@@ -301,262 +277,20 @@ __device__ __forceinline__ void tcd_mma(uint32_t d_tmem, uint64_t a, uint64_t b,
                  ::"r"(d_tmem), "l"(a), "l"(b), "r"(idesc), "r"(accumulate), "r"(0), "r"(0), "r"(0), "r"(0) : "memory");
 }
 
-// int16 pair (already XORed with 0x80008000) -> two floats scaled by 2^-5, exact: drop the biased 16-bit value into the
-// mantissa of 2^18 (ulp 2^-5) and subtract 2^18 + 32768 * 2^-5.
+// int16 pair (already XORed with 0x80008000) -> two floats scaled by 2^-6 (TCD_IN_SCALE), exact: drop the biased 16-bit value
+// into the mantissa of 2^17 (ulp 2^-6) and subtract 2^17 + 32768 * 2^-6.
 __device__ __forceinline__ void tcd_cvt2(uint32_t v, float& lo, float& hi) {
-    lo = __uint_as_float(__byte_perm(v, 0x48800000u, 0x7610)) - 263168.f;
-    hi = __uint_as_float(__byte_perm(v, 0x48800000u, 0x7632)) - 263168.f;
+    lo = __uint_as_float(__byte_perm(v, 0x48000000u, 0x7610)) - 131584.f;
+    hi = __uint_as_float(__byte_perm(v, 0x48000000u, 0x7632)) - 131584.f;
 }
 
-// eight floats -> fp16 hi and lo pieces, one 16-byte store each
-__device__ __forceinline__ void tcd_put8(__half* hi_dst, __half* lo_dst, const float (&v)[8]) {
-    uint32_t hw[4], lw[4];
-#pragma unroll
-    for (int p = 0; p < 4; ++p) {
-        const __half2 h = __floats2half2_rn(v[2 * p], v[2 * p + 1]);
-        const float2 hf = __half22float2(h);
-        const __half2 l = __floats2half2_rn(v[2 * p] - hf.x, v[2 * p + 1] - hf.y);
-        hw[p] = *reinterpret_cast<const uint32_t*>(&h);
-        lw[p] = *reinterpret_cast<const uint32_t*>(&l);
-    }
-    *reinterpret_cast<uint4*>(hi_dst) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-    *reinterpret_cast<uint4*>(lo_dst) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
-}
-
-__global__ void __launch_bounds__(TCD_THREADS, 1)
-mfcc_tc_stream_kernel(const int16_t* __restrict__ pcm, const int* __restrict__ ids, int n, int chunk, int hop,
-                      TcdTables tab, StreamState st) {
-    extern __shared__ __align__(128) unsigned char tcd_raw[];
-    TcdSmem& sm = *reinterpret_cast<TcdSmem*>(tcd_raw);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    constexpr int used = 512;
-
-    // ---- one-time setup: twiddle operands and small tables to shared memory, barriers, TMEM (all 512 columns)
-    {
-        uint4* dst = reinterpret_cast<uint4*>(&sm.b_hi[0][0][0][0]);
-        for (int e = tid; e < 2 * TCD_BLOCKS * 8 * 64; e += TCD_THREADS) dst[e] = __ldg(tab.b + e);     // b_hi then b_lo, contiguous
-        for (int e = tid; e < 257; e += TCD_THREADS) sm.etab[e] = __ldg(tab.etab + e);
-        for (int e = tid; e < TCD_MAX_OUT * 24; e += TCD_THREADS) (&sm.dct[0][0])[e] = __ldg(tab.dct + e);
-    }
-    if (tid == 0) {
-        mbar_init(&sm.a_full, TCD_PROD_WARPS * 32); mbar_init(&sm.a_empty, 1);
-        mbar_init(&sm.d_full, 1); mbar_init(&sm.d_empty, TCD_EPI_WARPS * 32);
-        fence_mbar_init();
-    }
-    if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm.tmem_base)), "n"(512) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    fence_proxy_async();
-    tc5_fence_before();
-    __syncthreads();
-    tc5_fence_after();
-    const uint32_t tmem = sm.tmem_base;
-    const uint32_t idesc = tcd_idesc(64);
-
-    uint32_t n_ksteps = 0;            // K-steps handed over so far (producers, issuer): phase of a_full / a_empty
-    uint32_t n_tiles_done = 0;        // tiles so far (issuer, epilogue): phase of d_full / d_empty
-
-    const int n_groups = (n + TCD_GROUP - 1) / TCD_GROUP;
-    for (int grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
-        const int base = grp * TCD_GROUP;
-        // ---- bookkeeping: thread t < 128 <-> stream base + t; frame list by a block-wide exclusive scan
-        int cnt = 0;
-        if (tid < TCD_GROUP) {
-            const int i = base + tid;
-            int sid = -1;
-            long long n0 = 0, c0 = 0, ts0 = 0;
-            if (i < n) {
-                sid = ids ? ids[i] : i;
-                n0 = st.n_samples[sid];
-                c0 = frames_ready(n0, used, hop);
-                cnt = (int)(frames_ready(n0 + chunk, used, hop) - c0);
-                ts0 = c0 * hop < n0 ? c0 * hop : n0;
-            }
-            sm.st_id[tid] = sid; sm.st_n0[tid] = n0; sm.st_c0[tid] = c0; sm.st_ts0[tid] = ts0; sm.st_cnt[tid] = cnt;
-        }
-        int incl = cnt;
-        if (warp < 4) {
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += v; }
-            if (lane == 31) sm.warp_tot[warp] = incl;
-        }
-        __syncthreads();
-        if (tid < TCD_GROUP) {
-            int off = incl - cnt;
-            for (int w = 0; w < warp; ++w) off += sm.warp_tot[w];
-            for (int j = 0; j < cnt; ++j) { sm.fr_stream[off + j] = (short)tid; sm.fr_sub[off + j] = (short)j; }
-            if (tid == TCD_GROUP - 1) sm.n_frames = off + cnt;
-        }
-        __syncthreads();
-        const int n_frames = sm.n_frames;
-        const int n_tiles = (n_frames + 127) >> 7;
-
-        for (int tile = 0; tile < n_tiles; ++tile) {
-            if (warp >= TCD_EPI_WARPS && warp < TCD_EPI_WARPS + TCD_PROD_WARPS) {
-                // ================= producers: thread <-> (frame row, K-group parity)
-                const int pw = warp - TCD_EPI_WARPS, row = 32 * (pw & 3) + lane, gq = pw >> 2;
-                const int f = tile * 128 + row;
-                const bool active = f < n_frames;
-                const int16_t *p0 = pcm, *p1 = pcm;
-                int len0 = 0;
-                if (active) {
-                    const int t = sm.fr_stream[f];
-                    const long long a0 = (sm.st_c0[t] + sm.fr_sub[f]) * hop, n0 = sm.st_n0[t];
-                    const int16_t* chunk_p = pcm + (long long)(base + t) * chunk;
-                    if (a0 >= n0) { len0 = 0; p1 = chunk_p + (a0 - n0); }
-                    else {
-                        len0 = (int)min((long long)used, n0 - a0);
-                        p0 = st.tail + (long long)sm.st_id[t] * st.tail_cap + (a0 - sm.st_ts0[t]);
-                        p1 = chunk_p;
-                    }
-                }
-#pragma unroll 1
-                for (int ks = 0; ks < TCD_KSTEPS; ++ks, ++n_ksteps) {
-                    const int g = 2 * ks + gq;                     // K-group: n2 = 4 g .. 4 g + 3
-                    float y[TCD_BLOCKS][8];                        // per block: the 8 values of this K-group
-                    if (active) {
-                        uint2 raw[16];
-#pragma unroll
-                        for (int q = 0; q < 16; ++q) {
-                            const int i = 4 * g + 32 * q;
-                            const int16_t* src = i < len0 ? p0 + i : p1 + (i - len0);
-                            raw[q] = __ldg(reinterpret_cast<const uint2*>(src));
-                        }
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            float x[16], yr[9], yi[9];
-#pragma unroll
-                            for (int q = 0; q < 16; ++q) {
-                                const uint32_t w = ((j & 2) ? raw[q].y : raw[q].x) ^ 0x80008000u;
-                                float a, b;
-                                tcd_cvt2(w, a, b);
-                                x[q] = (j & 1) ? b : a;
-                            }
-                            rdft16_x2(x, yr, yi);
-                            y[0][j] = yr[0]; y[0][4 + j] = yr[8];
-#pragma unroll
-                            for (int r = 1; r < 8; ++r) { y[r][j] = yr[r]; y[r][4 + j] = yi[r]; }
-                        }
-                    }
-                    // the tensor core has finished reading the previous K-step's tiles
-                    mbar_wait(&sm.a_empty, (n_ksteps & 1) ^ 1);
-                    if (active) {
-#pragma unroll
-                        for (int b = 0; b < TCD_BLOCKS; ++b) tcd_put8(&sm.a_hi[b][gq][row][0], &sm.a_lo[b][gq][row][0], y[b]);
-                    }
-                    fence_proxy_async();
-                    mbar_arrive(&sm.a_full);
-                }
-            } else if (warp == TCD_EPI_WARPS + TCD_PROD_WARPS) {
-                // ================= MMA issuer (one lane)
-                if (lane == 0) {
-                    mbar_wait(&sm.d_empty, (n_tiles_done & 1) ^ 1);          // the epilogue has drained the previous tile
-                    tc5_fence_after();
-#pragma unroll 1
-                    for (int ks = 0; ks < TCD_KSTEPS; ++ks, ++n_ksteps) {
-                        mbar_wait(&sm.a_full, n_ksteps & 1);
-                        tc5_fence_after();
-#pragma unroll 1
-                        for (int b = 0; b < TCD_BLOCKS; ++b) {
-                            const uint64_t dah = tc5_desc(&sm.a_hi[b][0][0][0], 2048, 128), dal = tc5_desc(&sm.a_lo[b][0][0][0], 2048, 128);
-                            const uint64_t dbh = tc5_desc(&sm.b_hi[b][2 * ks][0][0], 1024, 128), dbl = tc5_desc(&sm.b_lo[b][2 * ks][0][0], 1024, 128);
-                            const uint32_t d = tmem + 64 * b;
-                            tcd_mma(d, dal, dbh, idesc, ks > 0);
-                            tcd_mma(d, dah, dbl, idesc, 1);
-                            tcd_mma(d, dah, dbh, idesc, 1);
-                        }
-                        tc5_commit(&sm.a_empty);                             // arrives when these MMAs have read the A tiles
-                    }
-                    tc5_commit(&sm.d_full);
-                } else {
-                    n_ksteps += TCD_KSTEPS;
-                }
-                __syncwarp();
-                ++n_tiles_done;
-            } else {
-                // ================= epilogue: thread <-> frame = TMEM lane
-                const int f = tile * 128 + tid;
-                const bool active = f < n_frames;
-                const uint32_t t_row = tmem + ((uint32_t)(warp * 32) << 16);
-                float* acc = &sm.acc[0][tid];
-                for (int j = 0; j < tab.n_filt + 2; ++j) acc[j * 128] = 0.f;
-                mbar_wait(&sm.d_full, n_tiles_done & 1);
-                tc5_fence_after();
-                float tot = 0.f, a_r = 0.f, a_f = 0.f, p256 = 0.f;
-                int s_cur = 0;
-#pragma unroll 1
-                for (int c = 0; c < 16; ++c) {
-                    float re[16], im[16];
-                    tc5_ld16(t_row + 32 * c, re);
-                    tc5_ld16(t_row + 32 * c + 16, im);
-#pragma unroll
-                    for (int m = 0; m < 16; ++m) {
-                        float p = re[m] * re[m];
-                        if (c == 0 && m == 0) p256 = im[0] * im[0];
-                        else p = fmaf(im[m], im[m], p);
-                        const float4 e = sm.etab[16 * c + m];
-                        const int s = __float_as_int(e.z);
-                        if (s != s_cur) {                                        // warp-uniform: the table is shared
-                            acc[(s_cur + 1) * 128] += a_r; acc[s_cur * 128] += a_f;
-                            s_cur = s; a_r = 0.f; a_f = 0.f;
-                        }
-                        tot += p;
-                        a_r = fmaf(e.x, p, a_r);
-                        a_f = fmaf(e.y, p, a_f);
-                    }
-                }
-                {   // bin 256 (carried in the Im X[0] slot)
-                    const float4 e = sm.etab[256];
-                    const int s = __float_as_int(e.z);
-                    if (s != s_cur) { acc[(s_cur + 1) * 128] += a_r; acc[s_cur * 128] += a_f; s_cur = s; a_r = 0.f; a_f = 0.f; }
-                    tot += p256;
-                    a_r = fmaf(e.x, p256, a_r);
-                    a_f = fmaf(e.y, p256, a_f);
-                    acc[(s_cur + 1) * 128] += a_r; acc[s_cur * 128] += a_f;
-                }
-                tc5_fence_before();
-                mbar_arrive(&sm.d_empty);                                        // TMEM may be overwritten by the next tile
-                ++n_tiles_done;
-                if (active) {
-                    const int t = sm.fr_stream[f];
-                    const long long k = sm.st_c0[t] + sm.fr_sub[f];
-                    float* row = st.ring + ((long long)sm.st_id[t] * st.ring_rows + (int)(k % st.ring_rows)) * st.row_stride;
-                    for (int j = 0; j < tab.n_filt; ++j) acc[(j + 1) * 128] = logf(fmaxf(acc[(j + 1) * 128], K1_EPS));
-                    for (int o = 0; o < tab.n_out; ++o) {
-                        float v0 = 0.f, v1 = 0.f;
-                        const float* d = sm.dct[o];
-                        int j = 0;
-                        for (; j + 1 < tab.n_filt; j += 2) { v0 = fmaf(d[j], acc[(j + 1) * 128], v0); v1 = fmaf(d[j + 1], acc[(j + 2) * 128], v1); }
-                        if (j < tab.n_filt) v0 = fmaf(d[j], acc[(j + 1) * 128], v0);
-                        row[o] = o == 0 ? logf(fmaxf(tot * tab.tot_scale, K1_EPS)) : v0 + v1;
-                    }
-                }
-            }
-        }
-        __syncthreads();              // every frame of the group is done: all reads of the old tails are complete
-        // ---- tails and sample counters (chunk >= 512 samples: nothing of the old tail survives)
-        if (tid < TCD_GROUP && sm.st_id[tid] >= 0) {
-            const long long n0 = sm.st_n0[tid], n1 = n0 + chunk;
-            const long long c1 = sm.st_c0[tid] + sm.st_cnt[tid];
-            const long long ts1 = c1 * hop < n1 ? c1 * hop : n1;
-            sm.st_ts0[tid] = ts1 - n0;                                           // offset of the new tail inside the chunk
-            sm.st_cnt[tid] = (int)(n1 - ts1) >> 3;                               // 16-byte vectors
-            st.n_samples[sm.st_id[tid]] = n1;
-        }
-        __syncthreads();
-        for (int e = tid; e < TCD_GROUP * 64; e += TCD_THREADS) {
-            const int t = e >> 6, vi = e & 63;
-            if (sm.st_id[t] >= 0 && vi < sm.st_cnt[t]) {
-                const int4 v = __ldg(reinterpret_cast<const int4*>(pcm + (long long)(base + t) * chunk + sm.st_ts0[t]) + vi);
-                reinterpret_cast<int4*>(st.tail + (long long)sm.st_id[t] * st.tail_cap)[vi] = v;
-            }
-        }
-        __syncthreads();
-    }
-    tc5_fence_before();
-    __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512) : "memory");
+// four floats -> fp16 hi and lo pieces, one 8-byte store each
+__device__ __forceinline__ void tcd_put4(__half* hi_dst, __half* lo_dst, float v0, float v1, float v2, float v3) {
+    const __half2 h0 = __floats2half2_rn(v0, v1), h1 = __floats2half2_rn(v2, v3);
+    const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+    const __half2 l0 = __floats2half2_rn(v0 - f0.x, v1 - f0.y), l1 = __floats2half2_rn(v2 - f1.x, v3 - f1.y);
+    *reinterpret_cast<uint2*>(hi_dst) = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+    *reinterpret_cast<uint2*>(lo_dst) = make_uint2(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));
 }
 
 }  // namespace pb

@@ -6,6 +6,8 @@ dense_b, plus optional activation / recurrent_activation strings, next to the re
 """
 import numpy as np
 
+MODEL_SUFFIXES = ('.npz', '.pb', '.net')      # own format, frozen GraphDef, Keras HDF5 (Listener.find_runner: network_runner.py:111-119)
+
 
 class GruModel:
     def __init__(self, kernel, recurrent, bias, dense_w, dense_b, activation='linear',

@@ -19,7 +19,7 @@ from os.path import splitext
 import numpy as np
 
 from .core import PreciseB200
-from .model_io import GruModel, load_weights
+from .model_io import GruModel, load_weights, MODEL_SUFFIXES
 from .params import ListenerParams, load_params
 
 
@@ -64,12 +64,15 @@ class TriggerDetector:
 
 
 def _resolve_model(model):
-    """model: GruModel | path to .npz.  Returns (GruModel, ListenerParams)."""
+    """model: GruModel | path to a weights file.  Returns (GruModel, ListenerParams).
+
+    Same suffix dispatch as Listener.find_runner (network_runner.py:111-119: '.net' Keras HDF5, '.pb' frozen
+    GraphDef) plus this package's own '.npz'; the readers live in model_io.load_weights."""
     if isinstance(model, GruModel):
         return model, None
     ext = splitext(model)[-1]
-    if ext not in ('.npz', '.pb'):
-        raise ValueError('File extension of ' + model + " must be: ['.npz', '.pb']")
+    if ext not in MODEL_SUFFIXES:
+        raise ValueError('File extension of ' + model + ' must be: ' + str(list(MODEL_SUFFIXES)))
     return load_weights(model), load_params(model)
 
 

@@ -14,7 +14,15 @@ def sigmoid(x: float) -> float:            # functions.py:94-96
     return 1 / (1 + exp(-x))
 
 
-def asigmoid(x: float) -> float:           # functions.py:99-101
+def asigmoid(x) -> float:                  # functions.py:99-101: -log(1 / x - 1)
+    """Listener.update passes the np.float32 scalar that Runner.run returns (network_runner.py:73-74, :153), so under
+    NumPy >= 2 promotion (the reference as it runs in this image) ``1 / x - 1`` is float32 arithmetic and only the
+    logarithm is double; a python float (or NumPy 1.16's legacy promotion) evaluates it in float64.  Spelled out here
+    so the oracle does not depend on the installed NumPy's promotion rules; tests/golden/decoder_golden.npz holds the
+    reference class's own outputs for both kinds of argument (dec32_*, dec_*)."""
+    if isinstance(x, np.float32):
+        with np.errstate(all='ignore'):
+            return -log(float(np.float32(1) / x - np.float32(1)))
     return -log(1 / x - 1)
 
 

@@ -88,6 +88,11 @@ def decoder_golden():
         out['cd_%d' % i] = np.asarray(d.cd, dtype=np.float64)
         out['meta_%d' % i] = np.array([d.min_out, d.max_out, d.out_range], dtype=np.int64)
         out['dec_%d' % i] = np.array([d.decode(float(r)) for r in raws32], dtype=np.float64)
+        # what Listener.update really passes: the np.float32 scalar Runner.run returns (network_runner.py:73-74, :153).
+        # Under this image's NumPy (>= 2) `1 / x - 1` in functions.asigmoid then stays float32; dec_* above is the
+        # float64 evaluation (python float in, which is also what NumPy 1.16 promotion gives for np.float32 in).
+        with np.errstate(all='ignore'):
+            out['dec32_%d' % i] = np.array([d.decode(r) for r in raws32], dtype=np.float64)
         if d.out_range:
             out['enc_%d' % i] = np.array([d.encode(t) for t in np.linspace(0.02, 0.98, 49)], dtype=np.float64)
     out['kat'] = np.array([ThresholdDecoder(((6, 4),), 0.2).decode(v) for v in (0.0, 1.0, 0.5, 0.9, 0.99, 0.999)])
@@ -119,8 +124,8 @@ def trigger_golden():
     np.savez_compressed(os.path.join(HERE, 'trigger_golden.npz'), **out)
 
 
-def listener_golden():
-    weights = ogru.GruWeights.random(13, 20, seed=0, scale=0.3)
+def listener_golden(scale=0.3, fname='listener_golden.npz'):
+    weights = ogru.GruWeights.random(13, 20, seed=0, scale=scale)
 
     class OracleRunner(Runner):
         def __init__(self, _):
@@ -147,7 +152,8 @@ def listener_golden():
         out['conf_%d' % i] = np.array(confs, dtype=np.float64)
         out['ring_%d' % i] = np.array(rings, dtype=np.float64)[::5]      # every 5th window, keeps it small
         out['carry_%d' % i] = np.int64(len(lis.window_audio))
-    np.savez_compressed(os.path.join(HERE, 'listener_golden.npz'), **out)
+    out['numpy_version'] = np.array(np.__version__)
+    np.savez_compressed(os.path.join(HERE, fname), **out)
 
 
 if __name__ == '__main__':
@@ -156,5 +162,7 @@ if __name__ == '__main__':
     decoder_golden()
     trigger_golden()
     listener_golden()
+    # well-conditioned weights (outputs away from saturation): the set the tight end-to-end assertions use
+    listener_golden(scale=0.1, fname='listener_golden_s01.npz')
     for f in sorted(os.listdir(HERE)):
         print(f, os.path.getsize(os.path.join(HERE, f)))

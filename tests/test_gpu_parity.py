@@ -319,24 +319,43 @@ def test_predict_edge_sizes(core):
 
 
 # ------------------------------------------------------------------------------------------ K3
-def test_decode_vs_reference_golden(core, golden_dir):
+def _neighbour_values(d, r):
+    """Confidences of the LUT bins next to the one the oracle picks for raw output r."""
+    i = d.index(r)
+    out = []
+    for j in (i - 1, i + 1):
+        if 0 <= j < len(d.cd):
+            cp = d.cd[j]
+            out.append(0.5 * cp / d.center if cp < d.center else 0.5 + 0.5 * (cp - d.center) / (1 - d.center))
+    return out
+
+
+@pytest.mark.parametrize('case', range(5))
+@pytest.mark.parametrize('legacy', [False, True], ids=['asigmoid_f32', 'asigmoid_f64'])
+def test_decode_vs_reference_golden(golden_dir, case, legacy):
+    """pb_decode against values produced by the reference's ThresholdDecoder itself for all DECODER_CASES
+    (multi-Gaussian, centre 0.5 / 0.7, std 0 -> out_range 0).  Default mode: the decoder was fed np.float32 scalars
+    (what Runner.run returns; `1 / x - 1` in float32 under this image's NumPy) -> dec32_*; decode_legacy_f64: python
+    floats (= NumPy 1.16 promotion) -> dec_*."""
     import os
+    import sys
+    sys.path.insert(0, golden_dir)
+    from cases import DECODER_CASES
+    m = _mod()
+    cfg, center = DECODER_CASES[case]
+    pr = m.ListenerParams(threshold_config=cfg, threshold_center=center)
+    core = m.PreciseB200(pr, decode_legacy_f64=legacy)
     g = np.load(os.path.join(golden_dir, 'decoder_golden.npz'))
     raws = g['raws']
     got = core.decode(cuda(raws)).cpu().numpy()
-    want = g['dec_0']                                     # produced by the reference class itself
-    d = OracleDecoder(((6, 4),), 0.2)
+    want = g['dec_%d' % case] if legacy else g['dec32_%d' % case]
+    d = OracleDecoder(cfg, center)
     exact = got == want
-    print('decode: %d / %d bit-identical' % (exact.sum(), len(raws)))
-    assert exact.mean() > 0.998
+    print('decode case %d legacy=%s: %d / %d bit-identical' % (case, legacy, exact.sum(), len(raws)))
+    assert exact.mean() > 0.998                           # libm log vs CUDA log: an ulp can move a value across a bin edge
     for r, a in zip(raws[~exact], got[~exact]):           # the rest: neighbouring LUT bin
-        i = d.index(float(r))
-        cands = []
-        for j in (i - 1, i + 1):
-            if 0 <= j < len(d.cd):
-                cp = d.cd[j]
-                cands.append(0.5 * cp / d.center if cp < d.center else 0.5 + 0.5 * (cp - d.center) / (1 - d.center))
-        assert any(a == c for c in cands)
+        assert any(a == c for c in _neighbour_values(d, float(r) if legacy else r))
+    core.close()
 
 
 # ------------------------------------------------------------------------------------------ stateful
@@ -631,7 +650,7 @@ def test_runner_plugin_predict_shape():
 
 @pytest.mark.skipif(os.environ.get('PB_TEST_TC_K1') != '1',
                     reason='opt-in MFCC kernels (tensor-core DFT, lean set-up): not yet validated on hardware; set PB_TEST_TC_K1=1')
-@pytest.mark.parametrize('k1_mode', [2, 1], ids=['lean_setup', 'tensor_core'])
+@pytest.mark.parametrize('k1_mode', [2, 4], ids=['lean_setup', 'tensor_core'])
 def test_experimental_mfcc_tick(k1_mode):
     """pb_debug_k1_mode: 1 = windows produced by the tcgen05 DFT kernel, 2 = fast kernel with the 32-bit per-pass set-up,
     against the default kernels (mode 2 must be bit-identical: same arithmetic, different address computation)."""
@@ -647,7 +666,9 @@ def test_experimental_mfcc_tick(k1_mode):
         c = cuda(pcm[:, k * chunk:(k + 1) * chunk])
         a, b = ref.update(c), tc.update(c)
         wa, wb = ref.core.read_window(S).cpu().numpy(), tc.core.read_window(S).cpu().numpy()
-        assert np.max(np.abs(wa - wb)) < 2e-4, k
+        per = np.abs(wa - wb).reshape(S, -1).max(1)
+        print('tick', k, 'worst streams', np.argsort(per)[-4:], per[np.argsort(per)[-4:]])
+        assert np.max(per) < 2e-4, k
         if k1_mode == 2:
             assert np.array_equal(wa, wb), k
         assert np.max(np.abs(a['raw'].cpu().numpy() - b['raw'].cpu().numpy())) < 1e-4, k

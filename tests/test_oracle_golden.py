@@ -40,6 +40,9 @@ def test_decoder_bit_equal(golden_dir, i):
     assert np.array_equal(d.cd, g['cd_%d' % i])
     got = np.array([d.decode(float(r)) for r in g['raws']])
     assert np.array_equal(got, g['dec_%d' % i])
+    with np.errstate(all='ignore'):
+        got32 = np.array([d.decode(r) for r in g['raws']])          # np.float32 scalars in, like Listener.update
+    assert np.array_equal(got32, g['dec32_%d' % i])
     if d.out_range:
         enc = np.array([d.encode(t) for t in np.linspace(0.02, 0.98, 49)])
         assert np.array_equal(enc, g['enc_%d' % i])
