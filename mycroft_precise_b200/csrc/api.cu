@@ -362,7 +362,7 @@ PB_API int pb_create(const pb_config* cfg, pb_handle** out) {
     h->h_wrise = wrise; h->h_wfall = wfall; h->h_grid = grid;
     h->tcd_ok = h->fast_ok && c.vectorizer == PB_VEC_MFCCS && c.n_filt <= TCD_MAX_FILT && h->n_out <= TCD_MAX_OUT &&
                 c.chunk_samples % 8 == 0 && c.chunk_samples >= 512 && (c.chunk_samples + c.hop_samples - 1) / c.hop_samples <= TC2_MAX_NEW;
-    h->tc2_ok = h->tcd_ok && c.hop_samples <= 16384 && h->ring_rows <= 255 && h->n_out >= 1 &&
+    h->tc2_ok = h->tcd_ok && c.hop_samples >= 512 && c.hop_samples <= 16384 && h->ring_rows <= 255 && h->n_out >= 1 &&
                 (c.chunk_samples + c.hop_samples - 1) / c.hop_samples <= TC2_MAX_NEW &&
                 tc2_geo_matches<Tc2Geo20>(c.n_filt, h->n_bins, grid, wrise, wfall);
     h->k1_fast_smem = K1F_WARPS * sizeof(K1FWarp) + (size_t)h->npl * 128 * sizeof(float4) +

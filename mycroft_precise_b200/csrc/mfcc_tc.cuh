@@ -91,10 +91,11 @@ __host__ __device__ __forceinline__ void rdft16_x2(const float (&x)[16], float (
 // ---------------------------------------------------------------------------------------------------------------------
 // Host tables.
 //   B operand of block b, piece hi / lo: fp16 [kgroup 8][n 64][8]  (K-major canonical, no swizzle: element (n, k) at
-//   ((k / 8) * 64 + n) * 8 + k % 8).  K-group g holds the inputs n2 = 4 g .. 4 g + 3 (the four samples one producer lane
-//   loads per 32-sample row), first and second input half of the block; element order inside the 16-byte group:
-//   tcd_kslot(j, second, g) -- two 8-byte halves, one per sample pair (j >> 1), swapped for odd g so that the two lanes
-//   that share a frame row store to different bank halves.
+//   ((k / 8) * 64 + n) * 8 + k % 8).  K-group g holds the inputs n2 = 4 g .. 4 g + 3, first and second input half of the
+//   block.  K-step ks of the MMAs uses the groups ks and 4 + ks: the two producer lanes of a frame row each own one 32-byte
+//   sector of every sample row (groups 0-3 and 4-7).  Element order inside the 16-byte group: tcd_kslot(j, second, g) --
+//   two 8-byte halves, one per sample pair (j >> 1), swapped for the groups of the second lane (g >= 4) so that the two
+//   lanes store to different bank halves.
 //   Output column c of block b (accumulator column 64 b + c):
 //     block 0: [Re X[16m] | Im X[16m] (m = 0 carries X[256]) | Re X[16m+8] | Im X[16m+8]],   m = c % 16
 //     block r: [Re X[16m+r] | Im X[16m+r] | Re X[16m+16-r] | Im X[16m+16-r]]
@@ -105,7 +106,7 @@ struct TcdHostTables {
 };
 
 // position (0..7) inside K-group g of input n2 = 4 g + j, first (second = 0) or second (second = 1) input half of the block
-__host__ __device__ constexpr int tcd_kslot(int j, int second, int g) { return 4 * ((j >> 1) ^ (g & 1)) + 2 * second + (j & 1); }
+__host__ __device__ constexpr int tcd_kslot(int j, int second, int g) { return 4 * ((j >> 1) ^ (g >> 2)) + 2 * second + (j & 1); }
 
 // bin held by element m of 32-column chunk c = 2 b + h (16 re columns then 16 im columns)
 __host__ __device__ constexpr int tcd_chunk_bin_c(int c, int m) {
@@ -125,7 +126,7 @@ static inline void tcd_build_b(std::vector<__half>& b_hi, std::vector<__half>& b
         for (int k = 0; k < 64; ++k)
             for (int n = 0; n < 64; ++n) {
                 const int g = k >> 3, e = k & 7;                                             // which input this row multiplies:
-                const int second = (e >> 1) & 1, n2 = 4 * g + 2 * ((e >> 2) ^ (g & 1)) + (e & 1);   // inverse of tcd_kslot
+                const int second = (e >> 1) & 1, n2 = 4 * g + 2 * ((e >> 2) ^ (g >> 2)) + (e & 1);  // inverse of tcd_kslot
                 const int quarter = n >> 4, m = n & 15;
                 double v = 0.0;
                 if (b == 0) {

@@ -13,9 +13,10 @@
 // What changed against the first version (mfcc_tc_stream_kernel, 438 us per 131 072-stream tick on the B200):
 //   * super-groups of up to 1024 streams per CTA share one frame list, so tiles of 128 frames are full (93 % instead of
 //     64 % with 128-stream groups) and there is one bookkeeping pass per CTA instead of seven;
-//   * producer lanes are 16 frames x 2 K-groups: every LDG.64 instruction covers 16 bytes per frame (the old mapping,
-//     32 frames x 8 bytes, fetched every 32-byte sector four times); the loads of the next K-step are in flight while the
-//     current one is transformed;
+//   * a producer lane owns one 32-byte sector of every 64-byte sample row of its frame (the K-groups 4 gq + ks): 16-byte
+//     loads, each serving two K-steps (the old mapping, 32 frames x 8 bytes per instruction, fetched every sector four
+//     times and visited every L1 line sixteen times); the next half's loads are issued as soon as the registers are free;
+//   * the producer warp that delivers last issues the K-step's MMAs (descriptor arithmetic is one add per operand);
 //   * the mel stage is compiled for the geometry: each of the 512 accumulator columns knows its bin, segment and edge
 //     weights at compile time, so the 257 bins cost five FP32 instructions each into register accumulators (the old
 //     epilogue did a table look-up and a dependent shared-memory read-modify-write per bin);
@@ -108,7 +109,9 @@ struct Tc2Smem {
     unsigned short fr[TC2_MAX_FRAMES];           // frame list: (local stream << 2) | sub-frame
     int lane_tot[32];
     int n_frames;
-    unsigned long long a_full, a_empty, d_full, d_empty, b_ready;
+    unsigned int arrivals;                       // producer warps that have delivered their part of a K-step (monotonic)
+    int b_loaded;
+    unsigned long long a_empty, d_full, d_empty, b_ready;
     uint32_t tmem_base;
 };
 
@@ -118,6 +121,18 @@ struct Tc2Tables {               // device pointers
     int n_out;
     float pscale;                // (re^2 + im^2) of the scaled accumulators -> power / n_fft
 };
+
+// mbarrier wait for a role that is expected to wait long (the epilogue between tiles): back off between polls so the
+// spinning threads do not take issue slots from the producers
+__device__ __forceinline__ void tc2_mbar_wait_idle(unsigned long long* bar, uint32_t parity) {
+    uint32_t ok;
+    for (;;) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (ok) break;
+        __nanosleep(128);
+    }
+}
 
 __device__ __forceinline__ void tc2_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -151,7 +166,8 @@ mfcc_tc2_stream_kernel(const int16_t* __restrict__ pcm, const int* __restrict__ 
 
     // ---- one-time setup: barriers, TMEM (all 512 columns), twiddle operands by one bulk copy pair, DCT table
     if (tid == 0) {
-        mbar_init(&sm.a_full, TC2_PROD_WARPS * 32); mbar_init(&sm.a_empty, 1);
+        mbar_init(&sm.a_empty, 1);
+        sm.arrivals = 0; sm.b_loaded = 0;
         mbar_init(&sm.d_full, 1); mbar_init(&sm.d_empty, TC2_EPI_WARPS * 32);
         mbar_init(&sm.b_ready, 1);
         fence_mbar_init();
@@ -175,7 +191,6 @@ mfcc_tc2_stream_kernel(const int16_t* __restrict__ pcm, const int* __restrict__ 
 
     uint32_t n_ksteps = 0;            // K-steps handed over so far (producers, issuer): phase of a_full / a_empty
     uint32_t n_tiles_done = 0;        // tiles so far (issuer, epilogue): phase of d_full / d_empty
-    bool b_waited = false;
 
     const int n_groups = (n + sg - 1) / sg;
     for (int grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
@@ -222,10 +237,10 @@ mfcc_tc2_stream_kernel(const int16_t* __restrict__ pcm, const int* __restrict__ 
             // Per frame: samples [0, len0) come from the stream's tail, the rest from the chunk.  P0 / P1 are byte pointers such
             // that sample i sits at P0 + 2 i (i < len0) or P1 + 2 i (i >= len0); len0 is a multiple of 8, so a 4-sample group
             // never straddles.
-            struct Frame { const char* P0; const char* P1; int len0; float x0f; bool active; };
+            struct Frame { const char* P0; const char* P1; int len0; int x0; bool active; };
             auto setup = [&](int tile) {
                 Frame fr;
-                fr.P0 = fr.P1 = reinterpret_cast<const char*>(pcm); fr.len0 = 0; fr.x0f = 0.f;
+                fr.P0 = fr.P1 = reinterpret_cast<const char*>(pcm); fr.len0 = 0; fr.x0 = 0;
                 const int f = tile * 128 + row;
                 fr.active = tile < n_tiles && f < n_frames;
                 if (fr.active) {
@@ -238,97 +253,111 @@ mfcc_tc2_stream_kernel(const int16_t* __restrict__ pcm, const int* __restrict__ 
                         fr.P0 = reinterpret_cast<const char*>(st.tail + (long long)sm.st_sid[s] * st.tail_cap + j * hop);
                         fr.P1 = reinterpret_cast<const char*>(chunk_p - fr.len0);
                     }
-                    fr.x0f = (float)__ldg(reinterpret_cast<const int16_t*>(fr.len0 > 0 ? fr.P0 : fr.P1));
+                    fr.x0 = __ldg(reinterpret_cast<const int16_t*>(fr.len0 > 0 ? fr.P0 : fr.P1));   // converted by its first use, a K-step later
                 }
                 return fr;
             };
-            // the 16 loads of K-step ks of a frame: this lane's 4 samples n2 = 4 g .. 4 g + 3 of every 32-sample row q
-            auto load = [&](const Frame& fr, int ks, uint2 (&raw)[16]) {
+            // This lane owns one 32-byte sector of every 64-byte row q of its frame: samples 16 gq + 32 q .. + 15, i.e. the
+            // K-groups g = 4 gq + ks of the four K-steps.  One 16-byte load per row serves two K-steps (half h = ks >> 1).
+            auto load = [&](const Frame& fr, int h, uint4 (&raw)[16]) {
                 if (!fr.active) return;
-                const int g = 2 * ks + gq;
-                const int qs = (fr.len0 - 4 * g + 31) >> 5;            // rows q < qs come from the tail
-                const char* a0 = fr.P0 + 8 * g;
-                const char* a1 = fr.P1 + 8 * g;
+                const int i0 = 16 * gq + 8 * h;                        // first sample of the half in row 0
+                const int qs = (fr.len0 - i0 + 31) >> 5;               // rows q < qs come from the tail
+                const char* a0 = fr.P0 + 2 * i0;
+                const char* a1 = fr.P1 + 2 * i0;
 #pragma unroll
-                for (int q = 0; q < 16; ++q)
-                    raw[q] = __ldg(reinterpret_cast<const uint2*>((q < qs ? a0 : a1) + 64 * q));
+                for (int q = 0; q < 16; ++q) {
+                    if (q < qs) raw[q] = __ldg(reinterpret_cast<const uint4*>(a0 + 64 * q));
+                    else raw[q] = __ldg(reinterpret_cast<const uint4*>(a1 + 64 * q));
+                }
             };
-            Frame cur = setup(0);
-            uint2 raw[16];
+            Frame cur = setup(0), nxt = cur;
+            uint4 raw[16];
             load(cur, 0, raw);
             for (int tile = 0; tile < n_tiles; ++tile) {
-                if (cur.active && gq == 0) sm.x0[tile & 1][row] = cur.x0f;
                 const bool active = cur.active;
-                const float x0f = cur.x0f;
-                Frame nxt = cur;
+                const float x0f = (float)cur.x0;
+                if (active && gq == 0) sm.x0[tile & 1][row] = x0f;
 #pragma unroll 1
-                for (int ks = 0; ks < TCD_KSTEPS; ++ks, ++n_ksteps) {
-                    // software pipeline: the loads of the next K-step (of the next tile after the last one) are in flight
-                    // while this one is transformed
-                    uint2 raw_n[16];
-                    if (ks == TCD_KSTEPS - 1) { nxt = setup(tile + 1); load(nxt, 0, raw_n); }
-                    else load(cur, ks + 1, raw_n);
-                    // two sample pairs (j = 0, 1 from the low words, j = 2, 3 from the high words): two 16-point real DFTs each,
-                    // then one 8-byte store per block and piece into this lane's K-group (half (jp ^ gq), see tcd_kslot)
+                for (int h = 0; h < 2; ++h) {
+                    // the next tile's frame is looked up well before its first load
+                    if (h == 1) nxt = setup(tile + 1);
 #pragma unroll
-                    for (int jp = 0; jp < 2; ++jp) {
-                        float yv[TCD_BLOCKS][4];
-                        if (active) {
-                            float xa[16], xb[16], yr[9], yi[9];
+                    for (int sub = 0; sub < 2; ++sub, ++n_ksteps) {
+                        const int ks = 2 * h + sub;
+                        // two sample pairs (j = 0, 1 and j = 2, 3 of the K-group's four samples): two 16-point real DFTs each, then
+                        // one 8-byte store per block and piece into this lane's K-group (half (jp ^ gq), see tcd_kslot)
 #pragma unroll
-                            for (int q = 0; q < 16; ++q) tcd_cvt2((jp ? raw[q].y : raw[q].x) ^ 0x80008000u, xa[q], xb[q]);
-                            rdft16_x2(xa, yr, yi);
-                            yv[0][0] = yr[0] - TCD_X0_Y * x0f; yv[0][2] = yr[8];  // Y_0 of (x - x[0]): exact
+                        for (int jp = 0; jp < 2; ++jp) {
+                            float yv[TCD_BLOCKS][4];
 #pragma unroll
-                            for (int r = 1; r < 8; ++r) { yv[r][0] = yr[r]; yv[r][2] = yi[r]; }
-                            rdft16_x2(xb, yr, yi);
-                            yv[0][1] = yr[0] - TCD_X0_Y * x0f; yv[0][3] = yr[8];
+                            for (int e = 0; e < 2; ++e) {             // the pair's two samples: low / high half of the word
+                                float x[16], yr[9], yi[9];
+                                if (active) {
 #pragma unroll
-                            for (int r = 1; r < 8; ++r) { yv[r][1] = yr[r]; yv[r][3] = yi[r]; }
+                                    for (int q = 0; q < 16; ++q) {
+                                        const uint32_t w = (sub == 0 ? (jp == 0 ? raw[q].x : raw[q].y) : (jp == 0 ? raw[q].z : raw[q].w)) ^ 0x80008000u;
+                                        float lo, hi;
+                                        tcd_cvt2(w, lo, hi);
+                                        x[q] = e ? hi : lo;
+                                    }
+                                }
+                                // software pipeline: the registers are free once the last sample of this half is converted; the loads
+                                // of the next half (of the next tile after the second one) fly while it is transformed and stored
+                                if (sub == 1 && jp == 1 && e == 1) {
+                                    if (h == 0) load(cur, 1, raw);
+                                    else load(nxt, 0, raw);
+                                }
+                                if (active) {
+                                    rdft16_x2(x, yr, yi);
+                                    yv[0][e] = yr[0] - TCD_X0_Y * x0f; yv[0][2 + e] = yr[8];        // Y_0 of (x - x[0]): exact
+#pragma unroll
+                                    for (int r = 1; r < 8; ++r) { yv[r][e] = yr[r]; yv[r][2 + e] = yi[r]; }
+                                }
+                            }
+                            // the tensor core has finished reading the previous K-step's tiles
+                            if (jp == 0) mbar_wait(&sm.a_empty, (n_ksteps & 1) ^ 1);
+                            if (active) {
+#pragma unroll
+                                for (int b = 0; b < TCD_BLOCKS; ++b)
+                                    tcd_put4(&sm.a_hi[b][gq][row][4 * (jp ^ gq)], &sm.a_lo[b][gq][row][4 * (jp ^ gq)], yv[b][0], yv[b][1], yv[b][2], yv[b][3]);
+                            }
                         }
-                        // the tensor core has finished reading the previous K-step's tiles
-                        if (jp == 0) mbar_wait(&sm.a_empty, (n_ksteps & 1) ^ 1);
-                        if (active) {
-#pragma unroll
-                            for (int b = 0; b < TCD_BLOCKS; ++b)
-                                tcd_put4(&sm.a_hi[b][gq][row][4 * (jp ^ gq)], &sm.a_lo[b][gq][row][4 * (jp ^ gq)], yv[b][0], yv[b][1], yv[b][2], yv[b][3]);
-                        }
-                    }
-#pragma unroll
-                    for (int q = 0; q < 16; ++q) raw[q] = raw_n[q];
-                    fence_proxy_async();
-                    mbar_arrive(&sm.a_full);
-                    if (pw == 0) {
-                        // ---- MMA issue: one lane of this warp, once every producer has delivered the K-step
+                        // ---- hand-over: the warp that arrives last issues the K-step's MMAs (no thread waits for the others)
+                        fence_proxy_async();
+                        __syncwarp();
                         if (lane == 0) {
-                            if (!b_waited) { mbar_wait(&sm.b_ready, 0); b_waited = true; }
-                            if (ks == 0) {
-                                mbar_wait(&sm.d_empty, (n_tiles_done & 1) ^ 1);      // the epilogue has drained the previous tile
+                            uint32_t prev;
+                            asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], 1;" : "=r"(prev) : "r"(smem_u32(&sm.arrivals)) : "memory");
+                            if (prev == TC2_PROD_WARPS * (n_ksteps + 1) - 1) {
+                                if (!sm.b_loaded) { mbar_wait(&sm.b_ready, 0); sm.b_loaded = 1; }
+                                if (ks == 0) mbar_wait(&sm.d_empty, (n_tiles_done & 1) ^ 1);     // the epilogue has drained the previous tile
                                 tc5_fence_after();
+                                // descriptors of the first operand tiles; every other tile is a constant number of 16-byte units further on
+                                const uint64_t dA_hi = tc5_desc(&sm.a_hi[0][0][0][0], 2048, 128), dA_lo = tc5_desc(&sm.a_lo[0][0][0][0], 2048, 128);
+                                const uint64_t dbh0 = tc5_desc(&sm.b_hi[0][ks][0][0], 4096, 128), dbl0 = tc5_desc(&sm.b_lo[0][ks][0][0], 4096, 128);   // K-groups ks and 4 + ks
+#pragma unroll
+                                for (int b = 0; b < TCD_BLOCKS; ++b) {
+                                    const uint64_t dah = dA_hi + b * 256, dal = dA_lo + b * 256;       // a block of A: 2 x 128 x 16 B
+                                    const uint64_t dbh = dbh0 + b * 512, dbl = dbl0 + b * 512;         // a block of B: 8 x 64 x 16 B
+                                    const uint32_t d = tmem + 64 * b;
+                                    tcd_mma(d, dal, dbh, idesc, ks > 0);
+                                    tcd_mma(d, dah, dbl, idesc, 1);
+                                    tcd_mma(d, dah, dbh, idesc, 1);
+                                }
+                                tc5_commit(&sm.a_empty);                                 // arrives when these MMAs have read the A tiles
+                                if (ks == TCD_KSTEPS - 1) tc5_commit(&sm.d_full);
                             }
-                            mbar_wait(&sm.a_full, n_ksteps & 1);
-                            tc5_fence_after();
-#pragma unroll 1
-                            for (int b = 0; b < TCD_BLOCKS; ++b) {
-                                const uint64_t dah = tc5_desc(&sm.a_hi[b][0][0][0], 2048, 128), dal = tc5_desc(&sm.a_lo[b][0][0][0], 2048, 128);
-                                const uint64_t dbh = tc5_desc(&sm.b_hi[b][2 * ks][0][0], 1024, 128), dbl = tc5_desc(&sm.b_lo[b][2 * ks][0][0], 1024, 128);
-                                const uint32_t d = tmem + 64 * b;
-                                tcd_mma(d, dal, dbh, idesc, ks > 0);
-                                tcd_mma(d, dah, dbl, idesc, 1);
-                                tcd_mma(d, dah, dbh, idesc, 1);
-                            }
-                            tc5_commit(&sm.a_empty);                                 // arrives when these MMAs have read the A tiles
-                            if (ks == TCD_KSTEPS - 1) tc5_commit(&sm.d_full);
                         }
                         __syncwarp();
                     }
                 }
                 ++n_tiles_done;
                 cur = nxt;
-                // ---- new tails (chunk >= 512: they lie inside the chunk).  Every producer has consumed its loads of this tile,
-                // so the old tails of streams whose LAST frame sits in this tile are dead; warp pw copies those among its rows,
-                // four streams' loads in flight per batch.
-                asm volatile("bar.sync 1, %0;" ::"n"(TC2_PROD_WARPS * 32) : "memory");
+                // ---- new tails (chunk >= 512: they lie inside the chunk).  Only a stream's FIRST new frame can reach into the old
+                // tail (hop >= 512), so the warp that owns that frame's row is the tail's only reader; it has consumed those
+                // loads by now and replaces the tail itself, four streams' loads in flight per batch -- no block-wide barrier.
+                __syncwarp();
 #pragma unroll 1
                 for (int batch = 0; batch < 4; ++batch) {
                     int4 v[4][2];
@@ -341,7 +370,7 @@ mfcc_tc2_stream_kernel(const int16_t* __restrict__ pcm, const int* __restrict__ 
                         dst[u] = nullptr;
                         if (fi < n_frames) {
                             const int e = sm.fr[fi], s = e >> 2, cnt = sm.st_cnt[s];
-                            if ((e & 3) == cnt - 1) {
+                            if ((e & 3) == 0) {
                                 const int off = min((int)sm.st_d[s] + cnt * hop, chunk);          // new tail = chunk[off, chunk)
                                 nv[u] = (chunk - off) >> 3;
                                 const int4* src = reinterpret_cast<const int4*>(pcm + (long long)(base + s) * chunk + off);
@@ -368,7 +397,7 @@ mfcc_tc2_stream_kernel(const int16_t* __restrict__ pcm, const int* __restrict__ 
 #pragma unroll
                 for (int j = 0; j <= G::n_filt; ++j) { rise[j] = 0.f; fall[j] = 0.f; }
                 float tot = 0.f;
-                mbar_wait(&sm.d_full, n_tiles_done & 1);
+                tc2_mbar_wait_idle(&sm.d_full, n_tiles_done & 1);
                 tc5_fence_after();
                 const float x0f = sm.x0[tile & 1][tid];
                 uint32_t buf[2][32];
