@@ -75,7 +75,7 @@ struct pb_handle {
     bool tcd_ok = false;             // geometry the tensor-core DFT tables cover (CPU model + kernel)
     bool tc2_ok = false;             // ... and by mfcc_tc2_stream_kernel<Tc2Geo20> (run-time mel tables equal its compile-time ones)
     std::vector<float> h_wrise, h_wfall; std::vector<int> h_grid;      // host copies for the lazily built tcd tables
-    uint4* d_tcd_b = nullptr; float4* d_tcd_etab = nullptr; float* d_tcd_dct = nullptr;
+    uint4* d_tcd_b = nullptr; float* d_tcd_tw = nullptr; float* d_tcd_dct = nullptr;
     float tcd_tot_scale = 0.f;
     bool fast_ok = false;            // aligned geometry: warp-autonomous kernels (mfcc_fast.cuh)
     int npl = 0, maxc = 0, nol = 0;
@@ -254,7 +254,7 @@ PB_API void pb_destroy(pb_handle* h) {
     if (!h) return;
     cudaSetDevice(h->cfg.device);
     cudaFree(h->d_wrise); cudaFree(h->d_wfall); cudaFree(h->d_dct); cudaFree(h->d_grid);
-    cudaFree(h->d_tcd_b); cudaFree(h->d_tcd_etab); cudaFree(h->d_tcd_dct);
+    cudaFree(h->d_tcd_b); cudaFree(h->d_tcd_tw); cudaFree(h->d_tcd_dct);
     cudaFree(h->d_tw_stage); cudaFree(h->d_tw_post); cudaFree(h->d_tw_any); cudaFree(h->d_cd); cudaFree(h->d_ptab); cudaFree(h->d_ctab); cudaFree(h->d_dct_t);
     cudaFree(h->st.n_samples); cudaFree(h->st.tail); cudaFree(h->st.ring); cudaFree(h->st.trig);
     cudaFree(h->d_wcat); cudaFree(h->d_bias); cudaFree(h->d_wd); cudaFree(h->d_count);
@@ -684,9 +684,9 @@ PB_API int pb_debug_tc_mfcc_frame(const pb_config* cfg, const int16_t* x512, flo
         std::vector<float> dct;
         float tot_scale = 0.f;
         tcd_host_tables(h, etab, dct, &tot_scale);
-        float d[512], acc[TCD_MAX_FILT + 2];
+        float d[TCD_BLOCKS][64];
         tcd_host_accumulators(x512, d);
-        tcd_host_epilogue(d, etab.data(), dct.data(), cfg->n_filt, h->n_out, tot_scale, acc, out);
+        tcd_host_epilogue(d, etab.data(), dct.data(), cfg->n_filt, h->n_out, tot_scale, out);
     }
     delete h;
     return rc;
@@ -904,11 +904,12 @@ static int ensure_tcd_tables(pb_handle* h) {
     std::vector<__half> both(bh);
     both.insert(both.end(), bl.begin(), bl.end());
     std::vector<float4> etab;
-    std::vector<float> dct;
+    std::vector<float> dct, tw;
     tcd_host_tables(h, etab, dct, &h->tcd_tot_scale);
+    tcd_build_tw(tw);
     CK(cudaMalloc((void**)&h->d_tcd_b, both.size() * sizeof(__half)));
     CK(cudaMemcpy(h->d_tcd_b, both.data(), both.size() * sizeof(__half), cudaMemcpyHostToDevice));
-    CK(upload(&h->d_tcd_etab, etab));
+    CK(upload(&h->d_tcd_tw, tw));
     CK(upload(&h->d_tcd_dct, dct));
     CK(ensure_dyn_smem(mfcc_tc2_stream_kernel<Tc2Geo20>, sizeof(Tc2Smem) + 128));
     return PB_OK;
@@ -925,7 +926,7 @@ static int launch_stream_mfcc(pb_handle* h, const int16_t* d_pcm, const int32_t*
         int rc = ensure_tcd_tables(h);
         if (rc != PB_OK) return rc;
         Tc2Tables t;
-        t.b = h->d_tcd_b; t.dct = h->d_tcd_dct; t.n_out = h->n_out; t.pscale = h->tcd_tot_scale;
+        t.b = h->d_tcd_b; t.tw = h->d_tcd_tw; t.dct = h->d_tcd_dct; t.n_out = h->n_out; t.pscale = h->tcd_tot_scale;
         // super-groups: one per SM where the batch allows it, a multiple of 32 streams, at most TC2_SG_MAX
         int sg = (int)((n + h->sm_count - 1) / h->sm_count);
         sg = std::min(TC2_SG_MAX, std::max(128, (sg + 31) & ~31));

@@ -5,39 +5,62 @@
 // (Listener.update_vectors, precise/network_runner.py:125-146).
 //
 // Decomposition.  n = n2 + 32 q (n2 < 32, q < 16), k = 16 m + r:
-//     Y_r[n2]     = sum_q x[n2 + 32 q] w16^(q r)                      16-point DFT of REAL data, CUDA cores (fp32)
-//     X[16 m + r] = sum_n2 Y_r[n2] w512^(n2 r) w32^(n2 m)             eight 64 x 64 real GEMM blocks, tensor cores
-// Block 0 takes [Y_0 | Y_8] (both real), block r = 1..7 takes [Re Y_r | Im Y_r] and also yields X[16 m + 16 - r] from
-// conj(Y_r) = Y_(16-r).  Operands are fp16 hi + lo pieces, three passes (a_lo b_hi + a_hi b_lo + a_hi b_hi, fp32
-// accumulate): 6e-7 of the peak bin against a float64 FFT, the accuracy of the fp32 FFT kernels.
-// The CPU model below (same butterfly, same operand tables read through the same layout arithmetic) is what
-// tests/test_tc_dft_host_model.py checks without a device.
+//     Y_r[n2]     = sum_q x[n2 + 32 q] w16^(q r)          r = 0..8     16-point DFT of REAL data        CUDA cores (fp32)
+//     Z_r[n2]     = Y_r[n2] w512^(n2 r)                                twiddle                          CUDA cores (fp32)
+//     X[16 m + r]      = sum_n2       Z_r[n2]  w32^(n2 m)                                               tensor cores
+//     X[16 m + 16 - r] = sum_n2 conj(Z_r[n2]) w32^(n2 (m + 1))         (conj(Y_r) = Y_(16-r))           tensor cores
+// Because the twiddle is applied before the GEMM, every block r = 0..8 multiplies the SAME 64 x 64 real matrix (rows: Re Z,
+// Im Z of the 32 inputs; columns: Re, Im of X[16 m + r], then Re, Im of X[16 m + 16 - r]); 16 KB of operands instead of one
+// 64 x 64 matrix per block (128 KB), which is what leaves shared memory for staging the PCM by bulk copies and lets four
+// blocks of a frame be stacked along M (a tile is 32 frames x 4 rows).  Block 0 (Z_0 = Y_0, real) yields X[16 m] and, in the
+// second half at m = 15, X[256]; block 8 yields X[16 m + 8].  Operands are fp16 hi + lo pieces, three passes
+// (a_lo b_hi + a_hi b_lo + a_hi b_hi, fp32 accumulate): ~1e-6 of the peak bin against a float64 FFT.
+// The CPU model below (same butterfly, same twiddles, same operand tables read through the same layout arithmetic) is
+// what tests/test_tc_dft_host_model.py checks without a device.
 #pragma once
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
+#include <string.h>
 
 #include <vector>
 
-#include "gru_tc5.cuh"        // tc5_desc, tc5_commit, tcgen05 fences, tc5_ld16
+#include "gru_tc5.cuh"        // tc5_desc, tc5_commit, tcgen05 fences
 #include "mfcc_fast.cuh"      // mbarrier helpers
 #include "mfcc_kernels.cuh"   // StreamState, frames_ready, K1_EPS
 
 namespace pb {
 
-constexpr int TCD_BLOCKS = 8;                 // GEMM blocks per frame
+constexpr int TCD_BLOCKS = 9;                 // GEMM blocks per frame, r = 0..8
 constexpr int TCD_KSTEPS = 4;                 // K = 64 per block = 4 MMA K-steps of 16
-constexpr int TCD_MAX_NEW = 4;                // frames a stream may release per tick
-constexpr int TCD_MAX_FILT = 22;              // n_filt + 2 accumulator slots of 128 floats must fit
+constexpr int TCD_MAX_FILT = 22;
 constexpr int TCD_MAX_OUT = 16;
+constexpr int TCD_TW_STRIDE = 18;             // floats per input n2 in the twiddle table: (cos, -sin) of r = 1..8, + 2 of padding
 constexpr float TCD_IN_SCALE = 0.015625f;     // 2^-6 folded into the int16 -> float conversion; the butterfly returns 2 Y
-constexpr float TCD_A_SCALE = 0.03125f;       // => A operands hold Y * 2^-5: |A| <= 16384, and <= 32768 < fp16 max after the shift below
+constexpr float TCD_A_SCALE = 0.03125f;       // => A operands hold Z * 2^-5: |A| <= 16384, and <= 32768 < fp16 max after the shift below
 // The kernel transforms x - x[0] (a constant only moves X[0]; constant input then gives exact zeros everywhere else, like the
 // float64 reference and the FFT kernels): Y_0 loses 16 x[0], i.e. the butterfly output 2 * 16 * IN_SCALE * x[0], and the
 // X[0] accumulator gets 32 times that back.
 constexpr float TCD_X0_Y = 32.f * TCD_IN_SCALE;          // 0.5
 constexpr float TCD_X0_D = 32.f * TCD_X0_Y;              // 16
+
+// A tile row is (frame, h), h = 0..3; row h carries up to three blocks in the MMA "slots" 0..2 (64 accumulator columns each).
+__host__ __device__ constexpr int tcd_blk_h(int b) { constexpr int t[9] = {0, 0, 0, 1, 1, 2, 2, 3, 1}; return t[b]; }
+__host__ __device__ constexpr int tcd_blk_s(int b) { constexpr int t[9] = {2, 0, 1, 0, 1, 0, 1, 0, 2}; return t[b]; }
+__host__ __device__ constexpr int tcd_hs_blk(int h, int s) { constexpr int t[12] = {1, 2, 0, 3, 4, 8, 5, 6, -1, 7, -1, -1}; return t[3 * h + s]; }
+// position (0..7) inside K-group g (inputs n2 = 4 g .. 4 g + 3) of input n2 = 4 g + j, real (im = 0) or imaginary part:
+// two 8-byte halves, one per sample pair (j >> 1), swapped for odd g so that the lanes of a half-warp (4 K-groups x 4
+// frames) store to 16 different 8-byte bank groups
+__host__ __device__ constexpr int tcd_kslot(int j, int im, int g) { return 4 * ((j >> 1) ^ (g & 1)) + 2 * im + (j & 1); }
+// bin held by column c of block b (quarter c >> 4: Re / Im of X[16 m + b], Re / Im of X[16 m + 16 - b]; m = c & 15), or -1
+// where the column repeats another block's bin (second halves of blocks 0 and 8, except X[256] in block 0)
+__host__ __device__ constexpr int tcd_col_bin(int b, int c) {
+    const int m = c & 15, second = c >> 5;
+    if (b == 0) return second ? (m == 15 ? 256 : -1) : 16 * m;
+    if (b == 8) return second ? -1 : 16 * m + 8;
+    return second ? 16 * m + 16 - b : 16 * m + b;
+}
 
 // ---------------------------------------------------------------------------------------------------------------------
 // 16-point DFT of real data, outputs scaled by 2: yr[k] + i yi[k] = 2 * sum_q x[q] w16^(q k), k = 0..8 (yi[0] = yi[8] = 0).
@@ -90,77 +113,68 @@ __host__ __device__ __forceinline__ void rdft16_x2(const float (&x)[16], float (
 
 // ---------------------------------------------------------------------------------------------------------------------
 // Host tables.
-//   B operand of block b, piece hi / lo: fp16 [kgroup 8][n 64][8]  (K-major canonical, no swizzle: element (n, k) at
-//   ((k / 8) * 64 + n) * 8 + k % 8).  K-group g holds the inputs n2 = 4 g .. 4 g + 3, first and second input half of the
-//   block.  K-step ks of the MMAs uses the groups ks and 4 + ks: the two producer lanes of a frame row each own one 32-byte
-//   sector of every sample row (groups 0-3 and 4-7).  Element order inside the 16-byte group: tcd_kslot(j, second, g) --
-//   two 8-byte halves, one per sample pair (j >> 1), swapped for the groups of the second lane (g >= 4) so that the two
-//   lanes store to different bank halves.
-//   Output column c of block b (accumulator column 64 b + c):
-//     block 0: [Re X[16m] | Im X[16m] (m = 0 carries X[256]) | Re X[16m+8] | Im X[16m+8]],   m = c % 16
-//     block r: [Re X[16m+r] | Im X[16m+r] | Re X[16m+16-r] | Im X[16m+16-r]]
-struct TcdHostTables {
-    std::vector<__half> b_hi, b_lo;            // [8][8][64][8] each
-    std::vector<float4> etab;                  // [257]: entry 16 c + m of chunk c = 2 b + h (bin in tcd_chunk_bin), [256] = bin 256
-    std::vector<float> dct;                    // [TCD_MAX_OUT][24]
-};
-
-// position (0..7) inside K-group g of input n2 = 4 g + j, first (second = 0) or second (second = 1) input half of the block
-__host__ __device__ constexpr int tcd_kslot(int j, int second, int g) { return 4 * ((j >> 1) ^ (g >> 2)) + 2 * second + (j & 1); }
-
-// bin held by element m of 32-column chunk c = 2 b + h (16 re columns then 16 im columns)
-__host__ __device__ constexpr int tcd_chunk_bin_c(int c, int m) {
-    return (c >> 1) == 0 ? ((c & 1) == 0 ? 16 * m : 16 * m + 8) : ((c & 1) == 0 ? 16 * m + (c >> 1) : 16 * m + 16 - (c >> 1));
-}
-static inline int tcd_chunk_bin(int c, int m) {
-    const int b = c >> 1, h = c & 1;
-    if (b == 0) return h == 0 ? 16 * m : 16 * m + 8;
-    return h == 0 ? 16 * m + b : 16 * m + 16 - b;
-}
-
+//   B operand, piece hi / lo: fp16 [kgroup 8][n 64][8]  (K-major canonical, no swizzle: element (n, k) at
+//   ((k / 8) * 64 + n) * 8 + k % 8), k = 8 g + tcd_kslot(j, im, g) <-> input n2 = 4 g + j, part im.
+//   Twiddles: tw[n2 * TCD_TW_STRIDE + 2 (r - 1)] = (cos, -sin)(2 pi n2 r / 512), r = 1..8.
 static inline void tcd_build_b(std::vector<__half>& b_hi, std::vector<__half>& b_lo) {
-    b_hi.assign((size_t)TCD_BLOCKS * 8 * 64 * 8, __float2half_rn(0.f));
+    b_hi.assign((size_t)8 * 64 * 8, __float2half_rn(0.f));
     b_lo = b_hi;
     const double PI2 = 6.283185307179586476925286766559;
-    for (int b = 0; b < TCD_BLOCKS; ++b)
-        for (int k = 0; k < 64; ++k)
-            for (int n = 0; n < 64; ++n) {
-                const int g = k >> 3, e = k & 7;                                             // which input this row multiplies:
-                const int second = (e >> 1) & 1, n2 = 4 * g + 2 * ((e >> 2) ^ (g >> 2)) + (e & 1);  // inverse of tcd_kslot
-                const int quarter = n >> 4, m = n & 15;
-                double v = 0.0;
-                if (b == 0) {
-                    // first half: Y_0 -> X[16 m] (quarters 0, 1); second half: Y_8 -> X[16 m + 8] (quarters 2, 3)
-                    if (!second && quarter < 2) {
-                        const double a = PI2 * n2 * m / 32.0;
-                        v = quarter == 0 ? cos(a) : -sin(a);
-                        if (quarter == 1 && m == 0) v = (n2 & 1) ? -1.0 : 1.0;             // slot Im X[0] := X[256]
-                    } else if (second && quarter >= 2) {
-                        const double a = PI2 * n2 * 8 / 512.0 + PI2 * n2 * m / 32.0;
-                        v = quarter == 2 ? cos(a) : -sin(a);
-                    }
-                } else {
-                    const int r = quarter < 2 ? b : 16 - b;
-                    const double a = PI2 * n2 * r / 512.0 + PI2 * n2 * m / 32.0;
-                    const double tr = cos(a), ti = -sin(a);                                 // T = w512^(n2 r) w32^(n2 m)
+    for (int g = 0; g < 8; ++g)
+        for (int j = 0; j < 4; ++j)
+            for (int im = 0; im < 2; ++im)
+                for (int n = 0; n < 64; ++n) {
+                    const int n2 = 4 * g + j, quarter = n >> 4, m = n & 15;
+                    const double a = PI2 * n2 * (quarter < 2 ? m : m + 1) / 32.0;
+                    const double tr = cos(a), ti = -sin(a);                                 // T = w32^(n2 m) or w32^(n2 (m + 1))
                     // quarters 0, 1: (a + i b) T -> re: a tr - b ti, im: a ti + b tr
                     // quarters 2, 3: (a - i b) T -> re: a tr + b ti, im: a ti - b tr
-                    const bool im_out = quarter & 1;
-                    if (quarter < 2) v = !second ? (im_out ? ti : tr) : (im_out ? tr : -ti);
-                    else v = !second ? (im_out ? ti : tr) : (im_out ? -tr : ti);
+                    double v;
+                    if (quarter == 0) v = im ? -ti : tr;
+                    else if (quarter == 1) v = im ? tr : ti;
+                    else if (quarter == 2) v = im ? ti : tr;
+                    else v = im ? -tr : ti;
+                    const __half hi = __float2half_rn((float)v);
+                    const __half lo = __float2half_rn((float)(v - (double)__half2float(hi)));
+                    const size_t o = ((size_t)g * 64 + n) * 8 + tcd_kslot(j, im, g);
+                    b_hi[o] = hi; b_lo[o] = lo;
                 }
-                const __half hi = __float2half_rn((float)v);
-                const __half lo = __float2half_rn((float)(v - (double)__half2float(hi)));
-                const size_t o = (((size_t)b * 8 + g) * 64 + n) * 8 + e;
-                b_hi[o] = hi; b_lo[o] = lo;
-            }
 }
 
-// wrise / wfall / grid as built by api.cu (build_mel); pscale turns (re^2 + im^2) of the scaled accumulators into power / n_fft
+static inline void tcd_build_tw(std::vector<float>& tw) {
+    tw.assign((size_t)32 * TCD_TW_STRIDE, 0.f);
+    const double PI2 = 6.283185307179586476925286766559;
+    for (int n2 = 0; n2 < 32; ++n2)
+        for (int r = 1; r <= 8; ++r) {
+            const double a = PI2 * n2 * r / 512.0;
+            tw[(size_t)n2 * TCD_TW_STRIDE + 2 * (r - 1)] = (float)cos(a);
+            tw[(size_t)n2 * TCD_TW_STRIDE + 2 * (r - 1) + 1] = (float)-sin(a);
+        }
+}
+
+// One input's nine block operands from its 16-point DFT (yr, yi scaled as rdft16_x2 returns them): Z_0 = Y_0 - shift (real),
+// Z_r = Y_r w512^(n2 r).  Host + device: the kernel and the CPU model share this arithmetic.
+__host__ __device__ __forceinline__ void tcd_twiddle(const float (&yr)[9], const float (&yi)[9], const float* tw, float x0_shift,
+                                                     float (&zr)[9], float (&zi)[9]) {
+    zr[0] = yr[0] - x0_shift; zi[0] = 0.f;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int r = 1; r < 8; ++r) {
+        const float c = tw[2 * (r - 1)], s = tw[2 * (r - 1) + 1];
+        zr[r] = fmaf(yr[r], c, -(yi[r] * s));
+        zi[r] = fmaf(yr[r], s, yi[r] * c);
+    }
+    zr[8] = yr[8] * tw[14]; zi[8] = yr[8] * tw[15];
+}
+
+// wrise / wfall / grid as built by api.cu (build_mel); pscale turns (re^2 + im^2) of the scaled accumulators into power / n_fft.
+// etab[k] = (rising-edge weight, falling-edge weight, segment) of bin k  (CPU model of the epilogue only; the kernel has the same
+// numbers at compile time, mfcc_tc2.cuh)
 static inline void tcd_build_etab(std::vector<float4>& etab, const std::vector<float>& wrise, const std::vector<float>& wfall,
                                   const std::vector<int>& grid, int n_filt, float pscale) {
     etab.assign(257, make_float4(0.f, 0.f, 0.f, 0.f));
-    auto entry = [&](int k) {
+    for (int k = 0; k < 257; ++k) {
         int s = 0;
         float wr = 0.f, wf = 0.f;
         if (k >= grid[0] && k < grid[n_filt + 1]) {
@@ -170,28 +184,26 @@ static inline void tcd_build_etab(std::vector<float4>& etab, const std::vector<f
         }
         float sf;
         memcpy(&sf, &s, 4);
-        return make_float4(wr * pscale, wf * pscale, sf, 0.f);
-    };
-    for (int c = 0; c < 16; ++c)
-        for (int m = 0; m < 16; ++m) etab[16 * c + m] = entry(tcd_chunk_bin(c, m));
-    etab[256] = entry(256);
+        etab[k] = make_float4(wr * pscale, wf * pscale, sf, 0.f);
+    }
 }
 
-// CPU model of the tensor-core path for ONE frame of 512 int16 samples: the same butterfly, the same tables read through the
-// same layout arithmetic, fp16 products accumulated in fp32, the frame's first sample removed from Y_0 and restored in X[0].
-// d[512] = the frame's accumulator row (TMEM lane) as the epilogue sees it after that correction.
-static inline void tcd_host_accumulators(const int16_t* x, float* d) {
+// CPU model of the tensor-core path for ONE frame of 512 int16 samples: the same butterfly and twiddles, the same operand table
+// read through the same layout arithmetic, fp16 products accumulated in fp32, the frame's first sample removed from Y_0 and
+// restored in X[0].  d[9][64] = the frame's accumulator columns, block by block, as the epilogue sees them after that correction.
+static inline void tcd_host_accumulators(const int16_t* x, float (*d)[64]) {
     static std::vector<__half> b_hi, b_lo;
-    if (b_hi.empty()) tcd_build_b(b_hi, b_lo);
+    static std::vector<float> tw;
+    if (b_hi.empty()) { tcd_build_b(b_hi, b_lo); tcd_build_tw(tw); }
     std::vector<float> a((size_t)TCD_BLOCKS * 64);
     for (int g = 0; g < 8; ++g)
         for (int j = 0; j < 4; ++j) {
             const int n2 = 4 * g + j;
-            float in[16], yr[9], yi[9];
+            float in[16], yr[9], yi[9], zr[9], zi[9];
             for (int q = 0; q < 16; ++q) in[q] = (float)x[n2 + 32 * q] * TCD_IN_SCALE;
             rdft16_x2(in, yr, yi);
-            a[0 * 64 + 8 * g + tcd_kslot(j, 0, g)] = yr[0] - TCD_X0_Y * (float)x[0]; a[0 * 64 + 8 * g + tcd_kslot(j, 1, g)] = yr[8];
-            for (int r = 1; r < 8; ++r) { a[r * 64 + 8 * g + tcd_kslot(j, 0, g)] = yr[r]; a[r * 64 + 8 * g + tcd_kslot(j, 1, g)] = yi[r]; }
+            tcd_twiddle(yr, yi, tw.data() + (size_t)n2 * TCD_TW_STRIDE, TCD_X0_Y * (float)x[0], zr, zi);
+            for (int b = 0; b < TCD_BLOCKS; ++b) { a[b * 64 + 8 * g + tcd_kslot(j, 0, g)] = zr[b]; a[b * 64 + 8 * g + tcd_kslot(j, 1, g)] = zi[b]; }
         }
     for (int b = 0; b < TCD_BLOCKS; ++b)
         for (int n = 0; n < 64; ++n) {
@@ -201,69 +213,54 @@ static inline void tcd_host_accumulators(const int16_t* x, float* d) {
                     const float av = a[b * 64 + k];
                     const __half ah = __float2half_rn(av);
                     const __half al = __float2half_rn(av - __half2float(ah));
-                    const size_t o = (((size_t)b * 8 + (k >> 3)) * 64 + n) * 8 + (k & 7);
+                    const size_t o = ((size_t)(k >> 3) * 64 + n) * 8 + (k & 7);
                     const float pa = __half2float(pass == 0 ? al : ah), pb = __half2float(pass == 1 ? b_lo[o] : b_hi[o]);
                     acc += pa * pb;
                 }
-            d[64 * b + n] = acc;
+            d[b][n] = acc;
         }
-    d[0] += TCD_X0_D * (float)x[0];            // the kernel transforms x - x[0] (exact zeros for constant input) and restores X[0] here
+    d[0][0] += TCD_X0_D * (float)x[0];     // the kernel transforms x - x[0] (exact zeros for constant input) and restores X[0] here
 }
 
 // |X[k]|^2 of the raw samples, k = 0..256
 static inline void tcd_host_power(const int16_t* x, double* power) {
-    float d[512];
+    float d[TCD_BLOCKS][64];
     tcd_host_accumulators(x, d);
     const double inv = 1.0 / ((double)TCD_A_SCALE * (double)TCD_A_SCALE);
-    for (int c = 0; c < 16; ++c)
-        for (int m = 0; m < 16; ++m) {
-            const double re = d[32 * c + m], im = d[32 * c + 16 + m];
-            const int k = tcd_chunk_bin(c, m);
-            if (c == 0 && m == 0) { power[0] = re * re * inv; power[256] = im * im * inv; }
-            else power[k] = (re * re + im * im) * inv;
-        }
+    for (int b = 0; b < TCD_BLOCKS; ++b)
+        for (int half = 0; half < 2; ++half)
+            for (int m = 0; m < 16; ++m) {
+                const int k = tcd_col_bin(b, 32 * half + m);
+                if (k < 0) continue;
+                const double re = d[b][32 * half + m], im = d[b][32 * half + 16 + m];
+                power[k] = (k == 0 || k == 256) ? re * re * inv : (re * re + im * im) * inv;
+            }
 }
 
-// The epilogue of mfcc_tc_stream_kernel for one accumulator row, statement for statement (fp32): table-driven mel sums with
-// the run-length flush, log, DCT, c0.  acc: (n_filt + 2) floats of scratch.
-static inline void tcd_host_epilogue(const float* d, const float4* etab, const float* dct, int n_filt, int n_out, float tot_scale,
-                                     float* acc, float* out) {
-    for (int j = 0; j < n_filt + 2; ++j) acc[j] = 0.f;
-    float tot = 0.f, a_r = 0.f, a_f = 0.f, p256 = 0.f;
-    int s_cur = 0;
-    for (int c = 0; c < 16; ++c)
-        for (int m = 0; m < 16; ++m) {
-            const float re = d[32 * c + m], im = d[32 * c + 16 + m];
-            float p = re * re;
-            if (c == 0 && m == 0) p256 = im * im;
-            else p = fmaf(im, im, p);
-            const float4 e = etab[16 * c + m];
-            int s;
-            memcpy(&s, &e.z, 4);
-            if (s != s_cur) { acc[s_cur + 1] += a_r; acc[s_cur] += a_f; s_cur = s; a_r = 0.f; a_f = 0.f; }
-            tot += p;
-            a_r = fmaf(e.x, p, a_r);
-            a_f = fmaf(e.y, p, a_f);
-        }
-    {
-        const float4 e = etab[256];
-        int s;
-        memcpy(&s, &e.z, 4);
-        if (s != s_cur) { acc[s_cur + 1] += a_r; acc[s_cur] += a_f; s_cur = s; a_r = 0.f; a_f = 0.f; }
-        tot += p256;
-        a_r = fmaf(e.x, p256, a_r);
-        a_f = fmaf(e.y, p256, a_f);
-        acc[s_cur + 1] += a_r; acc[s_cur] += a_f;
-    }
+// The epilogue's arithmetic for one frame (fp32): per-segment rising / falling sums in column order, log, DCT, c0.
+static inline void tcd_host_epilogue(const float (*d)[64], const float4* etab, const float* dct, int n_filt, int n_out, float pscale,
+                                     float* out) {
+    float rise[TCD_MAX_FILT + 2] = {0}, fall[TCD_MAX_FILT + 2] = {0}, tot = 0.f;
+    for (int b = 0; b < TCD_BLOCKS; ++b)
+        for (int half = 0; half < 2; ++half)
+            for (int m = 0; m < 16; ++m) {
+                const int k = tcd_col_bin(b, 32 * half + m);
+                if (k < 0) continue;
+                const float re = d[b][32 * half + m], im = d[b][32 * half + 16 + m];
+                const float p = (k == 0 || k == 256) ? re * re : fmaf(im, im, re * re);
+                int s;
+                memcpy(&s, &etab[k].z, 4);
+                tot += p;
+                rise[s] = fmaf(etab[k].x, p, rise[s]);                  // weights carry pscale here (a power of two: exact)
+                fall[s] = fmaf(etab[k].y, p, fall[s]);
+            }
     const float eps = 2.220446049250313e-16f;
-    for (int j = 0; j < n_filt; ++j) acc[j + 1] = logf(fmaxf(acc[j + 1], eps));
+    float lg[TCD_MAX_FILT];
+    for (int j = 0; j < n_filt; ++j) lg[j] = logf(fmaxf(rise[j] + fall[j + 1], eps));
     for (int o = 0; o < n_out; ++o) {
-        float v0 = 0.f, v1 = 0.f;
-        const float* dr = dct + (size_t)o * 24;
-        int j = 0;
-        for (; j + 1 < n_filt; j += 2) { v0 = fmaf(dr[j], acc[j + 1], v0); v1 = fmaf(dr[j + 1], acc[j + 2], v1); }
-        if (j < n_filt) v0 = fmaf(dr[j], acc[j + 1], v0);
-        out[o] = o == 0 ? logf(fmaxf(tot * tot_scale, eps)) : v0 + v1;
+        float v = 0.f;
+        for (int j = 0; j < n_filt; ++j) v = fmaf(dct[(size_t)o * 24 + j], lg[j], v);
+        out[o] = o == 0 ? logf(fmaxf(tot * pscale, eps)) : v;
     }
 }
 
