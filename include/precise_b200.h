@@ -210,6 +210,9 @@ int pb_debug_tc_dft_power(const int16_t* x512, double* power257);
 /* ... and of the whole kernel for one frame (accumulators + mel / log / DCT epilogue with the tables this configuration
  * would upload) -> out[min(n_filt, n_mfcc)].  No device needed.  Test hook. */
 int pb_debug_tc_mfcc_frame(const pb_config* cfg, const int16_t* x512, float* out);
+/* The same for k1 mode 5 (csrc/mfcc_tc3.cuh: both DFT stages on the tensor cores, int16 split exactly into two fp16 pieces);
+ * power257 (optional) receives |X[k]|^2 of the raw samples as that kernel's accumulators hold it.  No device needed.  Test hook. */
+int pb_debug_tc3_mfcc_frame(const pb_config* cfg, const int16_t* x512, float* out, double* power257);
 /* Test/profiling hook: the first call arms, later calls read four device-side cycle counters of the wide-network
  * tensor-core kernel's MMA-issuer thread (operand wait, weight-tile wait, issue, total) for CTA 0. */
 int pb_debug_counters(pb_handle* h, long long out[4]);

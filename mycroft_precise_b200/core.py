@@ -66,6 +66,7 @@ SYMBOLS = {
     'pb_debug_k1_mode': (C.c_int, [_VP, C.c_int]),
     'pb_debug_tc_dft_power': (C.c_int, [_VP, _VP]),
     'pb_debug_tc_mfcc_frame': (C.c_int, [_VP, _VP, _VP]),
+    'pb_debug_tc3_mfcc_frame': (C.c_int, [_VP, _VP, _VP, _VP]),
     'pb_debug_counters': (C.c_int, [_VP, C.POINTER(C.c_longlong)]),
     'pb_last_error': (C.c_char_p, []),
     'pb_abi_version': (C.c_int, []),
@@ -209,8 +210,8 @@ class PreciseB200:
         self.n_features = self.params.n_features
         self.mfcc_width = int(self.lib.pb_mfcc_width(h))
         self.feature_size = int(self.lib.pb_feature_size(h))
-        cd, _, _ = numpy_cdf(self.params.threshold_config)
-        if len(cd):
+        cd, lo, hi = numpy_cdf(self.params.threshold_config)
+        if hi > lo:                      # out_range 0 (threshold_decoder.py:48-49): the table is never indexed
             check(self.lib.pb_set_cdf(h, cd.ctypes.data_as(C.c_void_p), len(cd)))
         self._count = torch.zeros(1, dtype=torch.int64, device=self.device)
 

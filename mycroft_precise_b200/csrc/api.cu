@@ -24,6 +24,7 @@
 #include "gru_tc5_big.cuh"
 #include "mfcc_tc.cuh"
 #include "mfcc_tc2.cuh"
+#include "mfcc_tc3.cuh"
 
 using namespace pb;
 
@@ -76,6 +77,10 @@ struct pb_handle {
     bool tc2_ok = false;             // ... and by mfcc_tc2_stream_kernel<Tc2Geo20> (run-time mel tables equal its compile-time ones)
     std::vector<float> h_wrise, h_wfall; std::vector<int> h_grid;      // host copies for the lazily built tcd tables
     uint4* d_tcd_b = nullptr; float* d_tcd_tw = nullptr; float* d_tcd_dct = nullptr;
+    bool tc3_ok = false;             // ... and by mfcc_tc3_kernel<Tc2Geo20> (both DFT stages on the tensor cores; needs chunk >= hop)
+    uint4 *d_tc3_b1 = nullptr, *d_tc3_b2 = nullptr; float* d_tc3_tw = nullptr;
+    Tc3Rec* d_tc3_recs = nullptr; unsigned int* d_tc3_counters = nullptr;
+    int tc3_parity = 0;              // which of the two frame counters the next tick's plan kernel fills
     float tcd_tot_scale = 0.f;
     bool fast_ok = false;            // aligned geometry: warp-autonomous kernels (mfcc_fast.cuh)
     int npl = 0, maxc = 0, nol = 0;
@@ -255,6 +260,7 @@ PB_API void pb_destroy(pb_handle* h) {
     cudaSetDevice(h->cfg.device);
     cudaFree(h->d_wrise); cudaFree(h->d_wfall); cudaFree(h->d_dct); cudaFree(h->d_grid);
     cudaFree(h->d_tcd_b); cudaFree(h->d_tcd_tw); cudaFree(h->d_tcd_dct);
+    cudaFree(h->d_tc3_b1); cudaFree(h->d_tc3_b2); cudaFree(h->d_tc3_tw); cudaFree(h->d_tc3_recs); cudaFree(h->d_tc3_counters);
     cudaFree(h->d_tw_stage); cudaFree(h->d_tw_post); cudaFree(h->d_tw_any); cudaFree(h->d_cd); cudaFree(h->d_ptab); cudaFree(h->d_ctab); cudaFree(h->d_dct_t);
     cudaFree(h->st.n_samples); cudaFree(h->st.tail); cudaFree(h->st.ring); cudaFree(h->st.trig);
     cudaFree(h->d_wcat); cudaFree(h->d_bias); cudaFree(h->d_wd); cudaFree(h->d_count);
@@ -365,6 +371,7 @@ PB_API int pb_create(const pb_config* cfg, pb_handle** out) {
     h->tc2_ok = h->tcd_ok && c.hop_samples >= 512 && c.hop_samples <= 16384 && h->ring_rows <= 255 && h->n_out >= 1 &&
                 (c.chunk_samples + c.hop_samples - 1) / c.hop_samples <= TC2_MAX_NEW &&
                 tc2_geo_matches<Tc2Geo20>(c.n_filt, h->n_bins, grid, wrise, wfall);
+    h->tc3_ok = h->tc2_ok && c.chunk_samples >= c.hop_samples && c.chunk_samples <= 32760;
     h->k1_fast_smem = K1F_WARPS * sizeof(K1FWarp) + (size_t)h->npl * 128 * sizeof(float4) +
                       (size_t)c.n_filt * 16 * h->nol * sizeof(float) + (((size_t)c.n_filt * h->maxc + 15) & ~(size_t)15);
     // DCT-II, norm='ortho' (scipy.fftpack.dct as sonopy.mfcc_spec calls it), first n_out rows
@@ -650,7 +657,8 @@ PB_API int pb_debug_gru_mode(pb_handle* h, int mode) { if (!h) return fail(PB_ER
 
 PB_API int pb_debug_k1_mode(pb_handle* h, int mode) {
     if (!h) return fail(PB_ERR_INVALID, "null handle");
-    if (mode < 0 || mode > 4 || mode == 1) return fail(PB_ERR_INVALID, "k1 mode must be 0 (automatic), 2 (FFT kernel, lean set-up), 3 (FFT kernel) or 4 (tensor-core DFT kernel)");
+    if (mode < 0 || mode > 6 || mode == 1) return fail(PB_ERR_INVALID, "k1 mode must be 0 (automatic), 2 (FFT kernel, lean set-up), 3 (FFT kernel), 4 (tensor-core DFT kernel, stage 2 only) or 5 (both DFT stages on the tensor cores)");
+    if (mode >= 5 && !h->tc3_ok) return fail(PB_ERR_UNSUPPORTED, "the two-stage tensor-core MFCC tick needs the default mel geometry, hop >= 512 and chunk >= hop, a multiple of 8");
     if (mode == 4 && !h->tc2_ok) return fail(PB_ERR_UNSUPPORTED, "the tensor-core MFCC tick needs the default mel geometry (20 filters, 16 kHz, n_fft 512), chunk >= 512 and a multiple of 8");
     if (mode == 2 && !h->fast_ok) return fail(PB_ERR_UNSUPPORTED, "k1 mode 2 needs the aligned geometry of the fast MFCC kernels");
     h->k1_mode = mode;
@@ -687,6 +695,42 @@ PB_API int pb_debug_tc_mfcc_frame(const pb_config* cfg, const int16_t* x512, flo
         float d[TCD_BLOCKS][64];
         tcd_host_accumulators(x512, d);
         tcd_host_epilogue(d, etab.data(), dct.data(), cfg->n_filt, h->n_out, tot_scale, out);
+    }
+    delete h;
+    return rc;
+}
+
+// ... and of the kernel with both DFT stages on the tensor cores (mfcc_tc3.cuh): exact int16 split, stage-1 matrix passes, twiddle,
+// fp16 split, stage-2 passes, its own epilogue order.  No device needed.  Test hook.
+PB_API int pb_debug_tc3_mfcc_frame(const pb_config* cfg, const int16_t* x512, float* out, double* power257) {
+    if (!cfg || !x512 || !out) return fail(PB_ERR_INVALID, "null argument");
+    if (cfg->n_fft != 512 || cfg->n_filt < 1 || cfg->n_filt > TCD_MAX_FILT || cfg->vectorizer != PB_VEC_MFCCS)
+        return fail(PB_ERR_UNSUPPORTED, "the tensor-core MFCC model covers n_fft 512, n_filt <= %d, MFCC vectorizer", TCD_MAX_FILT);
+    pb_handle* h = new (std::nothrow) pb_handle();
+    if (!h) return fail(PB_ERR_CUDA, "out of host memory");
+    h->cfg = *cfg;
+    h->n_bins = cfg->n_fft / 2 + 1;
+    h->n_out = std::min(cfg->n_filt, cfg->n_mfcc);
+    int rc = h->n_out > TCD_MAX_OUT ? fail(PB_ERR_UNSUPPORTED, "n_mfcc > %d", TCD_MAX_OUT) : build_mel(h, h->h_wrise, h->h_wfall, h->h_grid);
+    if (rc == PB_OK) {
+        std::vector<float4> etab;
+        std::vector<float> dct;
+        float tot_scale = 0.f;
+        tcd_host_tables(h, etab, dct, &tot_scale);
+        float d[TCD_BLOCKS][64];
+        tc3_host_accumulators(x512, d);
+        tc3_host_epilogue(d, h->h_wrise, h->h_wfall, h->h_grid, dct.data(), cfg->n_filt, h->n_out, tot_scale, out);
+        if (power257) {
+            const double inv = 1.0 / ((double)TCD_A_SCALE * (double)TCD_A_SCALE);
+            for (int b = 0; b < TCD_BLOCKS; ++b)
+                for (int half = 0; half < 2; ++half)
+                    for (int m = 0; m < 16; ++m) {
+                        const int k = tcd_col_bin(b, 32 * half + m);
+                        if (k < 0) continue;
+                        const double re = d[b][32 * half + m], im = d[b][32 * half + 16 + m];
+                        power257[k] = (k == 0 || k == 256) ? re * re * inv : (re * re + im * im) * inv;
+                    }
+        }
     }
     delete h;
     return rc;
@@ -915,6 +959,25 @@ static int ensure_tcd_tables(pb_handle* h) {
     return PB_OK;
 }
 
+static int ensure_tc3_tables(pb_handle* h) {
+    if (h->d_tc3_b1) return PB_OK;
+    int rc = ensure_tcd_tables(h);                       // DCT table and the power scale are shared with mfcc_tc2
+    if (rc != PB_OK) return rc;
+    std::vector<__half> b1, b2;
+    std::vector<float> tw;
+    tc3_build_b1(b1); tc3_build_b2(b2); tc3_build_tw(tw);
+    CK(cudaMalloc((void**)&h->d_tc3_b2, b2.size() * sizeof(__half)));
+    CK(cudaMemcpy(h->d_tc3_b2, b2.data(), b2.size() * sizeof(__half), cudaMemcpyHostToDevice));
+    CK(upload(&h->d_tc3_tw, tw));
+    CK(cudaMalloc((void**)&h->d_tc3_recs, (size_t)h->cfg.max_streams * (size_t)std::max(1, h->max_new) * sizeof(Tc3Rec)));
+    CK(cudaMalloc((void**)&h->d_tc3_counters, 2 * sizeof(unsigned int)));
+    CK(cudaMemset(h->d_tc3_counters, 0, 2 * sizeof(unsigned int)));
+    CK(ensure_dyn_smem(mfcc_tc3_kernel<Tc2Geo20>, sizeof(Tc3Smem) + 128));
+    CK(cudaMalloc((void**)&h->d_tc3_b1, b1.size() * sizeof(__half)));      // last: its presence marks the set as complete
+    CK(cudaMemcpy(h->d_tc3_b1, b1.data(), b1.size() * sizeof(__half), cudaMemcpyHostToDevice));
+    return PB_OK;
+}
+
 static int launch_stream_mfcc(pb_handle* h, const int16_t* d_pcm, const int32_t* d_ids, int64_t n, cudaStream_t s) {
     const bool pairs = (h->cfg.chunk_samples % 2 == 0) && (h->cfg.hop_samples % 2 == 0) && (h->used % 2 == 0) &&
                        ((uintptr_t)d_pcm % 4 == 0);
@@ -922,7 +985,19 @@ static int launch_stream_mfcc(pb_handle* h, const int16_t* d_pcm, const int32_t*
     const int grid = (int)std::min<int64_t>(tiles, (int64_t)h->sm_count * 4);
     const float inv = 1.0f / 32768.0f, scale = inv * inv / (float)h->cfg.n_fft;
     ProfScope ps(h, 0, s);
-    if (h->k1_mode == 4 && h->tc2_ok && (uintptr_t)d_pcm % 16 == 0 && !h->force_generic) {
+    if (h->k1_mode >= 5 && h->tc3_ok && (uintptr_t)d_pcm % 16 == 0 && !h->force_generic) {
+        int rc = ensure_tc3_tables(h);
+        if (rc != PB_OK) return rc;
+        Tc3Tables t;
+        t.b1 = h->d_tc3_b1; t.b2 = h->d_tc3_b2; t.tw = h->d_tc3_tw; t.dct = h->d_tcd_dct; t.n_out = h->n_out; t.pscale = h->tcd_tot_scale;
+        const int par = h->tc3_parity;
+        h->tc3_parity ^= 1;
+        mfcc_tc3_plan_kernel<<<(int)((n + TC3_PLAN_THREADS - 1) / TC3_PLAN_THREADS), TC3_PLAN_THREADS, 0, s>>>(
+            d_pcm, d_ids, (int)n, h->cfg.chunk_samples, h->cfg.hop_samples, h->st, h->d_tc3_recs, h->d_tc3_counters, par);
+        const int64_t max_tiles = (n * std::max(1, h->max_new) + TC3_TILE - 1) / TC3_TILE;
+        mfcc_tc3_kernel<Tc2Geo20><<<(int)std::min<int64_t>(max_tiles, h->sm_count), TC3_THREADS, sizeof(Tc3Smem) + 128, s>>>(
+            d_pcm, h->cfg.chunk_samples, t, h->st, h->d_tc3_recs, h->d_tc3_counters, par, h->k1_mode == 6 ? 1 : 0);
+    } else if (h->k1_mode == 4 && h->tc2_ok && (uintptr_t)d_pcm % 16 == 0 && !h->force_generic) {
         int rc = ensure_tcd_tables(h);
         if (rc != PB_OK) return rc;
         Tc2Tables t;

@@ -650,7 +650,7 @@ def test_runner_plugin_predict_shape():
 
 @pytest.mark.skipif(os.environ.get('PB_TEST_TC_K1') != '1',
                     reason='opt-in MFCC kernels (tensor-core DFT, lean set-up): not yet validated on hardware; set PB_TEST_TC_K1=1')
-@pytest.mark.parametrize('k1_mode', [2, 4], ids=['lean_setup', 'tensor_core'])
+@pytest.mark.parametrize('k1_mode', [2, 4, 5, 6], ids=['lean_setup', 'tensor_core', 'tensor_core_two_stage', 'two_stage_desc_swapped'])
 def test_experimental_mfcc_tick(k1_mode):
     """pb_debug_k1_mode: 1 = windows produced by the tcgen05 DFT kernel, 2 = fast kernel with the 32-bit per-pass set-up,
     against the default kernels (mode 2 must be bit-identical: same arithmetic, different address computation)."""
