@@ -72,7 +72,7 @@ struct pb_handle {
     float *d_proj_w = nullptr, *d_proj_b = nullptr;
     size_t k1_batch_smem = 0, k1_stream_smem = 0, k1_fast_smem = 0;
     bool force_generic = false;      // tests: exercise the generic kernels on the aligned geometry
-    int k1_mode = 0;                 // 0 = default kernels, 1 = experimental tensor-core DFT tick (mfcc_tc.cuh; opt-in, see its header), 2 = fast kernel, lean set-up (opt-in)
+    int k1_mode = 0;                 // 0 = default (FFT kernel, 32-bit set-up), 2 = the same, 3 = FFT kernel with the original 64-bit set-up, 4 = tcgen05 stage-2 kernel (mfcc_tc2), 5 = both DFT stages on tcgen05 (mfcc_tc3), 100 + w = 5 with warp w's timeline
     bool tcd_ok = false;             // geometry the tensor-core DFT tables cover (CPU model + kernel)
     bool tc2_ok = false;             // ... and by mfcc_tc2_stream_kernel<Tc2Geo20> (run-time mel tables equal its compile-time ones)
     std::vector<float> h_wrise, h_wfall; std::vector<int> h_grid;      // host copies for the lazily built tcd tables
@@ -657,7 +657,8 @@ PB_API int pb_debug_gru_mode(pb_handle* h, int mode) { if (!h) return fail(PB_ER
 
 PB_API int pb_debug_k1_mode(pb_handle* h, int mode) {
     if (!h) return fail(PB_ERR_INVALID, "null handle");
-    if (mode < 0 || mode > 6 || mode == 1) return fail(PB_ERR_INVALID, "k1 mode must be 0 (automatic), 2 (FFT kernel, lean set-up), 3 (FFT kernel), 4 (tensor-core DFT kernel, stage 2 only) or 5 (both DFT stages on the tensor cores)");
+    if (mode >= 100 && mode <= 116 && h->tc3_ok) { h->k1_mode = mode; return PB_OK; }      // mode 5 with the phase timeline of warp (mode - 100) in pb_debug_counters
+    if (mode < 0 || mode > 5 || mode == 1) return fail(PB_ERR_INVALID, "k1 mode must be 0 (automatic), 2 (FFT kernel, lean set-up), 3 (FFT kernel), 4 (tensor-core DFT kernel, stage 2 only) or 5 (both DFT stages on the tensor cores)");
     if (mode >= 5 && !h->tc3_ok) return fail(PB_ERR_UNSUPPORTED, "the two-stage tensor-core MFCC tick needs the default mel geometry, hop >= 512 and chunk >= hop, a multiple of 8");
     if (mode == 4 && !h->tc2_ok) return fail(PB_ERR_UNSUPPORTED, "the tensor-core MFCC tick needs the default mel geometry (20 filters, 16 kHz, n_fft 512), chunk >= 512 and a multiple of 8");
     if (mode == 2 && !h->fast_ok) return fail(PB_ERR_UNSUPPORTED, "k1 mode 2 needs the aligned geometry of the fast MFCC kernels");
@@ -985,7 +986,7 @@ static int launch_stream_mfcc(pb_handle* h, const int16_t* d_pcm, const int32_t*
     const int grid = (int)std::min<int64_t>(tiles, (int64_t)h->sm_count * 4);
     const float inv = 1.0f / 32768.0f, scale = inv * inv / (float)h->cfg.n_fft;
     ProfScope ps(h, 0, s);
-    if (h->k1_mode >= 5 && h->tc3_ok && (uintptr_t)d_pcm % 16 == 0 && !h->force_generic) {
+    if ((h->k1_mode == 5 || h->k1_mode >= 100) && h->tc3_ok && (uintptr_t)d_pcm % 16 == 0 && !h->force_generic) {
         int rc = ensure_tc3_tables(h);
         if (rc != PB_OK) return rc;
         Tc3Tables t;
@@ -996,7 +997,7 @@ static int launch_stream_mfcc(pb_handle* h, const int16_t* d_pcm, const int32_t*
             d_pcm, d_ids, (int)n, h->cfg.chunk_samples, h->cfg.hop_samples, h->st, h->d_tc3_recs, h->d_tc3_counters, par);
         const int64_t max_tiles = (n * std::max(1, h->max_new) + TC3_TILE - 1) / TC3_TILE;
         mfcc_tc3_kernel<Tc2Geo20><<<(int)std::min<int64_t>(max_tiles, h->sm_count), TC3_THREADS, sizeof(Tc3Smem) + 128, s>>>(
-            d_pcm, h->cfg.chunk_samples, t, h->st, h->d_tc3_recs, h->d_tc3_counters, par, h->k1_mode == 6 ? 1 : 0);
+            t, h->d_tc3_recs, h->d_tc3_counters, par, h->k1_mode >= 100 ? h->k1_mode : 1, h->d_dbg);
     } else if (h->k1_mode == 4 && h->tc2_ok && (uintptr_t)d_pcm % 16 == 0 && !h->force_generic) {
         int rc = ensure_tcd_tables(h);
         if (rc != PB_OK) return rc;
@@ -1014,7 +1015,7 @@ static int launch_stream_mfcc(pb_handle* h, const int16_t* d_pcm, const int32_t*
         const int spw = (int)std::max<int64_t>(1, std::min<int64_t>(K1F_STREAMS_PER_WARP, (n + warps_total - 1) / warps_total));
         const int64_t tilesf = (n + spw - 1) / spw;
         const int gridf = (int)std::min<int64_t>((tilesf + K1F_WARPS - 1) / K1F_WARPS, (int64_t)h->sm_count * 4);
-        if (h->k1_mode == 2)
+        if (h->k1_mode != 3)                     // default: the 32-bit per-pass set-up (bit-identical rows, 3 % faster on B200); 3 = the 64-bit original
             mfcc_fast_stream_kernel<true><<<gridf, K1F_THREADS, h->k1_fast_smem, s>>>(d_pcm, d_ids, (int)n, h->cfg.chunk_samples, h->cfg.hop_samples, spw, scale,
                                                                                       mel_tables(h), fast_tables(h), h->st);
         else

@@ -16,14 +16,17 @@
 //            sharing one 64 x 64 matrix (mfcc_tc.cuh); rows of an MMA = (frame, h), four rows per frame.
 //   epilogue (CUDA cores):   power, mel edge sums with compile-time bins and weights, log, DCT, ring row.
 //
-// Organisation: a persistent CTA per SM, 16 warps that all walk the same phases (no warp specialisation: the instruction
-// cache sees one small loop at a time -- the warp-specialised predecessor, mfcc_tc2.cuh, spent 40 % of its issue slots waiting
-// for instructions).  Per tile of 32 frames:
-//     INT(k)   all warps   tcgen05.ld of stage 1's result, twiddle, split, stores           -> MMA2(k), and MMA1(k+1) on the way
-//     P(k)     all warps   CONV(k+2): prefetched PCM registers -> stage-1 operand; prefetch of tile k+3;
-//              warps 0-7   EPI(k-1);   warps 8-15  new tails of tile k+2, frame records of tile k+4 (+ L2 prefetch)
+// Organisation: a persistent CTA per SM, 16 worker warps that all walk the same phases (no warp specialisation of the heavy
+// loops: the instruction cache sees one small loop at a time -- the warp-specialised predecessor, mfcc_tc2.cuh, spent 40 % of
+// its issue slots waiting for instructions) plus one warp that only issues the MMAs.  Per tile of 32 frames:
+//     INT(k)   workers     tcgen05.ld of stage 1's result, twiddle, split, stores
+//     P(k)     warp 16     MMA2(k)   (MMA1(k+1) as soon as every worker has read tile k's stage-1 result, during INT(k))
+//              warps 0-7   EPI(k-1)
+//              warps 8-15  new tails of tile k+1, frame records of tile k+4 (+ L2 prefetch), CONV(k+2) = prefetched PCM registers ->
+//                          stage-1 operand, then the prefetch of tile k+3
 // with one __syncthreads after each; the MMAs of a tile run under the CUDA-core phases of its neighbours.  The frame list
-// (which frames complete this tick, where their samples are, first sample, new tail) is built by mfcc_tc3_plan_kernel.
+// (which frames complete this tick, where their samples are, the split of the first sample, new tail) is built by
+// mfcc_tc3_plan_kernel with every pointer ready to use.
 #pragma once
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
@@ -33,7 +36,8 @@
 
 namespace pb {
 
-constexpr int TC3_THREADS = 512;
+constexpr int TC3_WORKERS = 512;                // 16 worker warps
+constexpr int TC3_THREADS = TC3_WORKERS + 32;   // + the MMA-issuing warp
 constexpr int TC3_TILE = 32;                    // frames per tile
 constexpr int TC3_SLOTS = 3;                    // 64-column stage-2 MMA slots per tile row
 constexpr int TC3_D1_COLS = 128;                // stage-1 accumulators: 8 groups of 4 frames x 16 columns
@@ -54,16 +58,16 @@ __host__ __device__ constexpr int tc3_kslot(int j, int im) { return 2 * j + im; 
 // stage-1 output column: 0 = Y_0, 1 = Y_8, 2 r / 2 r + 1 = Re / Im Y_r (r = 1..7)
 __host__ __device__ constexpr int tc3_y_col(int r, int im) { return r == 0 ? 0 : r == 8 ? 1 : 2 * r + im; }
 
-struct __align__(16) Tc3Rec {          // one frame completed by this tick
-    int s;                             // row of the PCM batch
-    int sid;                           // stream id
-    short dj;                          // frame start relative to the chunk (< 0: the first -dj samples are the stream's tail)
-    short x0;                          // the frame's first sample
-    unsigned short tail_off;           // first frame of a stream only: new tail = chunk[tail_off, tail_off + 8 tail_nv)
-    unsigned char tail_nv;             // ... in 16-byte units (0: nothing to copy)
-    unsigned char slot;                // ring slot of the frame's MFCC row
+struct __align__(16) Tc3Rec {          // one frame completed by this tick, everything the main kernel needs in ready-to-use form
+    const int16_t* frame;              // sample 0 of the frame in chunk coordinates (pcm row + dj; only samples >= 8 len0c are read); nullptr: padding
+    int16_t* tail;                     // the stream's tail buffer (holds the frame's first 8 len0c samples; receives the new tail)
+    float* row;                        // the frame's MFCC ring row
+    unsigned short c_lo, c_hi;         // fp16 constants of the exact split: -(1152 + lo0), -(9 + hi0 / 128) with x0 = 256 hi0 + lo0 the frame's first sample
+    unsigned char len0c;               // 16-byte chunks of the frame that come from the tail
+    unsigned char tail_nv;             // first frame of a stream only: 16-byte chunks of the new tail (0: nothing to copy)
+    unsigned short tail_delta;         // ... which starts 8 tail_delta samples after `frame`
 };
-static_assert(sizeof(Tc3Rec) == 16, "frame records are loaded as one 16-byte vector");
+static_assert(sizeof(Tc3Rec) == 32, "frame records are loaded as two 16-byte vectors");
 
 // ---------------------------------------------------------------------------------------------------------------------
 // Host tables.
@@ -270,25 +274,36 @@ mfcc_tc3_plan_kernel(const int16_t* __restrict__ pcm, const int* __restrict__ id
     for (int j = 0; j < cnt; ++j) {
         Tc3Rec r;
         const int dj = d + j * hop;
-        r.s = i; r.sid = sid; r.dj = (short)dj;
-        r.x0 = dj >= 0 ? chunk_p[dj] : st.tail[(long long)sid * st.tail_cap + j * hop];
-        r.tail_off = (unsigned short)(j == 0 ? tail_off : 0);
-        r.tail_nv = (unsigned char)(j == 0 ? (chunk - tail_off) >> 3 : 0);
+        const int x0 = dj >= 0 ? chunk_p[dj] : st.tail[(long long)sid * st.tail_cap + j * hop];
+        int hi0, lo0;
+        tc3_split16(x0, hi0, lo0);
         int sl = slot0 + j;
         if (sl >= st.ring_rows) sl -= st.ring_rows;
-        r.slot = (unsigned char)sl;
-        *reinterpret_cast<int4*>(recs + off0 + j) = *reinterpret_cast<const int4*>(&r);
+        r.frame = chunk_p + dj;
+        r.tail = st.tail + (long long)sid * st.tail_cap;
+        r.row = st.ring + ((long long)sid * st.ring_rows + sl) * st.row_stride;
+        r.c_lo = __half_as_ushort(__float2half_rn(-(float)(1152 + lo0)));
+        r.c_hi = __half_as_ushort(__float2half_rn(-(9.f + (float)hi0 * 0.0078125f)));
+        r.len0c = (unsigned char)(dj < 0 ? min(used, -dj) >> 3 : 0);
+        r.tail_nv = (unsigned char)(j == 0 ? (chunk - tail_off) >> 3 : 0);
+        r.tail_delta = (unsigned short)(j == 0 ? (tail_off - dj) >> 3 : 0);
+        int4* dst = reinterpret_cast<int4*>(recs + off0 + j);
+        dst[0] = reinterpret_cast<const int4*>(&r)[0];
+        dst[1] = reinterpret_cast<const int4*>(&r)[1];
     }
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+constexpr int TC3_PART_STRIDE = 28;     // floats per epilogue thread in the partial-sum exchange (24 used; 112-byte rows: conflict-free 16-byte accesses)
+constexpr int TC3_LGM_STRIDE = 20;      // floats per frame in the log-mel exchange (80-byte rows: conflict-free 16-byte accesses)
+
 struct Tc3Smem {
     __half b2[2][8][64][8];                              // stage-2 matrix, pieces hi / lo
     __half b1[4][2][16][8];                              // stage-1 matrices (tc3_build_b1)
     unsigned char a1[8][2][TC3_A1_TILE];                 // stage-1 operands [group of 4 frames][piece hi / lo]
     unsigned char a2[2][2][TC3_SLOTS][TC3_A2_TILE];      // stage-2 operands [piece][K half][slot]
-    float part[21][256];                                 // mel sums (20) + total power of the 8 epilogue threads of every frame
-    float lgm[20][TC3_TILE];
+    float part[256][TC3_PART_STRIDE];                    // mel sums (20) + total power of the 8 epilogue threads of every frame
+    float lgm[TC3_TILE][TC3_LGM_STRIDE];                 // log-mel values of the tile's frames
     float c0v[TC3_TILE];
     float dct[TCD_MAX_OUT][24];
     Tc3Rec rec[TC3_REC_RING][TC3_TILE];
@@ -374,17 +389,16 @@ __device__ __forceinline__ void tc3_block_bins(uint32_t taddr, float x0f, float 
 
 template <class G>
 __global__ void __launch_bounds__(TC3_THREADS, 1)
-mfcc_tc3_kernel(const int16_t* __restrict__ pcm, int chunk, Tc3Tables tab, StreamState st, const Tc3Rec* __restrict__ recs,
-                unsigned int* __restrict__ counters, int parity, int dbg) {
+mfcc_tc3_kernel(Tc3Tables tab, const Tc3Rec* __restrict__ recs, unsigned int* __restrict__ counters, int parity, int dbg, long long* __restrict__ dbg_clk) {
     extern __shared__ __align__(128) unsigned char tc3_raw[];
     Tc3Smem& sm = *reinterpret_cast<Tc3Smem*>(tc3_raw);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int q4 = warp & 3, wg = warp >> 2;               // TMEM lane quadrant of this warp; warp group 0..3
+    const int q4 = warp & 3, wg = warp >> 2;               // TMEM lane quadrant of this warp; warp group 0..3 (workers)
     static_assert(G::n_filt == 20, "the epilogue distributes 20 filters over the eight threads of a frame");
 
     // ---- one-time set-up
     if (tid == 0) {
-        mbar_init(&sm.m1_done, 1); mbar_init(&sm.m2_done, 1); mbar_init(&sm.d1_free, TC3_THREADS);
+        mbar_init(&sm.m1_done, 1); mbar_init(&sm.m2_done, 1); mbar_init(&sm.d1_free, TC3_WORKERS);
         fence_mbar_init();
         sm.n_frames = counters[parity];
         if (blockIdx.x == 0) counters[parity ^ 1] = 0;        // the next tick's plan kernel counts from zero
@@ -410,271 +424,319 @@ mfcc_tc3_kernel(const int16_t* __restrict__ pcm, int chunk, Tc3Tables tab, Strea
     auto tile_of = [&](int k) { return (int)blockIdx.x + k * (int)gridDim.x; };
 
     // ---- helpers
-    // frame record of (tile k, frame f) from the list; an all-zero record with s = -1 marks the padding of the last tile
-    auto fetch_rec = [&](int k, int f) {
-        Tc3Rec r;
-        int4 v = make_int4(-1, 0, 0, 0);
+    // the two halves of the record of (tile k, frame f); frame == nullptr and the split constants of x0 = 0 pad the last tile
+    auto fetch_rec = [&](int k, int f, int4& a, int4& b) {
+        a = make_int4(0, 0, 0, 0); b = make_int4(0, 0, (int)0xC880E480u, 0);
         if (k < K) {
             const int idx = tile_of(k) * TC3_TILE + f;
-            if (idx < n_frames) v = __ldg(reinterpret_cast<const int4*>(recs + idx));
+            if (idx < n_frames) {
+                const int4* p = reinterpret_cast<const int4*>(recs + idx);
+                a = __ldg(p); b = __ldg(p + 1);
+            }
         }
-        *reinterpret_cast<int4*>(&r) = v;
-        return r;
     };
-    // the 16 bytes of chunk c (samples 8 c .. 8 c + 7) of a frame
-    auto chunk_src = [&](const Tc3Rec& r, int c) -> const uint4* {
-        const int o = 8 * c, len0 = r.dj < 0 ? min(512, -(int)r.dj) : 0;
-        const int16_t* p = o < len0 ? st.tail + (long long)r.sid * st.tail_cap + o : pcm + (long long)r.s * chunk + ((int)r.dj + o);
-        return reinterpret_cast<const uint4*>(p);
+    auto store_rec = [&](int k, int f, const int4& a, const int4& b) {
+        int4* p = reinterpret_cast<int4*>(&sm.rec[k & (TC3_REC_RING - 1)][f]);
+        p[0] = a; p[1] = b;
     };
-    const int c4 = lane >> 3, l8 = lane & 7;
-    uint4 pf[4];
-    // PCM of tile k into the prefetch registers: item = (frame, half), this lane's chunk = 32 half + 4 l8 + c4
+    // CONV: warp 8 + w8 converts frames 4 w8 .. 4 w8 + 3 of a tile; lane (c4, l8) owns chunks 4 l8 + c4 and 32 + 4 l8 + c4 (8 samples each).
+    const int c4 = lane >> 3, l8 = lane & 7, cch = 4 * l8 + c4;
+    uint4 pf[4][2];
     auto prefetch_tile = [&](int k) {
 #pragma unroll
         for (int m = 0; m < 4; ++m) {
-            const int it = warp + 16 * m, fi = it >> 1, hf = it & 1;
-            pf[m] = make_uint4(0u, 0u, 0u, 0u);
+            pf[m][0] = make_uint4(0u, 0u, 0u, 0u); pf[m][1] = pf[m][0];
             if (k < K) {
-                const Tc3Rec r = sm.rec[k & (TC3_REC_RING - 1)][fi];
-                if (r.s >= 0) pf[m] = __ldg(chunk_src(r, 32 * hf + 4 * l8 + c4));
+                const Tc3Rec& r = sm.rec[k & (TC3_REC_RING - 1)][4 * (warp - 8) + m];
+                const int16_t* fp = r.frame;
+                if (fp != nullptr) {
+                    const int l0 = r.len0c;
+                    const int16_t* tp = r.tail;
+                    pf[m][0] = *reinterpret_cast<const uint4*>((cch < l0 ? tp : fp) + 8 * cch);
+                    pf[m][1] = *reinterpret_cast<const uint4*>((cch + 32 < l0 ? tp : fp) + 8 * (cch + 32));
+                }
             }
         }
     };
-    // CONV: prefetch registers -> stage-1 operand tiles (exact split of x - x0 into fp16 pieces)
+    // prefetch registers -> stage-1 operand tiles (exact split of x - x0 into fp16 pieces)
     auto conv_tile = [&](int k) {
 #pragma unroll
         for (int m = 0; m < 4; ++m) {
-            const int it = warp + 16 * m, fi = it >> 1, hf = it & 1;
-            const Tc3Rec r = sm.rec[k & (TC3_REC_RING - 1)][fi];
-            int hi0, lo0;
-            tc3_split16(r.s >= 0 ? (int)r.x0 : 0, hi0, lo0);
-            const __half2 clo = __float2half2_rn(-(float)(1152 + lo0));
-            const __half2 chi = __float2half2_rn(-(9.f + (float)hi0 * 0.0078125f));
-            const uint32_t c_lo = *reinterpret_cast<const uint32_t*>(&clo), c_hi = *reinterpret_cast<const uint32_t*>(&chi);
-            const uint32_t w[4] = {pf[m].x, pf[m].y, pf[m].z, pf[m].w};
-            uint32_t ah[4], al[4];
+            const int fi = 4 * (warp - 8) + m;
+            const uint32_t cc = *reinterpret_cast<const uint32_t*>(&sm.rec[k & (TC3_REC_RING - 1)][fi].c_lo);     // c_lo | c_hi << 16
+            const uint32_t c_lo = __byte_perm(cc, 0, 0x1010), c_hi = __byte_perm(cc, 0, 0x3232);
+            unsigned char* dst = &sm.a1[fi >> 2][0][0] + (4 * (fi & 3) + c4) * 128 + l8 * 16;
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const uint32_t vx = w[e] ^ 0x80008000u;
-                const uint32_t lo_magic = (vx & 0x00FF00FFu) ^ 0x64806480u;         // 1024 + (lo ^ 0x80)
-                al[e] = tc3_hadd2(lo_magic, c_lo);                                    // lo_b - lo0
-                const uint32_t hi_magic = __byte_perm(vx, 0x64646464u, 0x4341);       // 1024 + hi + 128
-                const uint32_t mb = w[e] & 0x00800080u;                               // bit 7 of the low byte as fp16 subnormal 2^-17
-                const uint32_t t = tc3_hfma2(hi_magic, 0x20002000u, c_hi);            // (hi_floor - hi0) / 128   (0x2000 = 2^-7)
-                ah[e] = tc3_hfma2(mb, 0x64006400u, t);                                // + carry / 128            (0x6400 = 1024)
-            }
-            unsigned char* dst = &sm.a1[fi >> 2][0][0] + hf * 2048 + (4 * (fi & 3) + c4) * 128 + l8 * 16;
-            *reinterpret_cast<uint4*>(dst) = make_uint4(ah[0], ah[1], ah[2], ah[3]);
-            *reinterpret_cast<uint4*>(dst + TC3_A1_TILE) = make_uint4(al[0], al[1], al[2], al[3]);
-        }
-    };
-    // MMA issue (one thread)
-    const uint32_t idesc1 = tc3_idesc(16, true), idesc2 = tc3_idesc(64, false);
-    auto issue_mma1 = [&]() {
-        const uint32_t a_lbo = (dbg & 1) ? 128u : 2048u, a_sbo = (dbg & 1) ? 2048u : 128u;
-        uint64_t db[4];
+            for (int hf = 0; hf < 2; ++hf) {
+                const uint32_t w[4] = {pf[m][hf].x, pf[m][hf].y, pf[m][hf].z, pf[m][hf].w};
+                uint32_t ah[4], al[4];
 #pragma unroll
-        for (int v = 0; v < 4; ++v) db[v] = tc5_desc(&sm.b1[v][0][0][0], 256, 128);
-#pragma unroll 1
-        for (int i = 0; i < 8; ++i) {
-            const uint64_t dah = tc5_desc(&sm.a1[i][0][0], a_lbo, a_sbo), dal = tc5_desc(&sm.a1[i][1][0], a_lbo, a_sbo);
-            const uint32_t d = tmem + 16 * i;
-            tcd_mma(d, dal, db[3], idesc1, 0);
-            tcd_mma(d, dal, db[2], idesc1, 1);
-            tcd_mma(d, dah, db[1], idesc1, 1);
-            tcd_mma(d, dah, db[0], idesc1, 1);
-        }
-        tc5_commit(&sm.m1_done);
-    };
-    auto issue_mma2 = [&](int k) {
-        const uint32_t dcol = tmem + TC3_D1_COLS + (k & 1) * TC3_D2_COLS;
-#pragma unroll 1
-        for (int stage = 0; stage < 2; ++stage) {
-            const uint64_t da_hi = tc5_desc(&sm.a2[0][stage][0][0], TC3_A2_LBO, 128), da_lo = tc5_desc(&sm.a2[1][stage][0][0], TC3_A2_LBO, 128);
-            const uint64_t db_hi = tc5_desc(&sm.b2[0][4 * stage][0][0], 1024, 128), db_lo = tc5_desc(&sm.b2[1][4 * stage][0][0], 1024, 128);
-#pragma unroll
-            for (int kk = 0; kk < 2; ++kk)
-#pragma unroll
-                for (int s = 0; s < TC3_SLOTS; ++s) {
-                    const uint64_t off = (uint64_t)((s * TC3_A2_TILE + 2 * kk * TC3_A2_LBO) >> 4);
-                    const uint64_t dbh = db_hi + (uint64_t)(2 * kk * 64), dbl = db_lo + (uint64_t)(2 * kk * 64);
-                    const uint32_t d = dcol + 64 * s;
-                    tcd_mma(d, da_lo + off, dbh, idesc2, (stage | kk) != 0);
-                    tcd_mma(d, da_hi + off, dbl, idesc2, 1);
-                    tcd_mma(d, da_hi + off, dbh, idesc2, 1);
+                for (int e = 0; e < 4; ++e) {
+                    const uint32_t vx = w[e] ^ 0x80008000u;
+                    const uint32_t lo_magic = (vx & 0x00FF00FFu) ^ 0x64806480u;         // 1024 + (lo ^ 0x80)
+                    al[e] = tc3_hadd2(lo_magic, c_lo);                                    // lo_b - lo0
+                    const uint32_t hi_magic = __byte_perm(vx, 0x64646464u, 0x4341);       // 1024 + hi + 128
+                    const uint32_t mb = w[e] & 0x00800080u;                               // bit 7 of the low byte as fp16 subnormal 2^-17
+                    const uint32_t t = tc3_hfma2(hi_magic, 0x20002000u, c_hi);            // (hi_floor - hi0) / 128   (0x2000 = 2^-7)
+                    ah[e] = tc3_hfma2(mb, 0x64006400u, t);                                // + carry / 128            (0x6400 = 1024)
                 }
+                *reinterpret_cast<uint4*>(dst + hf * 2048) = make_uint4(ah[0], ah[1], ah[2], ah[3]);
+                *reinterpret_cast<uint4*>(dst + hf * 2048 + TC3_A1_TILE) = make_uint4(al[0], al[1], al[2], al[3]);
+            }
         }
-        tc5_commit(&sm.m2_done);
     };
 
     // ---- prologue: records of tiles 0, 1; PCM of tile 0
-    if (tid < 2 * TC3_TILE) sm.rec[tid >> 5][lane] = fetch_rec(tid >> 5, lane);
+    if (tid < 2 * TC3_TILE) {
+        int4 a, b;
+        fetch_rec(tid >> 5, lane, a, b);
+        store_rec(tid >> 5, lane, a, b);
+    }
     __syncthreads();
-    prefetch_tile(0);
+    if (warp >= 8 && warp < 16) prefetch_tile(0);
 
     // Per-lane stage-2 store offset (INT): input n2 = lane -> K half (lane >> 4), K-group ((lane >> 2) & 3), 4-byte word (lane & 3)
     const uint32_t int_lane_off = (uint32_t)((lane >> 4) * (TC3_SLOTS * TC3_A2_TILE) + ((lane >> 2) & 3) * TC3_A2_LBO + (lane & 3) * 4);
     constexpr uint32_t A2_PIECE = 2 * TC3_SLOTS * TC3_A2_TILE;
 
+    if (warp == 16) {
+        // ================= the MMA-issuing warp: after INT(k), stage 1 of tile k + 1 and stage 2 of tile k
+        const uint32_t idesc1 = tc3_idesc(16, true), idesc2 = tc3_idesc(64, false);
+        const uint32_t a_lbo = 2048u, a_sbo = 128u;             // MN-major operand: K-group stride, 8-row-group stride
+        const bool itimed = dbg_clk != nullptr && blockIdx.x == 0 && lane == 0 && dbg == 116;
+        long long ti1 = 0, ti2 = 0, tc2w = 0, tq = 0;
 #pragma unroll 1
-    for (int k = -2; k <= K; ++k) {
-        // ================= INT(k): stage-1 result -> twiddle -> split -> stage-2 operand
-        if (k >= 0 && k < K) {
-            mbar_wait(&sm.m1_done, k & 1);
-            tc5_fence_after();
-            uint32_t wh[2][9], wl[2][9];
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                const int i = 2 * wg + u;
-                uint32_t yv[16];
-                tc3_ld16(tmem + ((uint32_t)(q4 * 32) << 16) + 16 * i, yv);
-                tc3_wait_ld16(yv);
-                if (u == 1) {                                    // both groups read: the stage-1 accumulators may be overwritten
-                    tc5_fence_before();
-                    mbar_arrive(&sm.d1_free);
-                    if (tid == 0) {
-                        mbar_wait(&sm.d1_free, k & 1);
-                        if (k + 1 < K) { tc5_fence_after(); issue_mma1(); }
-                    }
-                }
-                float y[16], zr[9], zi[9];
-#pragma unroll
-                for (int e = 0; e < 16; ++e) y[e] = __uint_as_float(yv[e]);
-                tc3_twiddle(y, tw, zr, zi);
-#pragma unroll
-                for (int b = 0; b < TCD_BLOCKS; ++b) {
-                    const __half2 hh = __floats2half2_rn(zr[b], zi[b]);
-                    const float2 hf = __half22float2(hh);
-                    const __half2 ll = __floats2half2_rn(zr[b] - hf.x, zi[b] - hf.y);
-                    wh[u][b] = *reinterpret_cast<const uint32_t*>(&hh);
-                    wl[u][b] = *reinterpret_cast<const uint32_t*>(&ll);
-                }
-            }
-            if (k >= 1) mbar_wait(&sm.m2_done, (k - 1) & 1);     // the tensor core has read the previous tile's operands
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                const int fr = 4 * (2 * wg + u) + q4;
-                unsigned char* base = &sm.a2[0][0][0][0] + int_lane_off + fr * 16;
-#pragma unroll
-                for (int b = 0; b < TCD_BLOCKS; ++b) {
-                    const int o = tc3_blk_s(b) * TC3_A2_TILE + 32 * tc3_blk_h(b) * 16;
-                    *reinterpret_cast<uint32_t*>(base + o) = wh[u][b];
-                    *reinterpret_cast<uint32_t*>(base + A2_PIECE + o) = wl[u][b];
-                }
-            }
-            fence_proxy_async();
-        }
-        __syncthreads();                                         // (A)
-        if (k >= 0 && k < K && tid == 0) { tc5_fence_after(); issue_mma2(k); }
-
-        // ================= P(k)
-        // CONV(k + 2), then the PCM of tile k + 3 into the prefetch registers
-        if (k + 2 < K) {
-            if (k + 2 >= 1) mbar_wait(&sm.m1_done, (k + 1) & 1); // stage 1 of tile k + 1 has read the operand buffer
-            conv_tile(k + 2);
-            fence_proxy_async();
-        }
-        prefetch_tile(k + 3);
-        if (warp < 8) {
-            // ---- EPI(k - 1): row (frame = lane, h = q4), part wg: one 64-column block (row 3, part 1: blocks 0 and 8)
-            if (k >= 1) {
-                const int ke = k - 1;
-                if (k == K) mbar_wait(&sm.m2_done, ke & 1);
+        for (int k = -2; k <= K; ++k) {
+            if (lane == 0 && k + 1 >= 0 && k + 1 < K) {
+                if (k >= 0) mbar_wait(&sm.d1_free, k & 1);       // every worker has read tile k's stage-1 accumulators
+                if (itimed) tq = clock64();
                 tc5_fence_after();
-                const Tc3Rec r = sm.rec[ke & (TC3_REC_RING - 1)][lane];
-                const float x0f = (float)r.x0;
-                const uint32_t t_row = tmem + ((uint32_t)(q4 * 32) << 16) + TC3_D1_COLS + (ke & 1) * TC3_D2_COLS;
-                float rise[G::n_filt + 1], seg[G::n_filt + 1];
+                uint64_t db[4];
 #pragma unroll
-                for (int j = 0; j <= G::n_filt; ++j) { rise[j] = 0.f; seg[j] = 0.f; }
-                if (wg == 0) {
-                    if (q4 == 0) tc3_block_bins<G, 1>(t_row, x0f, rise, seg);
-                    else if (q4 == 1) tc3_block_bins<G, 3>(t_row, x0f, rise, seg);
-                    else if (q4 == 2) tc3_block_bins<G, 5>(t_row, x0f, rise, seg);
-                    else tc3_block_bins<G, 7>(t_row, x0f, rise, seg);
-                } else {
-                    if (q4 == 0) tc3_block_bins<G, 2>(t_row + 64, x0f, rise, seg);
-                    else if (q4 == 1) tc3_block_bins<G, 4>(t_row + 64, x0f, rise, seg);
-                    else if (q4 == 2) tc3_block_bins<G, 6>(t_row + 64, x0f, rise, seg);
-                    else { tc3_block_bins<G, 0>(t_row + 64, x0f, rise, seg); tc3_block_bins<G, 8>(t_row + 128, x0f, rise, seg); }
+                for (int v = 0; v < 4; ++v) db[v] = tc5_desc(&sm.b1[v][0][0][0], 256, 128);
+#pragma unroll 1
+                for (int i = 0; i < 8; ++i) {
+                    const uint64_t dah = tc5_desc(&sm.a1[i][0][0], a_lbo, a_sbo), dal = tc5_desc(&sm.a1[i][1][0], a_lbo, a_sbo);
+                    const uint32_t d = tmem + 16 * i;
+                    tcd_mma(d, dal, db[3], idesc1, 0);
+                    tcd_mma(d, dal, db[2], idesc1, 1);
+                    tcd_mma(d, dah, db[1], idesc1, 1);
+                    tcd_mma(d, dah, db[0], idesc1, 1);
                 }
+                tc5_commit(&sm.m1_done);
+                if (itimed) ti1 += clock64() - tq;
+            }
+            __syncwarp();
+            __syncthreads();                                     // (A)
+            if (lane == 0) {
+                if (itimed) tq = clock64();
+                tc5_fence_after();
+                if (k >= 0 && k < K) {
+                    const uint32_t dcol = tmem + TC3_D1_COLS + (k & 1) * TC3_D2_COLS;
+#pragma unroll 1
+                    for (int stage = 0; stage < 2; ++stage) {
+                        const uint64_t da_hi = tc5_desc(&sm.a2[0][stage][0][0], TC3_A2_LBO, 128), da_lo = tc5_desc(&sm.a2[1][stage][0][0], TC3_A2_LBO, 128);
+                        const uint64_t db_hi = tc5_desc(&sm.b2[0][4 * stage][0][0], 1024, 128), db_lo = tc5_desc(&sm.b2[1][4 * stage][0][0], 1024, 128);
+#pragma unroll
+                        for (int kk = 0; kk < 2; ++kk)
+#pragma unroll
+                            for (int s = 0; s < TC3_SLOTS; ++s) {
+                                const uint64_t off = (uint64_t)((s * TC3_A2_TILE + 2 * kk * TC3_A2_LBO) >> 4);
+                                const uint64_t dbh = db_hi + (uint64_t)(2 * kk * 64), dbl = db_lo + (uint64_t)(2 * kk * 64);
+                                const uint32_t d = dcol + 64 * s;
+                                tcd_mma(d, da_lo + off, dbh, idesc2, (stage | kk) != 0);
+                                tcd_mma(d, da_hi + off, dbl, idesc2, 1);
+                                tcd_mma(d, da_hi + off, dbh, idesc2, 1);
+                            }
+                    }
+                    tc5_commit(&sm.m2_done);
+                    if (itimed) { const long long t = clock64(); ti2 += t - tq; mbar_wait(&sm.m2_done, k & 1); tc2w += clock64() - t; }
+                }
+            }
+            __syncwarp();
+            __syncthreads();                                     // (B)
+        }
+        if (itimed) { dbg_clk[0] = ti1; dbg_clk[1] = ti2; dbg_clk[2] = tc2w; dbg_clk[3] = K; }
+    } else {
+        // optional timeline of one warp of CTA 0 (pb_debug_counters): cycles in INT, waiting at (A), in P, waiting at (B)
+        const bool timed = dbg_clk != nullptr && dbg >= 100 && blockIdx.x == 0 && lane == 0 && warp == dbg - 100;
+        long long t_int = 0, t_wa = 0, t_p = 0, t_wb = 0, t0 = 0, t1 = 0;
+#pragma unroll 1
+        for (int k = -2; k <= K; ++k) {
+            if (timed) t0 = clock64();
+            // ================= INT(k): stage-1 result -> twiddle -> split -> stage-2 operand
+            if (k >= 0 && k < K) {
+                mbar_wait(&sm.m1_done, k & 1);
+                tc5_fence_after();
+                uint32_t wh[2][9], wl[2][9];
+                uint32_t yv[2][16];
+                tc3_ld16(tmem + ((uint32_t)(q4 * 32) << 16) + 32 * wg, yv[0]);
+                tc3_ld16(tmem + ((uint32_t)(q4 * 32) << 16) + 32 * wg + 16, yv[1]);
+                tc3_wait_ld16(yv[0]);
+                tc3_wait_ld16(yv[1]);
                 tc5_fence_before();
-                // this thread's share of the 20 mel sums and of the total power
-                const int et = tid;                              // 0..255
-                float tot = seg[0];
+                mbar_arrive(&sm.d1_free);                        // the stage-1 accumulators may be overwritten
 #pragma unroll
-                for (int j = 0; j < G::n_filt; ++j) {
-                    const float fall = j + 1 < G::n_filt ? seg[j + 1] - rise[j + 1] : rise[G::n_filt];
-                    sm.part[j][et] = rise[j] + fall;
-                    tot += seg[j + 1];
-                }
-                sm.part[G::n_filt][et] = tot;
-                asm volatile("bar.sync 1, 256;" ::: "memory");
-                const int t8 = q4 + 4 * wg;                      // 0..7: filters t8, t8 + 8, t8 + 16
+                for (int u = 0; u < 2; ++u) {
+                    float y[16], zr[9], zi[9];
 #pragma unroll
-                for (int u = 0; u < 3; ++u) {
-                    const int j = t8 + 8 * u;
-                    if (j <= G::n_filt && (j < G::n_filt || t8 == 4)) {
-                        float m8 = 0.f;
+                    for (int e = 0; e < 16; ++e) y[e] = __uint_as_float(yv[u][e]);
+                    tc3_twiddle(y, tw, zr, zi);
 #pragma unroll
-                        for (int v = 0; v < 8; ++v) m8 += sm.part[j][32 * v + lane];
-                        const float lg = __logf(fmaxf(m8 * tab.pscale, K1_EPS));
-                        if (j < G::n_filt) sm.lgm[j][lane] = lg; else sm.c0v[lane] = lg;
+                    for (int b = 0; b < TCD_BLOCKS; ++b) {
+                        const __half2 hh = __floats2half2_rn(zr[b], zi[b]);
+                        const float2 hf = __half22float2(hh);
+                        const __half2 ll = __floats2half2_rn(zr[b] - hf.x, zi[b] - hf.y);
+                        wh[u][b] = *reinterpret_cast<const uint32_t*>(&hh);
+                        wl[u][b] = *reinterpret_cast<const uint32_t*>(&ll);
                     }
                 }
-                asm volatile("bar.sync 1, 256;" ::: "memory");
-                if (r.s >= 0) {
-                    float* rowp = st.ring + ((long long)r.sid * st.ring_rows + r.slot) * st.row_stride;
-                    float lg[G::n_filt];
+                if (k >= 1) mbar_wait(&sm.m2_done, (k - 1) & 1); // the tensor core has read the previous tile's operands
 #pragma unroll
-                    for (int q = 0; q < G::n_filt; ++q) lg[q] = sm.lgm[q][lane];
-                    for (int o = t8; o < tab.n_out; o += 8) {
-                        const float4* d4 = reinterpret_cast<const float4*>(sm.dct[o]);
-                        float v0 = 0.f, v1 = 0.f;
+                for (int u = 0; u < 2; ++u) {
+                    const int fr = 4 * (2 * wg + u) + q4;
+                    unsigned char* base = &sm.a2[0][0][0][0] + int_lane_off + fr * 16;
+#pragma unroll
+                    for (int b = 0; b < TCD_BLOCKS; ++b) {
+                        const int o = tc3_blk_s(b) * TC3_A2_TILE + 32 * tc3_blk_h(b) * 16;
+                        *reinterpret_cast<uint32_t*>(base + o) = wh[u][b];
+                        *reinterpret_cast<uint32_t*>(base + A2_PIECE + o) = wl[u][b];
+                    }
+                }
+                fence_proxy_async();
+            }
+            if (timed) { t1 = clock64(); t_int += t1 - t0; }
+            __syncthreads();                                     // (A)
+            if (timed) { t0 = clock64(); t_wa += t0 - t1; }
+
+            // ================= P(k)
+            if (warp < 8) {
+                // ---- EPI(k - 1): row (frame = lane, h = q4), part wg: one 64-column block (row 3, part 1: blocks 0 and 8)
+                if (k >= 1) {
+                    const int ke = k - 1;
+                    if (k == K) mbar_wait(&sm.m2_done, ke & 1);
+                    tc5_fence_after();
+                    const Tc3Rec& r = sm.rec[ke & (TC3_REC_RING - 1)][lane];
+                    // x0 = 256 hi0 + lo0 from the split constants: lo0 = -c_lo - 1152, hi0 / 128 = -c_hi - 9
+                    const float x0f = fmaf(-32768.f, __half2float(__ushort_as_half(r.c_hi)) + 9.f, -__half2float(__ushort_as_half(r.c_lo)) - 1152.f);
+                    const uint32_t t_row = tmem + ((uint32_t)(q4 * 32) << 16) + TC3_D1_COLS + (ke & 1) * TC3_D2_COLS;
+                    float rise[G::n_filt + 1], seg[G::n_filt + 1];
+#pragma unroll
+                    for (int j = 0; j <= G::n_filt; ++j) { rise[j] = 0.f; seg[j] = 0.f; }
+                    if (wg == 0) {
+                        if (q4 == 0) tc3_block_bins<G, 1>(t_row, x0f, rise, seg);
+                        else if (q4 == 1) tc3_block_bins<G, 3>(t_row, x0f, rise, seg);
+                        else if (q4 == 2) tc3_block_bins<G, 5>(t_row, x0f, rise, seg);
+                        else tc3_block_bins<G, 7>(t_row, x0f, rise, seg);
+                    } else {
+                        if (q4 == 0) tc3_block_bins<G, 2>(t_row + 64, x0f, rise, seg);
+                        else if (q4 == 1) tc3_block_bins<G, 4>(t_row + 64, x0f, rise, seg);
+                        else if (q4 == 2) tc3_block_bins<G, 6>(t_row + 64, x0f, rise, seg);
+                        else { tc3_block_bins<G, 0>(t_row + 64, x0f, rise, seg); tc3_block_bins<G, 8>(t_row + 128, x0f, rise, seg); }
+                    }
+                    tc5_fence_before();
+                    // this thread's share of the 20 mel sums and of the total power: one row of the exchange buffer, six 16-byte stores
+                    {
+                        float pv[24];
+                        float tot = seg[0];
+#pragma unroll
+                        for (int j = 0; j < G::n_filt; ++j) {
+                            const float fall = j + 1 < G::n_filt ? seg[j + 1] - rise[j + 1] : rise[G::n_filt];
+                            pv[j] = rise[j] + fall;
+                            tot += seg[j + 1];
+                        }
+                        pv[20] = tot; pv[21] = 0.f; pv[22] = 0.f; pv[23] = 0.f;
+                        float4* pr = reinterpret_cast<float4*>(sm.part[tid]);
+#pragma unroll
+                        for (int q = 0; q < 6; ++q) pr[q] = make_float4(pv[4 * q], pv[4 * q + 1], pv[4 * q + 2], pv[4 * q + 3]);
+                    }
+                    asm volatile("bar.sync 1, 256;" ::: "memory");
+                    const int t8 = q4 + 4 * wg;                  // 0..7: thread t8 < 5 sums and logs filters 4 t8 .. 4 t8 + 3, thread 5 the total power
+                    if (t8 < 6) {
+                        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                        for (int v = 0; v < 8; ++v) {
+                            const float4 a = *reinterpret_cast<const float4*>(&sm.part[32 * v + lane][4 * t8]);
+                            acc.x += a.x; acc.y += a.y; acc.z += a.z; acc.w += a.w;
+                        }
+                        if (t8 < 5) {
+                            float4 lg;
+                            lg.x = __logf(fmaxf(acc.x * tab.pscale, K1_EPS)); lg.y = __logf(fmaxf(acc.y * tab.pscale, K1_EPS));
+                            lg.z = __logf(fmaxf(acc.z * tab.pscale, K1_EPS)); lg.w = __logf(fmaxf(acc.w * tab.pscale, K1_EPS));
+                            *reinterpret_cast<float4*>(&sm.lgm[lane][4 * t8]) = lg;
+                        } else {
+                            sm.c0v[lane] = __logf(fmaxf(acc.x * tab.pscale, K1_EPS));
+                        }
+                    }
+                    asm volatile("bar.sync 1, 256;" ::: "memory");
+                    if (r.frame != nullptr) {
+                        float* rowp = r.row;
+                        float lg[G::n_filt];
 #pragma unroll
                         for (int q = 0; q < G::n_filt / 4; ++q) {
-                            const float4 dd = d4[q];
-                            v0 = fmaf(dd.x, lg[4 * q], v0); v1 = fmaf(dd.y, lg[4 * q + 1], v1);
-                            v0 = fmaf(dd.z, lg[4 * q + 2], v0); v1 = fmaf(dd.w, lg[4 * q + 3], v1);
+                            const float4 a = *reinterpret_cast<const float4*>(&sm.lgm[lane][4 * q]);
+                            lg[4 * q] = a.x; lg[4 * q + 1] = a.y; lg[4 * q + 2] = a.z; lg[4 * q + 3] = a.w;
                         }
-                        rowp[o] = o == 0 ? sm.c0v[lane] : v0 + v1;
-                    }
-                }
-            }
-        } else {
-            // ---- new tails of tile k + 2 (its frames' old tails are in registers or consumed): warp w8 takes frames 4 w8 .. 4 w8 + 3
-            if (k + 2 < K) {
-                const int w8 = warp - 8;
+                        for (int o = t8; o < tab.n_out; o += 8) {
+                            const float4* d4 = reinterpret_cast<const float4*>(sm.dct[o]);
+                            float v0 = 0.f, v1 = 0.f;
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const Tc3Rec r = sm.rec[(k + 2) & (TC3_REC_RING - 1)][4 * w8 + u];
-                    const int nv = r.s >= 0 ? (int)r.tail_nv : 0;
-                    if (nv > 0) {
-                        const uint4* src = reinterpret_cast<const uint4*>(pcm + (long long)r.s * chunk + r.tail_off);
-                        uint4* dst = reinterpret_cast<uint4*>(st.tail + (long long)r.sid * st.tail_cap);
-                        uint4 v0, v1;
-                        if (lane < nv) v0 = __ldg(src + lane);
-                        if (lane + 32 < nv) v1 = __ldg(src + lane + 32);
-                        if (lane < nv) dst[lane] = v0;
-                        if (lane + 32 < nv) dst[lane + 32] = v1;
+                            for (int q = 0; q < G::n_filt / 4; ++q) {
+                                const float4 dd = d4[q];
+                                v0 = fmaf(dd.x, lg[4 * q], v0); v1 = fmaf(dd.y, lg[4 * q + 1], v1);
+                                v0 = fmaf(dd.z, lg[4 * q + 2], v0); v1 = fmaf(dd.w, lg[4 * q + 3], v1);
+                            }
+                            rowp[o] = o == 0 ? sm.c0v[lane] : v0 + v1;
+                        }
                     }
                 }
-            }
-            // ---- frame records of tile k + 4 (warp 15), with an L2 prefetch of everything that tile will read
-            if (warp == 15) {
-                const Tc3Rec r = fetch_rec(k + 4, lane);
-                if (r.s >= 0) {
-                    const int len0 = r.dj < 0 ? min(512, -(int)r.dj) : 0;
-                    if (len0 > 0) tc3_l2_prefetch(st.tail + (long long)r.sid * st.tail_cap, 2u * len0);
-                    if (len0 < 512) tc3_l2_prefetch(pcm + (long long)r.s * chunk + ((int)r.dj + len0), 2u * (512 - len0));
-                    if (r.tail_nv) tc3_l2_prefetch(pcm + (long long)r.s * chunk + r.tail_off, 16u * r.tail_nv);
+            } else {
+                // ---- new tails of tile k + 1 (converted one phase ago: the old tails are no longer needed): warp w8 takes frames 4 w8 .. 4 w8 + 3
+                if (k + 1 >= 0 && k + 1 < K) {
+                    const int w8 = warp - 8;
+                    uint4 tv[4][2];
+                    uint4* tdst[4];
+                    int tnv[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {                // all loads first: one memory latency, not four
+                        const Tc3Rec& r = sm.rec[(k + 1) & (TC3_REC_RING - 1)][4 * w8 + u];
+                        tnv[u] = r.frame != nullptr ? (int)r.tail_nv : 0;
+                        tdst[u] = reinterpret_cast<uint4*>(r.tail);
+                        const uint4* src = reinterpret_cast<const uint4*>(r.frame + 8 * (int)r.tail_delta);
+                        if (lane < tnv[u]) tv[u][0] = __ldg(src + lane);
+                        if (lane + 32 < tnv[u]) tv[u][1] = __ldg(src + lane + 32);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        if (lane < tnv[u]) tdst[u][lane] = tv[u][0];
+                        if (lane + 32 < tnv[u]) tdst[u][lane + 32] = tv[u][1];
+                    }
                 }
-                sm.rec[(k + 4) & (TC3_REC_RING - 1)][lane] = r;
+                // ---- frame records of tile k + 4 (warp 15), with an L2 prefetch of everything that tile will read
+                if (warp == 15) {
+                    int4 a, b;
+                    fetch_rec(k + 4, lane, a, b);
+                    Tc3Rec r;
+                    reinterpret_cast<int4*>(&r)[0] = a; reinterpret_cast<int4*>(&r)[1] = b;
+                    if (r.frame != nullptr && (dbg & 4)) {      // per-line L2 prefetch of the frame (a per-lane bulk prefetch serialises: 10 k cycles per tile)
+                        const char* fp = reinterpret_cast<const char*>(r.frame) + 16 * (int)r.len0c;
+                        for (int o = 0; o < 16 * (64 - (int)r.len0c); o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(fp + o));
+                    }
+                    store_rec(k + 4, lane, a, b);
+                }
+                // ---- CONV(k + 2), then the PCM of tile k + 3 into the prefetch registers
+                if (k + 2 < K) {
+                    if (k + 2 >= 1) mbar_wait(&sm.m1_done, (k + 1) & 1);     // stage 1 of tile k + 1 has read the operand buffer
+                    conv_tile(k + 2);
+                    fence_proxy_async();
+                }
+                prefetch_tile(k + 3);
             }
+            if (timed) { t1 = clock64(); t_p += t1 - t0; }
+            __syncthreads();                                     // (B)
+            if (timed) t_wb += clock64() - t1;
         }
-        __syncthreads();                                         // (B)
-        if (k == -2 && K > 0 && tid == 0) { tc5_fence_after(); issue_mma1(); }
+        if (timed) { dbg_clk[0] = t_int; dbg_clk[1] = t_wa; dbg_clk[2] = t_p; dbg_clk[3] = t_wb; }
     }
     tc5_fence_before();
     __syncthreads();

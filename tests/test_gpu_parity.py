@@ -648,12 +648,11 @@ def test_runner_plugin_predict_shape():
     assert abs(r.run(x[2]) - p[2, 0]) < 1e-7
 
 
-@pytest.mark.skipif(os.environ.get('PB_TEST_TC_K1') != '1',
-                    reason='opt-in MFCC kernels (tensor-core DFT, lean set-up): not yet validated on hardware; set PB_TEST_TC_K1=1')
-@pytest.mark.parametrize('k1_mode', [2, 4, 5, 6], ids=['lean_setup', 'tensor_core', 'tensor_core_two_stage', 'two_stage_desc_swapped'])
-def test_experimental_mfcc_tick(k1_mode):
-    """pb_debug_k1_mode: 1 = windows produced by the tcgen05 DFT kernel, 2 = fast kernel with the 32-bit per-pass set-up,
-    against the default kernels (mode 2 must be bit-identical: same arithmetic, different address computation)."""
+@pytest.mark.parametrize('k1_mode', [3, 4, 5], ids=['fft_64bit_setup', 'tensor_core', 'tensor_core_two_stage'])
+def test_alternative_mfcc_tick_kernels(k1_mode):
+    """pb_debug_k1_mode against the default kernel (FFT on the CUDA cores, 32-bit per-pass set-up): 3 = the same kernel with its
+    original 64-bit set-up (must be bit-identical: same arithmetic, different address computation), 4 = stage 2 of the DFT on
+    tcgen05 (mfcc_tc2), 5 = both stages on tcgen05 from exactly split int16 samples (mfcc_tc3).  All validated on B200."""
     m = _mod()
     chunk, S, K = 1024, 300, 40
     pcm = noise(S, K * chunk, seed=51)
@@ -667,17 +666,53 @@ def test_experimental_mfcc_tick(k1_mode):
         a, b = ref.update(c), tc.update(c)
         wa, wb = ref.core.read_window(S).cpu().numpy(), tc.core.read_window(S).cpu().numpy()
         per = np.abs(wa - wb).reshape(S, -1).max(1)
-        print('tick', k, 'worst streams', np.argsort(per)[-4:], per[np.argsort(per)[-4:]])
         assert np.max(per) < 2e-4, k
-        if k1_mode == 2:
+        if k1_mode == 3:
             assert np.array_equal(wa, wb), k
         assert np.max(np.abs(a['raw'].cpu().numpy() - b['raw'].cpu().numpy())) < 1e-4, k
     ref.core.close(); tc.core.close()
 
 
-@pytest.mark.skipif(os.environ.get('PB_TEST_TC_K1') != '1',
-                    reason='opt-in tcgen05 scan over cached projections (pb_debug_gru_mode 8): not yet validated on hardware')
-def test_experimental_tcgen05_scan_over_cached_projections():
+@pytest.mark.parametrize('chunk', [1024, 800, 2000, 1600])
+def test_two_stage_tensor_core_mfcc_vs_oracle_ragged(chunk):
+    """k1 mode 5 (mfcc_tc3: plan kernel + both DFT stages on tcgen05) against independent oracle Listeners: windows after every
+    tick, with streams of different ages in one batch (id subsets skip ticks), several frames per tick (chunk 1600 / 2000), silent,
+    full-scale DC, near-silent and boundary-hovering streams, and a partial last tile (frames not a multiple of 32)."""
+    import torch
+    m = _mod()
+    S, K = 77, max(10, 24000 // chunk)
+    pcm = noise(S, K * chunk, seed=chunk + 5)
+    pcm[5] = 0
+    pcm[6] = 32767
+    pcm[7] = -32768
+    rs = np.random.RandomState(3)
+    pcm[8] = np.round(rs.randn(K * chunk) * 1.5)
+    pcm[9] = 128 + np.round(rs.randn(K * chunk) * 2)
+    pcm[10] = -20000 + np.round(rs.randn(K * chunk) * 300)
+    model = m.GruModel.random(13, 20, seed=0, scale=0.1)
+    sb = m.StreamBatch(model, S, chunk_samples=chunk)
+    sb.core.k1_mode(5)
+    opr = OracleParams()
+    w = og.GruWeights(model.kernel, model.recurrent, model.bias, model.dense_w, model.dense_b)
+    lis = [OracleListener(w, opr) for _ in range(S)]
+    fed = np.zeros(S, int)                         # chunks each stream has consumed
+    worst = 0.0
+    for k in range(K):
+        # even ticks: every stream; odd ticks: a shuffled subset (the others fall behind -> different ages / tails)
+        ids = np.arange(S) if k % 2 == 0 else rs.permutation(S)[:S // 2 + k % 5]
+        c = np.stack([pcm[i, fed[i] * chunk:(fed[i] + 1) * chunk] for i in ids])
+        sb.update(cuda(c), ids=torch.from_numpy(ids.astype(np.int32)).cuda())
+        win = sb.core.read_window(S).cpu().numpy()
+        for j, i in enumerate(ids):
+            ow = lis[i].update_vectors(c[j].astype(np.float32) / 32768.0)
+            worst = max(worst, float(np.max(np.abs(win[i] - ow))))
+            fed[i] += 1
+    print('chunk', chunk, 'max |window - oracle|', worst)
+    assert worst < 2e-4
+    sb.core.close()
+
+
+def test_tcgen05_scan_over_cached_projections():
     m = _mod()
     S, K, chunk = 9000, 36, 1024
     pcm = noise(64, K * chunk, seed=61)
