@@ -28,6 +28,10 @@ import sys
 import tempfile
 import time
 
+# one BLAS / OpenMP thread per process ("OMP_NUM_THREADS=1 per worker"); must be set before numpy loads its BLAS
+for _v in ('OMP_NUM_THREADS', 'OPENBLAS_NUM_THREADS', 'MKL_NUM_THREADS', 'NUMEXPR_NUM_THREADS'):
+    os.environ[_v] = '1'
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -38,6 +42,10 @@ PRIME = 24                # ticks that fill a 29-frame window: (24 * 1024 - 1600
 ALG_BYTES_PER_UPDATE = 2048 + 1.28 * 13 * 4           # 2114.56 B (F=13)
 ALG_FLOP_PER_UPDATE_GRU = 2 * (29 * (13 + 20) * 60 + 20)   # 114 880
 FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12     # 74.4 (148 SMs x 128 lanes x 2 x max clock)
+K2_BYTES_PER_UPDATE = 29 * 240 + 4 + 8 + 1 + 8        # 29 cached projection rows + raw, conf, fired, trigger state
+K2_MMA_FLOP_PER_UPDATE = 29 * 81 * 2048 // 16         # 81 HMMA.1688 (2048 FLOP) per 16-stream tile and step, 3xTF32 split included
+K1_NAMES = {0: 'mfcc_fast_stream_kernel<LEAN> (K1, FFT on the CUDA cores)', 2: 'mfcc_fast_stream_kernel<LEAN> (K1)', 3: 'mfcc_fast_stream_kernel (K1, 64-bit set-up)',
+            4: 'mfcc_tc2_stream_kernel (K1, DFT stage 2 on tcgen05)', 5: 'mfcc_tc3_plan_kernel + mfcc_tc3_kernel (K1, both DFT stages on tcgen05)'}
 
 
 def peaks():
@@ -63,29 +71,103 @@ def synth_pcm(n_streams, n_samples, seed, stream_offset=0):
 
 
 # ------------------------------------------------------------------------------------ CPU arm
-def _cpu_worker(args):
-    seed, n_streams, ticks, warm = args
-    try:                                        # one BLAS/OpenMP thread per worker: one core each
-        from threadpoolctl import threadpool_limits
-        threadpool_limits(1)
-    except Exception:
-        pass
+def workload_config(S, world, l2=None):
+    """The ``config`` object of both arms (same keys and workload text, so that the two lines describe the same job)."""
+    return {'workload': 'per-GPU shard of configs[3]: %d streams/GPU x %d GPU, default hey-mycroft parameters '
+                        '(n_fft 512, hop 800, window 1600, n_filt 20, n_mfcc 13, GRU 20, 29-frame window), 1024-sample chunks' % (S, world),
+            'streams_per_gpu': S, 'chunk_samples': CHUNK,
+            'priming': '%d untimed ticks before the warm-up fill every 29-frame window: each timed update scans 29 real frames' % PRIME,
+            'l2': l2 or 'inputs larger than L2',
+            'parallelism': 'streams block-sharded over GPUs, NCCL all-reduce of the detection count per tick' if world > 1 else 'single GPU'}
+
+
+def _limit_threads():
+    """One BLAS/OpenMP thread in this process; fails loudly if that cannot be enforced."""
+    from threadpoolctl import threadpool_limits, threadpool_info
+    threadpool_limits(1)
+    bad = [i for i in threadpool_info() if i.get('num_threads', 1) != 1]
+    if bad:
+        raise RuntimeError('could not pin BLAS/OpenMP to one thread: %r' % bad)
+
+
+def _cpu_worker_loop(conn, seed, warm):
+    """One Listener per process, as the reference runs it (precise/network_runner.py:101-153 + runner.py:127-142): the numpy oracle
+    port of Listener.update + TriggerDetector.update on one stream.  Warm-up once (window filled, caches hot), then timed batches."""
+    _limit_threads()
     from oracle.gru import GruWeights
     from oracle.listener import OracleListener
     from oracle.trigger import OracleTrigger
     w = GruWeights.random(13, 20, seed=0, scale=0.1)
-    pcm = synth_pcm(n_streams, (ticks + warm) * CHUNK, seed)
-    lis = [OracleListener(w) for _ in range(n_streams)]
-    det = [OracleTrigger(2 * CHUNK) for _ in range(n_streams)]
-    fired = 0
-    t0 = None
-    for k in range(ticks + warm):
-        if k == warm:
-            t0 = time.perf_counter()
-        for s in range(n_streams):
-            c = pcm[s, k * CHUNK:(k + 1) * CHUNK].astype(np.float32) / 32768.0
-            fired += det[s].update(lis[s].update(c))
-    return n_streams * ticks, time.perf_counter() - t0, fired
+    ring = 256
+    pcm = synth_pcm(1, ring * CHUNK, seed)[0]
+    chunks = [pcm[k * CHUNK:(k + 1) * CHUNK].astype(np.float32) / 32768.0 for k in range(ring)]
+    lis, det = OracleListener(w), OracleTrigger(2 * CHUNK)
+    k = 0
+    for _ in range(warm):
+        det.update(lis.update(chunks[k % ring])); k += 1
+    conn.send('ready')
+    while True:
+        cmd = conn.recv()
+        if cmd is None:
+            return
+        ticks = int(cmd)
+        fired = 0
+        t0 = time.perf_counter()
+        for _ in range(ticks):
+            fired += det.update(lis.update(chunks[k % ring])); k += 1
+        conn.send((ticks, time.perf_counter() - t0, fired))
+
+
+class CpuPool:
+    """Persistent worker processes (one stream each, one core each, 50 warm-up ticks at start)."""
+    WARM = 50
+
+    def __init__(self, procs=None):
+        import multiprocessing as mp
+        self.procs = procs or usable_cores()
+        ctx = mp.get_context('fork')
+        self.w = []
+        for i in range(self.procs):
+            a, b = ctx.Pipe()
+            p = ctx.Process(target=_cpu_worker_loop, args=(b, 1000 + i, self.WARM), daemon=True)
+            p.start()
+            self.w.append((p, a))
+        for _, a in self.w:
+            assert a.recv() == 'ready'
+
+    def step(self, ticks):
+        """Every worker runs `ticks` timed ticks concurrently -> (stream-updates, wall seconds = slowest worker)."""
+        for _, a in self.w:
+            a.send(ticks)
+        res = [a.recv() for _, a in self.w]
+        return sum(r[0] for r in res), max(r[1] for r in res)
+
+    def close(self):
+        for p, a in self.w:
+            try:
+                a.send(None)
+            except Exception:
+                pass
+        for p, _ in self.w:
+            p.join(timeout=5)
+
+
+def cpu_port_rate(ticks=1000, steps=3, pool=None):
+    """The oracle port on all usable host cores: `steps` batches of `ticks` (>= 1000) timed ticks per worker
+    after 50 warm-up ticks per worker -> (stream-updates/s, workers, description, wall seconds per step)."""
+    own = pool is None
+    pool = pool or CpuPool()
+    try:
+        upd = wall = 0.0
+        for _ in range(steps):
+            u, t = pool.step(ticks)
+            upd += u; wall += t
+    finally:
+        if own:
+            pool.close()
+    return upd / wall, pool.procs, ('%d worker processes x 1 stream x %d x %d timed ticks of 1024 samples (after %d warm-up ticks per worker, persistent '
+                                    'workers), numpy oracle port of Listener.update + TriggerDetector.update, OMP/BLAS threads = 1 per worker'
+                                    % (pool.procs, steps, ticks, CpuPool.WARM)), wall / steps
 
 
 def cpu_c_port_rate(streams_per_thread=48, ticks=80):
@@ -103,6 +185,38 @@ def cpu_c_port_rate(streams_per_thread=48, ticks=80):
     dt = time.perf_counter() - t0
     return S * ticks / dt, threads, '%d threads x %d streams x %d ticks of 1024 samples, scalar C restatement (gcc -O2), float64 MFCC / float32 GRU' % (
         threads, streams_per_thread, ticks)
+
+
+def _cpu_batched_worker(args):
+    """The batched offline pattern of the reference (precise/scripts/simulate.py:92-104): vectorize a whole recording, cut one
+    29-frame window per chunk_size // hop_samples frames, Runner.predict on [N, 29, 13]."""
+    seed, seconds = args
+    _limit_threads()
+    from oracle import mfcc as om
+    from oracle.gru import GruWeights, predict
+    from oracle.params import OracleParams
+    pr = OracleParams()
+    w = GruWeights.random(13, 20, seed=0, scale=0.1)
+    audio = synth_pcm(1, int(seconds * 16000), seed)[0].astype(np.float32) / 32768.0
+    hops = max(1, CHUNK // pr.hop_samples)
+    t0 = time.perf_counter()
+    mf = om.vectorize_raw(audio, pr)
+    inputs = np.array([mf[i - pr.n_features:i] for i in range(pr.n_features, len(mf), hops)])
+    p = predict(w, inputs)
+    return len(p), time.perf_counter() - t0, seconds
+
+
+def cpu_batched_rate(seconds=120.0):
+    import multiprocessing as mp
+    procs = usable_cores()
+    ctx = mp.get_context('fork')
+    with ctx.Pool(procs) as pool:
+        pool.map(_cpu_batched_worker, [(i, 5.0) for i in range(procs)])              # warm-up
+        res = pool.map(_cpu_batched_worker, [(2000 + i, seconds) for i in range(procs)])
+    wall = max(r[1] for r in res)
+    return {'value': sum(r[0] for r in res) / wall, 'unit': 'window-predictions/s', 'realtime_streams': procs * seconds / wall, 'cores': procs,
+            'kind': 'port', 'sample': '%d workers x %.0f s of audio: vectorize_raw on the whole recording, one 29 x 13 window per frame, '
+                                      'batched GRU predict (simulate.py:92-104 pattern), numpy oracle port' % (procs, seconds)}
 
 
 def usable_cores():
@@ -123,22 +237,9 @@ def usable_cores():
     return n
 
 
-def cpu_port_rate(ticks=3000, warm=50, streams_per_proc=1, procs=None):
-    """The oracle port (numpy restatement of Listener.update + TriggerDetector.update) on the host
-    cores, one stream per worker process as in the reference (one Listener per process)."""
-    import multiprocessing as mp
-    procs = procs or usable_cores()
-    ctx = mp.get_context('fork')
-    with ctx.Pool(procs) as pool:
-        res = pool.map(_cpu_worker, [(1000 + i, streams_per_proc, ticks, warm) for i in range(procs)])
-    updates = sum(r[0] for r in res)
-    wall = max(r[1] for r in res)
-    return updates / wall, procs, '%d worker processes x %d stream x %d ticks of 1024 samples (after %d warm-up ticks), numpy oracle port, 1 BLAS thread per worker' % (
-        procs, streams_per_proc, ticks, warm)
-
-
-def cpu_latency(calls=600, warm=50):
+def cpu_latency(calls=1000, warm=50):
     """p50/p99 of one oracle Listener.update + TriggerDetector.update (batch 1, one core), microseconds."""
+    _limit_threads()
     from oracle.gru import GruWeights
     from oracle.listener import OracleListener
     from oracle.trigger import OracleTrigger
@@ -155,39 +256,70 @@ def cpu_latency(calls=600, warm=50):
     return float(np.percentile(ts, 50)), float(np.percentile(ts, 99))
 
 
+def host_info():
+    model = None
+    try:
+        for ln in open('/proc/cpuinfo'):
+            if ln.startswith('model name'):
+                model = ln.split(':', 1)[1].strip()
+                break
+    except Exception:
+        pass
+    return {'os_cpu_count': os.cpu_count(), 'usable_cores': usable_cores(), 'cpu_model': model,
+            'threads_per_worker': {v: os.environ.get(v) for v in ('OMP_NUM_THREADS', 'OPENBLAS_NUM_THREADS', 'MKL_NUM_THREADS')}}
+
+
 def run_reference(args, rank):
-    """--impl reference: the reference's CPU path (oracle port; the TF/Keras/sonopy stack is not
-    installable on this image) on all host cores, bounded sample per step."""
+    """--impl reference: the reference's CPU path (numpy oracle port; the TF/Keras/sonopy stack is not installable on this image)
+    on all usable host cores.  A step = 1000 timed ticks on every worker (one stream per worker process, persistent workers,
+    50 warm-up ticks each: BASELINE.md section 3); value = stream-updates over all timed steps / their wall time."""
     if rank != 0:
         return
-    t0 = time.perf_counter()
-    rates = []
-    for step in range(args.warmup + args.steps):
-        r, cores, sample = cpu_port_rate(ticks=40, warm=5)
-        if step >= args.warmup:
-            rates.append(r)
-    v = float(np.mean(rates))
+    TICKS = 1000
+    pool = CpuPool()
+    try:
+        for _ in range(args.warmup):
+            pool.step(TICKS)
+        upd = wall = 0.0
+        for _ in range(args.steps):
+            u, t = pool.step(TICKS)
+            upd += u; wall += t
+    finally:
+        pool.close()
+    v = upd / wall
+    sample = ('%d worker processes x 1 stream x %d timed ticks per step (after %d warm-up ticks per worker and %d warm-up steps), numpy oracle '
+              'port, OMP/BLAS threads = 1 per worker' % (pool.procs, TICKS, CpuPool.WARM, args.warmup))
     try:                                           # extra evidence: the compiled scalar C restatement on the same cores
         cc = cpu_c_port_rate()
         cpu_c = {'value': cc[0], 'unit': 'stream-updates/s', 'cores': cc[1], 'kind': 'port', 'sample': cc[2]}
     except Exception as e:
         cpu_c = None
         print('note: C port baseline skipped: %r' % (e,), file=sys.stderr)
+    try:
+        batched = cpu_batched_rate(60.0)
+    except Exception as e:
+        batched = None
+        print('note: batched CPU baseline skipped: %r' % (e,), file=sys.stderr)
+    S = args.streams_per_gpu                       # the same `config` object as the b200 arm prints for these arguments
+    cfg = workload_config(S, args.gpus, ('inputs larger than L2: %d MB of PCM per tick, %d distinct ticks resident' % (S * CHUNK * 2 >> 20, args.ticks_resident))
+                          if S * CHUNK * 2 >= (160 << 20) else 'explicit 256 MB flush write between steps (its time measured separately and subtracted)')
     line = {
         'impl': 'reference', 'metric': 'stream-updates/s (16 kHz int16 PCM, 1024-sample chunk -> decoded confidence + trigger)',
         'value': v, 'unit': 'stream-updates/s', 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
-        'ms_per_step': 1e3 * (time.perf_counter() - t0) / max(1, args.steps + args.warmup),
+        'ms_per_step': 1e3 * wall / max(1, args.steps),
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64 MFCC / f32 GRU', 'data': 'synthetic',
-        'config': {'workload': 'per-GPU shard of configs[3]: default hey-mycroft parameters (n_fft 512, hop 800, window 1600, n_filt 20, n_mfcc 13, '
-                               'GRU 20, 29-frame window), 1024-sample chunks; CPU arm: bounded sample of the same per-stream work '
-                               '(one stream per worker process, as the reference runs one Listener per process)',
-                   'streams_per_gpu': args.streams_per_gpu, 'chunk_samples': CHUNK},
-        'cpu_baseline': {'value': v, 'unit': 'stream-updates/s', 'cores': cores, 'kind': 'port', 'sample': sample + ' per step'},
+        'config': cfg,
+        'cpu_baseline': {'value': v, 'unit': 'stream-updates/s', 'cores': pool.procs, 'kind': 'port', 'sample': sample,
+                         'per_core': v / pool.procs},
         'e2e': {'value': v, 'unit': 'stream-updates/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'realtime_streams': v / 15.625,
+        'sample': 'the CPU arm times a bounded sample of the per-stream work of `config`: ' + sample,
         'cpu_baseline_c': cpu_c,
+        'cpu_baseline_batched': batched,
+        'host': host_info(),
         'note': 'value = numpy oracle port (the reference itself is Python + numpy + Keras/TF per Listener); cpu_baseline_c = the same '
-                'path as compiled scalar C, a stronger CPU baseline than the reference could reach',
+                'path as compiled scalar C, a stronger CPU baseline than the reference could reach; cpu_baseline_batched = the offline '
+                'simulate.py pattern (whole-recording MFCC + batched predict)',
     }
     print(json.dumps(line))
 
@@ -245,9 +377,14 @@ def run_b200(args):
     cpu = None
     cpu_lat = None
     cpu_c = None
+    cpu_batched = None
     if int(os.environ.get('WORLD_SIZE', '1')) == 1 and not args.no_cpu_baseline:
         cpu = cpu_port_rate()                  # before CUDA is initialised in this process (fork safety)
         cpu_lat = cpu_latency() if args.latency else None
+        try:
+            cpu_batched = cpu_batched_rate(60.0)
+        except Exception as e:
+            print('note: batched CPU baseline skipped: %r' % (e,), file=sys.stderr)
         try:
             cpu_c = cpu_c_port_rate()
         except Exception as e:                     # the C port is optional evidence; never fail the bench on it
@@ -412,22 +549,32 @@ def run_b200(args):
         sb3.core.close()
         del tk
 
-    # ---- configs[4]: latency mode, batch = 1: one Engine.get_prediction-sized call at a time
+    # ---- configs[4]: latency mode, batch = 1 PER GPU: every rank runs one Engine.get_prediction-sized call at a time, concurrently
     lat = None
-    if rank == 0 and args.latency:
+    if args.latency:
         sb1 = StreamBatch(model, 1, chunk_samples=CHUNK, device=local)
         one, p1 = pinned_empty((1, CHUNK), np.int16)
         c1, p2 = pinned_empty((1,), np.float64)
-        src = synth_pcm(1, CHUNK * 64, 777)
+        src = synth_pcm(1, CHUNK * 64, 777 + rank)
         ts = []
+        if world > 1:
+            dist.barrier()
         for k in range(2200):                               # the first 200 calls (window filled after 24) are dropped below
             one[0] = src[0, (k % 64) * CHUNK:(k % 64 + 1) * CHUNK]
             t0 = time.perf_counter()
             sb1.update_host(one, c1)                        # H2D 2 KB -> K1 -> K2/K3 -> D2H 8 B, host-synchronous
             ts.append(time.perf_counter() - t0)
         ts = np.array(ts[200:]) * 1e6
-        lat = {'workload': 'configs[4]: batch 1, window->decision through pb_update_host (pinned 2 KB in, 8 B out)',
-               'p50_us': float(np.percentile(ts, 50)), 'p99_us': float(np.percentile(ts, 99)), 'calls': int(len(ts))}
+        mine = torch.tensor([float(np.percentile(ts, 50)), float(np.percentile(ts, 99))], dtype=torch.float64, device=dev)
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        if world > 1:
+            dist.all_gather(allr, mine)
+        else:
+            allr = [mine]
+        per_rank = [[float(v[0]), float(v[1])] for v in allr]
+        lat = {'workload': 'configs[4]: batch 1 per GPU on %d GPU(s), window->decision through pb_update_host (pinned 2 KB in, 8 B out), all ranks concurrently' % world,
+               'p50_us': max(v[0] for v in per_rank), 'p99_us': max(v[1] for v in per_rank), 'per_rank_p50_p99_us': per_rank, 'calls': int(len(ts)),
+               'aggregate': 'p50_us / p99_us = the slowest rank'}
         if cpu_lat:
             lat.update(cpu_p50_us=cpu_lat[0], cpu_p99_us=cpu_lat[1], cpu='oracle port, 1 core')
         pinned_free(p1); pinned_free(p2)
@@ -444,6 +591,12 @@ def run_b200(args):
     k1_ms = kms[0] / max(1, klaunch[0])
     k2_ms = kms[1] / max(1, klaunch[1])
     k1_gbs = S * ALG_BYTES_PER_UPDATE / (k1_ms * 1e-3) / 1e9 if k1_ms > 0 else None
+    proj_ms = (kms[3] / klaunch[3]) if klaunch[3] else 0.0
+    bf16_peak = None
+    try:
+        bf16_peak = float(json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))['bf16_tflops_sustained'])
+    except Exception:
+        pass
     traffic = None
     tp = os.path.join(ROOT, 'profiles', 'k1_traffic.json')
     if os.path.isfile(tp):
@@ -456,30 +609,38 @@ def run_b200(args):
         'value': value, 'unit': 'stream-updates/s', 'n_gpus': world, 'steps': K, 'warmup': W,
         'ms_per_step': ms_all / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': 'per-GPU shard of configs[3]: %d streams/GPU x %d GPU, default hey-mycroft parameters '
-                               '(n_fft 512, hop 800, window 1600, n_filt 20, n_mfcc 13, GRU 20, 29-frame window), 1024-sample chunks' % (S, world),
-                   'streams_per_gpu': S, 'chunk_samples': CHUNK,
-                   'priming': '%d untimed ticks before the warm-up fill every 29-frame window: each timed update scans 29 real frames' % PRIME,
-                   'l2': ('inputs larger than L2: %d MB of PCM per tick, %d distinct ticks resident' % (S * CHUNK * 2 >> 20, NT))
-                         if flush is None else 'explicit 256 MB flush write between steps (its time measured separately and subtracted)',
-                   'parallelism': 'streams block-sharded over GPUs, NCCL all-reduce of the detection count per tick' if world > 1 else 'single GPU'},
+        'config': workload_config(S, world, ('inputs larger than L2: %d MB of PCM per tick, %d distinct ticks resident' % (S * CHUNK * 2 >> 20, NT))
+                                  if flush is None else 'explicit 256 MB flush write between steps (its time measured separately and subtracted)'),
         'realtime_streams': value / 15.625,
         'detections': total_fired,
-        'roofline': {'kernel': 'mfcc_fast_stream_kernel (K1)', 'bound': 'hbm', 'achieved': k1_gbs, 'peak': hbm_peak, 'unit': 'GB/s',
+        'roofline': {'kernel': K1_NAMES.get(args.k1_mode, 'k1 mode %d' % args.k1_mode), 'bound': 'hbm', 'achieved': k1_gbs, 'peak': hbm_peak, 'unit': 'GB/s',
                      'frac': (k1_gbs / hbm_peak) if k1_gbs else None, 'of': which, 'traffic': traffic,
+                     'traffic_source': 'profiles/k1_traffic.json (one ncu --set full capture of this kernel, not a live counter)' if traffic else None,
                      'algorithmic_bytes_per_launch': S * ALG_BYTES_PER_UPDATE, 'ms_per_launch': k1_ms, 'launches': klaunch[0]},
-        'roofline_gru': {'kernel': 'gru_mma_kernel<20,13> (K2+K3; mma.sync TF32x3)', 'bound': 'fp32-fma (algorithmic FLOP vs CUDA-core fp32 peak)', 'achieved': S * ALG_FLOP_PER_UPDATE_GRU / (k2_ms * 1e-3) / 1e12 if k2_ms > 0 else None,
-                         'peak': FP32_PEAK_TFLOPS, 'unit': 'TFLOP/s', 'frac': (S * ALG_FLOP_PER_UPDATE_GRU / (k2_ms * 1e-3) / 1e12 / FP32_PEAK_TFLOPS) if k2_ms > 0 else None,
-                         'of': 'nominal 148 SM x 128 lanes x 2 x 1.965 GHz', 'ms_per_launch': k2_ms, 'launches': klaunch[1], 'input_projection_ms_per_launch': (kms[3] / klaunch[3] if klaunch[3] else None)},
+        # K2 (scan over cached projections) against both of its ceilings: HBM for the bytes it must read (29 cached projection rows of
+        # 240 B per update + 21 B of results) and the tensor pipe for the MMA FLOPs it executes (3xTF32 split, 81 m16n8k8 HMMA per 16
+        # streams and step = 300 672 FLOP per update; TF32 dense peak taken as half the measured sustained bf16 rate)
+        'roofline_k2': {'kernel': 'gru_mma_kernel<20,13,PROJ,MB=1> (K2+K3; mma.sync TF32x3) after input_proj_kernel', 'ms_per_launch': k2_ms, 'launches': klaunch[1],
+                        'input_projection_ms_per_launch': proj_ms or None,
+                        'hbm': {'algorithmic_bytes_per_update': K2_BYTES_PER_UPDATE, 'achieved': S * K2_BYTES_PER_UPDATE / (k2_ms * 1e-3) / 1e9 if k2_ms > 0 else None,
+                                'peak': hbm_peak, 'unit': 'GB/s', 'frac': S * K2_BYTES_PER_UPDATE / (k2_ms * 1e-3) / 1e9 / hbm_peak if k2_ms > 0 else None},
+                        'tensor': {'executed_flop_per_update': K2_MMA_FLOP_PER_UPDATE, 'achieved': S * K2_MMA_FLOP_PER_UPDATE / (k2_ms * 1e-3) / 1e12 if k2_ms > 0 else None,
+                                   'peak': (bf16_peak / 2) if bf16_peak else None, 'unit': 'TFLOP/s (TF32, executed incl. the 3x split)',
+                                   'frac': (S * K2_MMA_FLOP_PER_UPDATE / (k2_ms * 1e-3) / 1e12 / (bf16_peak / 2)) if (bf16_peak and k2_ms > 0) else None},
+                        'algorithmic_flop_per_update': ALG_FLOP_PER_UPDATE_GRU},
         'e2e': e2e,
         'gpu_launches': int(sum(klaunch)),
         'cpu_baseline': ({'value': cpu[0], 'unit': 'stream-updates/s', 'cores': cpu[1], 'kind': 'port', 'sample': cpu[2]} if cpu else None),
         'cpu_baseline_c': ({'value': cpu_c[0], 'unit': 'stream-updates/s', 'cores': cpu_c[1], 'kind': 'port', 'sample': cpu_c[2]} if cpu_c else None),
+        'cpu_baseline_batched': cpu_batched,
+        'host': host_info(),
         'clocks': clocks,
         'small_batch': small,
         'latency': lat,
         'config3': big,
     }
+    if big:
+        big.pop('k2_fp32_frac', None)
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -498,7 +659,7 @@ def main():
     ap.add_argument('--no-latency', dest='latency', action='store_false')
     ap.add_argument('--no-config3', dest='config3', action='store_false')
     ap.add_argument('--gru-mode', type=int, default=0, help='debug: 0 auto, 1 CUDA-core, 2 mma.sync, 3 tcgen05, 7 mma.sync with 32-stream tiles')
-    ap.add_argument('--k1-mode', type=int, default=0, help='debug (A/B runs only): 0 default MFCC kernels, 1 tensor-core DFT, 2 lean set-up')
+    ap.add_argument('--k1-mode', type=int, default=0, help='debug (A/B runs only): 0 default MFCC kernel, 3 FFT kernel with 64-bit set-up, 4 tcgen05 stage 2, 5 both DFT stages on tcgen05')
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
