@@ -78,7 +78,7 @@ def workload_config(S, world, l2=None):
             'streams_per_gpu': S, 'chunk_samples': CHUNK,
             'priming': '%d untimed ticks before the warm-up fill every 29-frame window: each timed update scans 29 real frames' % PRIME,
             'l2': l2 or 'inputs larger than L2',
-            'parallelism': 'streams block-sharded over GPUs, NCCL all-reduce of the detection count per tick' if world > 1 else 'single GPU'}
+            'parallelism': 'streams block-sharded over GPUs, NCCL all-reduce of the detection count per tick (on a side stream, under the next tick)' if world > 1 else 'single GPU'}
 
 
 def _limit_threads():
@@ -372,7 +372,7 @@ def run_b200(args):
     import torch.distributed as dist
     from mycroft_precise_b200 import GruModel, StreamBatch
     from mycroft_precise_b200.core import pinned_empty, pinned_free
-    from mycroft_precise_b200.dist import init_from_env, DetectionCounter
+    from mycroft_precise_b200.dist import init_from_env, DetectionCounter, bind_to_gpu_numa_node
 
     cpu = None
     cpu_lat = None
@@ -395,6 +395,9 @@ def run_b200(args):
         print('note: WORLD_SIZE=%d, --gpus=%d' % (world, args.gpus), file=sys.stderr)
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
+    # CPU legs are done: from here on this process only feeds its GPU.  Pin it (and the pinned buffers it is about to allocate)
+    # to the GPU's NUMA node, so that N ranks do not push their host traffic across the socket interconnect.
+    numa_cpus = None if args.no_numa_bind else bind_to_gpu_numa_node(local)
     S = args.streams_per_gpu
     K, W = args.steps, args.warmup
     model = GruModel.random(13, 20, seed=0, scale=0.1)
@@ -423,7 +426,7 @@ def run_b200(args):
             flush.add_(1)                      # rewrite 256 MB: evicts L2 between iterations
         sb.update(dev_ticks[t % NT])
         if world > 1:
-            counter.all_reduce()
+            counter.all_reduce_overlapped()    # snapshot on this stream, NCCL on a side stream under the next tick's K1
 
     # ---- value: inputs resident in HBM
     # Priming (untimed, before the warm-up): PRIME ticks fill every stream's 29-frame window, so that each timed update
@@ -449,6 +452,7 @@ def run_b200(args):
     e0.record()
     for t in range(K):
         step(W + t)
+    counter.wait()                              # the last tick's all-reduce is inside the timed region
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1) - flush_ms
@@ -459,6 +463,7 @@ def run_b200(args):
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     ms_all = float(tmax.item())
     value = S * world * K / (ms_all * 1e-3)
+    torch.cuda.synchronize()
     total_fired = int(counter.total.item()) if world > 1 else int(sb.count.item())
 
     # ---- e2e: host buffers through pb_update_host (H2D of the PCM and D2H of the results inside)
@@ -480,7 +485,8 @@ def run_b200(args):
         for t in range(K):
             cnt += sb.update_host(hp[t % len(hp)], conf, None, fired)
             if world > 1:
-                counter.all_reduce()
+                counter.all_reduce_overlapped()
+        counter.wait()
         g1.record()
         barrier()
         wall_ms = (time.perf_counter() - t0) * 1e3
@@ -633,7 +639,7 @@ def run_b200(args):
         'cpu_baseline': ({'value': cpu[0], 'unit': 'stream-updates/s', 'cores': cpu[1], 'kind': 'port', 'sample': cpu[2]} if cpu else None),
         'cpu_baseline_c': ({'value': cpu_c[0], 'unit': 'stream-updates/s', 'cores': cpu_c[1], 'kind': 'port', 'sample': cpu_c[2]} if cpu_c else None),
         'cpu_baseline_batched': cpu_batched,
-        'host': host_info(),
+        'host': dict(host_info(), numa_bound_cpus=(('%d CPUs of the GPU\'s NUMA node, %d..%d' % (len(numa_cpus), numa_cpus[0], numa_cpus[-1])) if numa_cpus else None)),
         'clocks': clocks,
         'small_batch': small,
         'latency': lat,
@@ -658,6 +664,7 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-latency', dest='latency', action='store_false')
     ap.add_argument('--no-config3', dest='config3', action='store_false')
+    ap.add_argument('--no-numa-bind', action='store_true', help='do not pin the process to the CPUs of its GPU\'s NUMA node')
     ap.add_argument('--gru-mode', type=int, default=0, help='debug: 0 auto, 1 CUDA-core, 2 mma.sync, 3 tcgen05, 7 mma.sync with 32-stream tiles')
     ap.add_argument('--k1-mode', type=int, default=0, help='debug (A/B runs only): 0 default MFCC kernel, 3 FFT kernel with 64-bit set-up, 4 tcgen05 stage 2, 5 both DFT stages on tcgen05')
     args = ap.parse_args()

@@ -38,7 +38,11 @@ def _worker(rank, world, port, n_streams, q):
     _, _, fired = run_streams(wts, pcm, 1024, sensitivity=0.9, trigger_level=0)
     for k in range(16):
         local[0] = int(fired[:, k].sum()) if len(fired) else 0
-        counter.all_reduce()
+        if k % 2:
+            counter.all_reduce()
+        else:
+            counter.all_reduce_overlapped()        # CPU tensors: same result through the synchronous path
+            counter.wait()
         per_tick.append(int(counter.total.item()))
     q.put((rank, lo, hi, per_tick))
     dist.destroy_process_group()

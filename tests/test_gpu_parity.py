@@ -712,6 +712,20 @@ def test_two_stage_tensor_core_mfcc_vs_oracle_ragged(chunk):
     sb.core.close()
 
 
+def test_detection_counter_overlapped_allreduce_single_rank():
+    """DetectionCounter.all_reduce_overlapped (snapshot on the compute stream, reduce on a side stream) follows the device counter."""
+    import torch
+    from mycroft_precise_b200.dist import DetectionCounter
+    local = torch.zeros(1, dtype=torch.int64, device='cuda')
+    c = DetectionCounter(local)
+    for k in range(7):
+        local += k + 1
+        c.all_reduce_overlapped()
+    c.wait()
+    torch.cuda.synchronize()
+    assert int(c.total.item()) == int(local.item()) == 28
+
+
 def test_tcgen05_scan_over_cached_projections():
     m = _mod()
     S, K, chunk = 9000, 36, 1024
