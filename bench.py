@@ -44,7 +44,8 @@ ALG_FLOP_PER_UPDATE_GRU = 2 * (29 * (13 + 20) * 60 + 20)   # 114 880
 FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12     # 74.4 (148 SMs x 128 lanes x 2 x max clock)
 K2_BYTES_PER_UPDATE = 29 * 240 + 4 + 8 + 1 + 8        # 29 cached projection rows + raw, conf, fired, trigger state
 K2_MMA_FLOP_PER_UPDATE = 29 * 81 * 2048 // 16         # 81 HMMA.1688 (2048 FLOP) per 16-stream tile and step, 3xTF32 split included
-K1_NAMES = {0: 'mfcc_fast_stream_kernel<LEAN> (K1, FFT on the CUDA cores)', 2: 'mfcc_fast_stream_kernel<LEAN> (K1)', 3: 'mfcc_fast_stream_kernel (K1, 64-bit set-up)',
+K1_NAMES = {0: 'mfcc_tc3_plan_kernel + mfcc_tc3_kernel (K1: int16 split exactly into fp16 pieces, both DFT stages on tcgen05 / TMEM) -- default from 49152 streams per tick',
+            2: 'mfcc_fast_stream_kernel<LEAN> (K1, FFT on the CUDA cores)', 3: 'mfcc_fast_stream_kernel (K1, FFT, 64-bit set-up)',
             4: 'mfcc_tc2_stream_kernel (K1, DFT stage 2 on tcgen05)', 5: 'mfcc_tc3_plan_kernel + mfcc_tc3_kernel (K1, both DFT stages on tcgen05)'}
 
 
@@ -594,6 +595,7 @@ def run_b200(args):
         return
 
     hbm_peak, which = peaks()
+    k1_name = K1_NAMES.get(args.k1_mode, 'k1 mode %d' % args.k1_mode) if (args.k1_mode or S >= 49152) else K1_NAMES[2]
     k1_ms = kms[0] / max(1, klaunch[0])
     k2_ms = kms[1] / max(1, klaunch[1])
     k1_gbs = S * ALG_BYTES_PER_UPDATE / (k1_ms * 1e-3) / 1e9 if k1_ms > 0 else None
@@ -619,10 +621,11 @@ def run_b200(args):
                                   if flush is None else 'explicit 256 MB flush write between steps (its time measured separately and subtracted)'),
         'realtime_streams': value / 15.625,
         'detections': total_fired,
-        'roofline': {'kernel': K1_NAMES.get(args.k1_mode, 'k1 mode %d' % args.k1_mode), 'bound': 'hbm', 'achieved': k1_gbs, 'peak': hbm_peak, 'unit': 'GB/s',
+        'roofline': {'kernel': k1_name, 'bound': 'hbm', 'achieved': k1_gbs, 'peak': hbm_peak, 'unit': 'GB/s',
                      'frac': (k1_gbs / hbm_peak) if k1_gbs else None, 'of': which, 'traffic': traffic,
                      'traffic_source': 'profiles/k1_traffic.json (one ncu --set full capture of this kernel, not a live counter)' if traffic else None,
-                     'algorithmic_bytes_per_launch': S * ALG_BYTES_PER_UPDATE, 'ms_per_launch': k1_ms, 'launches': klaunch[0]},
+                     'algorithmic_bytes_per_launch': S * ALG_BYTES_PER_UPDATE, 'ms_per_launch': k1_ms, 'launches': klaunch[0],
+                     'note': 'ms_per_launch = one tick of K1 (for the tcgen05 path: plan kernel + main kernel, both inside the CUDA-event bracket)'},
         # K2 (scan over cached projections) against both of its ceilings: HBM for the bytes it must read (29 cached projection rows of
         # 240 B per update + 21 B of results) and the tensor pipe for the MMA FLOPs it executes (3xTF32 split, 81 m16n8k8 HMMA per 16
         # streams and step = 300 672 FLOP per update; TF32 dense peak taken as half the measured sustained bf16 rate)
@@ -635,7 +638,7 @@ def run_b200(args):
                                    'frac': (S * K2_MMA_FLOP_PER_UPDATE / (k2_ms * 1e-3) / 1e12 / (bf16_peak / 2)) if (bf16_peak and k2_ms > 0) else None},
                         'algorithmic_flop_per_update': ALG_FLOP_PER_UPDATE_GRU},
         'e2e': e2e,
-        'gpu_launches': int(sum(klaunch)),
+        'gpu_launches': int(sum(klaunch)) + (int(klaunch[0]) if (args.k1_mode in (0, 5) and S >= 49152) else 0),     # K1 on the tcgen05 path = plan kernel + main kernel
         'cpu_baseline': ({'value': cpu[0], 'unit': 'stream-updates/s', 'cores': cpu[1], 'kind': 'port', 'sample': cpu[2]} if cpu else None),
         'cpu_baseline_c': ({'value': cpu_c[0], 'unit': 'stream-updates/s', 'cores': cpu_c[1], 'kind': 'port', 'sample': cpu_c[2]} if cpu_c else None),
         'cpu_baseline_batched': cpu_batched,
@@ -666,7 +669,7 @@ def main():
     ap.add_argument('--no-config3', dest='config3', action='store_false')
     ap.add_argument('--no-numa-bind', action='store_true', help='do not pin the process to the CPUs of its GPU\'s NUMA node')
     ap.add_argument('--gru-mode', type=int, default=0, help='debug: 0 auto, 1 CUDA-core, 2 mma.sync, 3 tcgen05, 7 mma.sync with 32-stream tiles')
-    ap.add_argument('--k1-mode', type=int, default=0, help='debug (A/B runs only): 0 default MFCC kernel, 3 FFT kernel with 64-bit set-up, 4 tcgen05 stage 2, 5 both DFT stages on tcgen05')
+    ap.add_argument('--k1-mode', type=int, default=0, help='debug (A/B runs only): 0 default MFCC kernel choice, 2 FFT kernel, 3 FFT kernel with 64-bit set-up, 4 tcgen05 stage 2 only, 5 both DFT stages on tcgen05')
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

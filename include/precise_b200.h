@@ -199,10 +199,12 @@ int pb_debug_force_generic(pb_handle* h, int on);
  * batches, tensor-core scan otherwise), 1 = CUDA-core thread-per-stream kernel, 2 = tensor-core kernel,
  * 3 = tcgen05 scan, 7 = tensor-core kernel with 32-stream warp tiles. */
 int pb_debug_gru_mode(pb_handle* h, int mode);
-/* Experimental (opt-in, default 0): 2 = the fast MFCC tick kernel with its per-pass set-up in 32-bit arithmetic;
- * 1 routes the stateful tick's MFCC through the tensor-core DFT kernel
- * (csrc/mfcc_tc.cuh: radix-16 butterflies on the CUDA cores + fp16x3 GEMM blocks on tcgen05).  Its host-side tables
- * are CPU-verified.  Neither variant has been validated on hardware yet -- do not enable in production. */
+/* Test / A-B hook for the stateful tick's MFCC kernel (aligned default geometry).  0 = automatic: from 49 152 streams per tick on the
+ * kernel with both DFT stages on the tensor cores (csrc/mfcc_tc3.cuh: int16 samples split exactly into two fp16 pieces, tcgen05
+ * MMAs with TMEM accumulators), below that the FFT kernel on the CUDA cores (csrc/mfcc_fast.cuh); 2 = always the FFT kernel;
+ * 3 = the FFT kernel with its original 64-bit set-up; 4 = csrc/mfcc_tc2.cuh (radix-16 butterflies on the CUDA cores, second DFT
+ * stage on tcgen05); 5 = always mfcc_tc3; 100 + w = mfcc_tc3 with the phase timeline of warp w in pb_debug_counters.  All variants
+ * are parity-tested on B200 (tests/test_gpu_parity.py). */
 int pb_debug_k1_mode(pb_handle* h, int mode);
 /* CPU model of that kernel's DFT for one frame of 512 int16 samples -> |X[k]|^2, k = 0..256 (same butterfly, operand tables
  * and layout arithmetic; no device needed).  Test hook. */

@@ -72,7 +72,7 @@ struct pb_handle {
     float *d_proj_w = nullptr, *d_proj_b = nullptr;
     size_t k1_batch_smem = 0, k1_stream_smem = 0, k1_fast_smem = 0;
     bool force_generic = false;      // tests: exercise the generic kernels on the aligned geometry
-    int k1_mode = 0;                 // 0 = default (FFT kernel, 32-bit set-up), 2 = the same, 3 = FFT kernel with the original 64-bit set-up, 4 = tcgen05 stage-2 kernel (mfcc_tc2), 5 = both DFT stages on tcgen05 (mfcc_tc3), 100 + w = 5 with warp w's timeline
+    int k1_mode = 0;                 // 0 = default (mfcc_tc3 from TC3_MIN_STREAMS streams per tick on, else the FFT kernel with 32-bit set-up), 2 = always the FFT kernel, 3 = FFT kernel with the original 64-bit set-up, 4 = tcgen05 stage-2 kernel (mfcc_tc2), 5 = both DFT stages on tcgen05 (mfcc_tc3), 100 + w = 5 with warp w's timeline
     bool tcd_ok = false;             // geometry the tensor-core DFT tables cover (CPU model + kernel)
     bool tc2_ok = false;             // ... and by mfcc_tc2_stream_kernel<Tc2Geo20> (run-time mel tables equal its compile-time ones)
     std::vector<float> h_wrise, h_wfall; std::vector<int> h_grid;      // host copies for the lazily built tcd tables
@@ -986,7 +986,11 @@ static int launch_stream_mfcc(pb_handle* h, const int16_t* d_pcm, const int32_t*
     const int grid = (int)std::min<int64_t>(tiles, (int64_t)h->sm_count * 4);
     const float inv = 1.0f / 32768.0f, scale = inv * inv / (float)h->cfg.n_fft;
     ProfScope ps(h, 0, s);
-    if ((h->k1_mode == 5 || h->k1_mode >= 100) && h->tc3_ok && (uintptr_t)d_pcm % 16 == 0 && !h->force_generic) {
+    // Default choice (k1_mode 0): from TC3_MIN_STREAMS streams on, the tick's MFCCs come from the kernel with both DFT stages on the
+    // tensor cores (measured on B200: 116 vs 128 us at 65 536 streams, 208 vs 228 us at 131 072, 392 vs 414 us at 262 144; below
+    // that its persistent pipeline does not fill and the FFT kernel wins: 71 vs 64 us at 32 768).
+    const bool tc3_auto = h->k1_mode == 0 && n >= TC3_MIN_STREAMS;
+    if ((h->k1_mode == 5 || h->k1_mode >= 100 || tc3_auto) && h->tc3_ok && (uintptr_t)d_pcm % 16 == 0 && !h->force_generic) {
         int rc = ensure_tc3_tables(h);
         if (rc != PB_OK) return rc;
         Tc3Tables t;

@@ -21,10 +21,10 @@
 // its issue slots waiting for instructions) plus one warp that only issues the MMAs.  Per tile of 32 frames:
 //     INT(k)   workers     tcgen05.ld of stage 1's result, twiddle, split, stores
 //     P(k)     warp 16     MMA2(k)   (MMA1(k+1) as soon as every worker has read tile k's stage-1 result, during INT(k))
-//              warps 0-7   EPI(k-1)
-//              warps 8-15  new tails of tile k+1, frame records of tile k+4 (+ L2 prefetch), CONV(k+2) = prefetched PCM registers ->
-//                          stage-1 operand, then the prefetch of tile k+3
-// with one __syncthreads after each; the MMAs of a tile run under the CUDA-core phases of its neighbours.  The frame list
+//              warps 0-7   EPI(k-1), then a quarter of CONV(k+2)
+//              warps 8-15  new tails of tile k+1, frame records of tile k+4 (+ L2 prefetch), three quarters of CONV(k+2)
+//              CONV = prefetched PCM registers -> stage-1 operand, then the prefetch of tile k+3
+// with one barrier of the worker warps per tile (the MMA warp follows mbarriers only); the MMAs of a tile run under the CUDA-core phases of its neighbours.  The frame list
 // (which frames complete this tick, where their samples are, the split of the first sample, new tail) is built by
 // mfcc_tc3_plan_kernel with every pointer ready to use.
 #pragma once
@@ -48,6 +48,7 @@ constexpr int TC3_A2_TILE = 4 * TC3_A2_LBO;     // one (piece, stage, slot) tile
 constexpr int TC3_REC_RING = 8;                 // tiles of frame records resident in shared memory
 constexpr float TC3_Z_SCALE = 0.03125f;         // stage-2 operands hold Z * 2^-5 (= TCD_A_SCALE): |.| <= 32768 < fp16 max
 constexpr int TC3_PLAN_THREADS = 256;
+constexpr int TC3_MIN_STREAMS = 49152;          // streams per tick from which this kernel is the default (api.cu: launch_stream_mfcc)
 
 // block r -> tile row h (of the frame's four) and MMA slot: rows hold 64, 64, 64 and 65 bins
 __host__ __device__ constexpr int tc3_blk_h(int b) { constexpr int t[9] = {3, 0, 0, 1, 1, 2, 2, 3, 3}; return t[b]; }
@@ -307,7 +308,7 @@ struct Tc3Smem {
     float c0v[TC3_TILE];
     float dct[TCD_MAX_OUT][24];
     Tc3Rec rec[TC3_REC_RING][TC3_TILE];
-    unsigned long long m1_done, m2_done, d1_free;
+    unsigned long long m1_done, m2_done, d1_free, a1_ready, a2_ready, d2_free[2];
     uint32_t tmem_base;
     unsigned int n_frames;
 };
@@ -399,6 +400,8 @@ mfcc_tc3_kernel(Tc3Tables tab, const Tc3Rec* __restrict__ recs, unsigned int* __
     // ---- one-time set-up
     if (tid == 0) {
         mbar_init(&sm.m1_done, 1); mbar_init(&sm.m2_done, 1); mbar_init(&sm.d1_free, TC3_WORKERS);
+        mbar_init(&sm.a1_ready, TC3_WORKERS); mbar_init(&sm.a2_ready, TC3_WORKERS);
+        mbar_init(&sm.d2_free[0], TC3_WORKERS / 2); mbar_init(&sm.d2_free[1], TC3_WORKERS / 2);
         fence_mbar_init();
         sm.n_frames = counters[parity];
         if (blockIdx.x == 0) counters[parity ^ 1] = 0;        // the next tick's plan kernel counts from zero
@@ -439,21 +442,25 @@ mfcc_tc3_kernel(Tc3Tables tab, const Tc3Rec* __restrict__ recs, unsigned int* __
         int4* p = reinterpret_cast<int4*>(&sm.rec[k & (TC3_REC_RING - 1)][f]);
         p[0] = a; p[1] = b;
     };
-    // CONV: warp 8 + w8 converts frames 4 w8 .. 4 w8 + 3 of a tile; lane (c4, l8) owns chunks 4 l8 + c4 and 32 + 4 l8 + c4 (8 samples each).
+    // CONV: warp 8 + w8 converts frames 3 w8 .. 3 w8 + 2 of a tile, warp w < 8 (after its epilogue share) frame 24 + w; lane (c4, l8)
+    // owns chunks 4 l8 + c4 and 32 + 4 l8 + c4 (8 samples each).
     const int c4 = lane >> 3, l8 = lane & 7, cch = 4 * l8 + c4;
-    uint4 pf[4][2];
+    const int cv_n = warp < 8 ? 1 : 3, cv_f0 = warp < 8 ? 24 + warp : 3 * (warp - 8);
+    uint4 pf[3][2];
     auto prefetch_tile = [&](int k) {
 #pragma unroll
-        for (int m = 0; m < 4; ++m) {
-            pf[m][0] = make_uint4(0u, 0u, 0u, 0u); pf[m][1] = pf[m][0];
-            if (k < K) {
-                const Tc3Rec& r = sm.rec[k & (TC3_REC_RING - 1)][4 * (warp - 8) + m];
-                const int16_t* fp = r.frame;
-                if (fp != nullptr) {
-                    const int l0 = r.len0c;
-                    const int16_t* tp = r.tail;
-                    pf[m][0] = *reinterpret_cast<const uint4*>((cch < l0 ? tp : fp) + 8 * cch);
-                    pf[m][1] = *reinterpret_cast<const uint4*>((cch + 32 < l0 ? tp : fp) + 8 * (cch + 32));
+        for (int m = 0; m < 3; ++m) {
+            if (m < cv_n) {
+                pf[m][0] = make_uint4(0u, 0u, 0u, 0u); pf[m][1] = pf[m][0];
+                if (k < K) {
+                    const Tc3Rec& r = sm.rec[k & (TC3_REC_RING - 1)][cv_f0 + m];
+                    const int16_t* fp = r.frame;
+                    if (fp != nullptr) {
+                        const int l0 = r.len0c;
+                        const int16_t* tp = r.tail;
+                        pf[m][0] = *reinterpret_cast<const uint4*>((cch < l0 ? tp : fp) + 8 * cch);
+                        pf[m][1] = *reinterpret_cast<const uint4*>((cch + 32 < l0 ? tp : fp) + 8 * (cch + 32));
+                    }
                 }
             }
         }
@@ -461,27 +468,29 @@ mfcc_tc3_kernel(Tc3Tables tab, const Tc3Rec* __restrict__ recs, unsigned int* __
     // prefetch registers -> stage-1 operand tiles (exact split of x - x0 into fp16 pieces)
     auto conv_tile = [&](int k) {
 #pragma unroll
-        for (int m = 0; m < 4; ++m) {
-            const int fi = 4 * (warp - 8) + m;
-            const uint32_t cc = *reinterpret_cast<const uint32_t*>(&sm.rec[k & (TC3_REC_RING - 1)][fi].c_lo);     // c_lo | c_hi << 16
-            const uint32_t c_lo = __byte_perm(cc, 0, 0x1010), c_hi = __byte_perm(cc, 0, 0x3232);
-            unsigned char* dst = &sm.a1[fi >> 2][0][0] + (4 * (fi & 3) + c4) * 128 + l8 * 16;
+        for (int m = 0; m < 3; ++m) {
+            if (m < cv_n) {
+                const int fi = cv_f0 + m;
+                const uint32_t cc = *reinterpret_cast<const uint32_t*>(&sm.rec[k & (TC3_REC_RING - 1)][fi].c_lo);     // c_lo | c_hi << 16
+                const uint32_t c_lo = __byte_perm(cc, 0, 0x1010), c_hi = __byte_perm(cc, 0, 0x3232);
+                unsigned char* dst = &sm.a1[fi >> 2][0][0] + (4 * (fi & 3) + c4) * 128 + l8 * 16;
 #pragma unroll
-            for (int hf = 0; hf < 2; ++hf) {
-                const uint32_t w[4] = {pf[m][hf].x, pf[m][hf].y, pf[m][hf].z, pf[m][hf].w};
-                uint32_t ah[4], al[4];
+                for (int hf = 0; hf < 2; ++hf) {
+                    const uint32_t w[4] = {pf[m][hf].x, pf[m][hf].y, pf[m][hf].z, pf[m][hf].w};
+                    uint32_t ah[4], al[4];
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const uint32_t vx = w[e] ^ 0x80008000u;
-                    const uint32_t lo_magic = (vx & 0x00FF00FFu) ^ 0x64806480u;         // 1024 + (lo ^ 0x80)
-                    al[e] = tc3_hadd2(lo_magic, c_lo);                                    // lo_b - lo0
-                    const uint32_t hi_magic = __byte_perm(vx, 0x64646464u, 0x4341);       // 1024 + hi + 128
-                    const uint32_t mb = w[e] & 0x00800080u;                               // bit 7 of the low byte as fp16 subnormal 2^-17
-                    const uint32_t t = tc3_hfma2(hi_magic, 0x20002000u, c_hi);            // (hi_floor - hi0) / 128   (0x2000 = 2^-7)
-                    ah[e] = tc3_hfma2(mb, 0x64006400u, t);                                // + carry / 128            (0x6400 = 1024)
+                    for (int e = 0; e < 4; ++e) {
+                        const uint32_t vx = w[e] ^ 0x80008000u;
+                        const uint32_t lo_magic = (vx & 0x00FF00FFu) ^ 0x64806480u;         // 1024 + (lo ^ 0x80)
+                        al[e] = tc3_hadd2(lo_magic, c_lo);                                    // lo_b - lo0
+                        const uint32_t hi_magic = __byte_perm(vx, 0x64646464u, 0x4341);       // 1024 + hi + 128
+                        const uint32_t mb = w[e] & 0x00800080u;                               // bit 7 of the low byte as fp16 subnormal 2^-17
+                        const uint32_t t = tc3_hfma2(hi_magic, 0x20002000u, c_hi);            // (hi_floor - hi0) / 128   (0x2000 = 2^-7)
+                        ah[e] = tc3_hfma2(mb, 0x64006400u, t);                                // + carry / 128            (0x6400 = 1024)
+                    }
+                    *reinterpret_cast<uint4*>(dst + hf * 2048) = make_uint4(ah[0], ah[1], ah[2], ah[3]);
+                    *reinterpret_cast<uint4*>(dst + hf * 2048 + TC3_A1_TILE) = make_uint4(al[0], al[1], al[2], al[3]);
                 }
-                *reinterpret_cast<uint4*>(dst + hf * 2048) = make_uint4(ah[0], ah[1], ah[2], ah[3]);
-                *reinterpret_cast<uint4*>(dst + hf * 2048 + TC3_A1_TILE) = make_uint4(al[0], al[1], al[2], al[3]);
             }
         }
     };
@@ -493,7 +502,7 @@ mfcc_tc3_kernel(Tc3Tables tab, const Tc3Rec* __restrict__ recs, unsigned int* __
         store_rec(tid >> 5, lane, a, b);
     }
     __syncthreads();
-    if (warp >= 8 && warp < 16) prefetch_tile(0);
+    if (warp < 16) prefetch_tile(0);
 
     // Per-lane stage-2 store offset (INT): input n2 = lane -> K half (lane >> 4), K-group ((lane >> 2) & 3), 4-byte word (lane & 3)
     const uint32_t int_lane_off = (uint32_t)((lane >> 4) * (TC3_SLOTS * TC3_A2_TILE) + ((lane >> 2) & 3) * TC3_A2_LBO + (lane & 3) * 4);
@@ -504,34 +513,39 @@ mfcc_tc3_kernel(Tc3Tables tab, const Tc3Rec* __restrict__ recs, unsigned int* __
         const uint32_t idesc1 = tc3_idesc(16, true), idesc2 = tc3_idesc(64, false);
         const uint32_t a_lbo = 2048u, a_sbo = 128u;             // MN-major operand: K-group stride, 8-row-group stride
         const bool itimed = dbg_clk != nullptr && blockIdx.x == 0 && lane == 0 && dbg == 116;
-        long long ti1 = 0, ti2 = 0, tc2w = 0, tq = 0;
+        long long ti1 = 0, ti2 = 0, tq = 0;
+        // Decoupled from the workers' barrier: it waits only for the data of the MMAs it is about to issue.
+        //   MMA1(t): operand written (a1_ready: CONV(t)) and tile t - 1's stage-1 result read (d1_free: INT(t - 1))
+        //   MMA2(t): operand written (a2_ready: INT(t)) and the accumulator buffer drained (d2_free[t & 1]: EPI(t - 2))
+        if (lane == 0) {
 #pragma unroll 1
-        for (int k = -2; k <= K; ++k) {
-            if (lane == 0 && k + 1 >= 0 && k + 1 < K) {
-                if (k >= 0) mbar_wait(&sm.d1_free, k & 1);       // every worker has read tile k's stage-1 accumulators
-                if (itimed) tq = clock64();
-                tc5_fence_after();
-                uint64_t db[4];
+            for (int t = 0; t <= K; ++t) {
+                if (t < K) {
+                    mbar_wait(&sm.a1_ready, t & 1);
+                    if (t >= 1) mbar_wait(&sm.d1_free, (t - 1) & 1);
+                    if (itimed) tq = clock64();
+                    tc5_fence_after();
+                    uint64_t db[4];
 #pragma unroll
-                for (int v = 0; v < 4; ++v) db[v] = tc5_desc(&sm.b1[v][0][0][0], 256, 128);
+                    for (int v = 0; v < 4; ++v) db[v] = tc5_desc(&sm.b1[v][0][0][0], 256, 128);
 #pragma unroll 1
-                for (int i = 0; i < 8; ++i) {
-                    const uint64_t dah = tc5_desc(&sm.a1[i][0][0], a_lbo, a_sbo), dal = tc5_desc(&sm.a1[i][1][0], a_lbo, a_sbo);
-                    const uint32_t d = tmem + 16 * i;
-                    tcd_mma(d, dal, db[3], idesc1, 0);
-                    tcd_mma(d, dal, db[2], idesc1, 1);
-                    tcd_mma(d, dah, db[1], idesc1, 1);
-                    tcd_mma(d, dah, db[0], idesc1, 1);
+                    for (int i = 0; i < 8; ++i) {
+                        const uint64_t dah = tc5_desc(&sm.a1[i][0][0], a_lbo, a_sbo), dal = tc5_desc(&sm.a1[i][1][0], a_lbo, a_sbo);
+                        const uint32_t d = tmem + 16 * i;
+                        tcd_mma(d, dal, db[3], idesc1, 0);
+                        tcd_mma(d, dal, db[2], idesc1, 1);
+                        tcd_mma(d, dah, db[1], idesc1, 1);
+                        tcd_mma(d, dah, db[0], idesc1, 1);
+                    }
+                    tc5_commit(&sm.m1_done);
+                    if (itimed) ti1 += clock64() - tq;
                 }
-                tc5_commit(&sm.m1_done);
-                if (itimed) ti1 += clock64() - tq;
-            }
-            __syncwarp();
-            __syncthreads();                                     // (A)
-            if (lane == 0) {
-                if (itimed) tq = clock64();
-                tc5_fence_after();
-                if (k >= 0 && k < K) {
+                if (t >= 1) {
+                    const int k = t - 1;
+                    mbar_wait(&sm.a2_ready, k & 1);
+                    if (k >= 2) mbar_wait(&sm.d2_free[k & 1], ((k - 2) >> 1) & 1);
+                    if (itimed) tq = clock64();
+                    tc5_fence_after();
                     const uint32_t dcol = tmem + TC3_D1_COLS + (k & 1) * TC3_D2_COLS;
 #pragma unroll 1
                     for (int stage = 0; stage < 2; ++stage) {
@@ -540,23 +554,22 @@ mfcc_tc3_kernel(Tc3Tables tab, const Tc3Rec* __restrict__ recs, unsigned int* __
 #pragma unroll
                         for (int kk = 0; kk < 2; ++kk)
 #pragma unroll
-                            for (int s = 0; s < TC3_SLOTS; ++s) {
-                                const uint64_t off = (uint64_t)((s * TC3_A2_TILE + 2 * kk * TC3_A2_LBO) >> 4);
+                            for (int sl = 0; sl < TC3_SLOTS; ++sl) {
+                                const uint64_t off = (uint64_t)((sl * TC3_A2_TILE + 2 * kk * TC3_A2_LBO) >> 4);
                                 const uint64_t dbh = db_hi + (uint64_t)(2 * kk * 64), dbl = db_lo + (uint64_t)(2 * kk * 64);
-                                const uint32_t d = dcol + 64 * s;
+                                const uint32_t d = dcol + 64 * sl;
                                 tcd_mma(d, da_lo + off, dbh, idesc2, (stage | kk) != 0);
                                 tcd_mma(d, da_hi + off, dbl, idesc2, 1);
                                 tcd_mma(d, da_hi + off, dbh, idesc2, 1);
                             }
                     }
                     tc5_commit(&sm.m2_done);
-                    if (itimed) { const long long t = clock64(); ti2 += t - tq; mbar_wait(&sm.m2_done, k & 1); tc2w += clock64() - t; }
+                    if (itimed) ti2 += clock64() - tq;
                 }
             }
-            __syncwarp();
-            __syncthreads();                                     // (B)
         }
-        if (itimed) { dbg_clk[0] = ti1; dbg_clk[1] = ti2; dbg_clk[2] = tc2w; dbg_clk[3] = K; }
+        __syncwarp();
+        if (itimed) { dbg_clk[0] = ti1; dbg_clk[1] = ti2; dbg_clk[2] = 0; dbg_clk[3] = K; }
     } else {
         // optional timeline of one warp of CTA 0 (pb_debug_counters): cycles in INT, waiting at (A), in P, waiting at (B)
         const bool timed = dbg_clk != nullptr && dbg >= 100 && blockIdx.x == 0 && lane == 0 && warp == dbg - 100;
@@ -604,10 +617,9 @@ mfcc_tc3_kernel(Tc3Tables tab, const Tc3Rec* __restrict__ recs, unsigned int* __
                     }
                 }
                 fence_proxy_async();
+                mbar_arrive(&sm.a2_ready);                       // the stage-2 operand of tile k is complete once all workers are here
             }
-            if (timed) { t1 = clock64(); t_int += t1 - t0; }
-            __syncthreads();                                     // (A)
-            if (timed) { t0 = clock64(); t_wa += t0 - t1; }
+            if (timed) { t1 = clock64(); t_int += t1 - t0; t0 = t1; }
 
             // ================= P(k)
             if (warp < 8) {
@@ -635,6 +647,7 @@ mfcc_tc3_kernel(Tc3Tables tab, const Tc3Rec* __restrict__ recs, unsigned int* __
                         else { tc3_block_bins<G, 0>(t_row + 64, x0f, rise, seg); tc3_block_bins<G, 8>(t_row + 128, x0f, rise, seg); }
                     }
                     tc5_fence_before();
+                    mbar_arrive(&sm.d2_free[ke & 1]);            // this accumulator buffer may be overwritten (by tile ke + 2)
                     // this thread's share of the 20 mel sums and of the total power: one row of the exchange buffer, six 16-byte stores
                     {
                         float pv[24];
@@ -718,22 +731,25 @@ mfcc_tc3_kernel(Tc3Tables tab, const Tc3Rec* __restrict__ recs, unsigned int* __
                     fetch_rec(k + 4, lane, a, b);
                     Tc3Rec r;
                     reinterpret_cast<int4*>(&r)[0] = a; reinterpret_cast<int4*>(&r)[1] = b;
-                    if (r.frame != nullptr && (dbg & 4)) {      // per-line L2 prefetch of the frame (a per-lane bulk prefetch serialises: 10 k cycles per tile)
+                    if (r.frame != nullptr) {                    // everything tile k + 4 will read: into L2 now, line by line
                         const char* fp = reinterpret_cast<const char*>(r.frame) + 16 * (int)r.len0c;
                         for (int o = 0; o < 16 * (64 - (int)r.len0c); o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(fp + o));
+                        const char* tp = reinterpret_cast<const char*>(r.frame) + 16 * (int)r.tail_delta;
+                        for (int o = 0; o < 16 * (int)r.tail_nv; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(tp + o));
                     }
                     store_rec(k + 4, lane, a, b);
                 }
-                // ---- CONV(k + 2), then the PCM of tile k + 3 into the prefetch registers
-                if (k + 2 < K) {
-                    if (k + 2 >= 1) mbar_wait(&sm.m1_done, (k + 1) & 1);     // stage 1 of tile k + 1 has read the operand buffer
-                    conv_tile(k + 2);
-                    fence_proxy_async();
-                }
-                prefetch_tile(k + 3);
             }
+            // ---- CONV(k + 2) (every worker its share), then the PCM of tile k + 3 into the prefetch registers
+            if (k + 2 < K) {
+                if (k + 2 >= 1) mbar_wait(&sm.m1_done, (k + 1) & 1);         // stage 1 of tile k + 1 has read the operand buffer
+                conv_tile(k + 2);
+                fence_proxy_async();
+                mbar_arrive(&sm.a1_ready);                       // the stage-1 operand of tile k + 2 is complete once all workers are here
+            }
+            prefetch_tile(k + 3);
             if (timed) { t1 = clock64(); t_p += t1 - t0; }
-            __syncthreads();                                     // (B)
+            asm volatile("bar.sync 2, 512;" ::: "memory");       // workers only: frame records and exchange buffers change hands
             if (timed) t_wb += clock64() - t1;
         }
         if (timed) { dbg_clk[0] = t_int; dbg_clk[1] = t_wa; dbg_clk[2] = t_p; dbg_clk[3] = t_wb; }

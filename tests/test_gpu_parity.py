@@ -659,6 +659,7 @@ def test_alternative_mfcc_tick_kernels(k1_mode):
     pcm[0] = 0; pcm[1] = 32767; pcm[2] = -32768
     model = m.GruModel.random(13, 20, seed=9, scale=0.1)
     ref = m.StreamBatch(model, S, chunk_samples=chunk)
+    ref.core.k1_mode(2)                               # the FFT kernel whatever the batch size
     tc = m.StreamBatch(model, S, chunk_samples=chunk)
     tc.core.k1_mode(k1_mode)
     for k in range(K):
@@ -710,6 +711,33 @@ def test_two_stage_tensor_core_mfcc_vs_oracle_ragged(chunk):
     print('chunk', chunk, 'max |window - oracle|', worst)
     assert worst < 2e-4
     sb.core.close()
+
+
+def test_default_kernel_choice_large_tick_matches_fft_kernel():
+    """From 49 152 streams per tick on, the default MFCC kernel is mfcc_tc3 (tcgen05); its windows, network outputs and detections
+    must agree with the FFT kernel's on the same audio (many tiles per CTA, several CTAs per SM count, partial last tile)."""
+    m = _mod()
+    chunk, S, K = 1024, 49152 + 37, 30
+    base = noise(256, K * chunk, seed=77)
+    base[3] = 0; base[4] = 32767; base[5] = np.round(np.random.RandomState(1).randn(K * chunk) * 2)
+    pcm = np.tile(base, (S // 256 + 1, 1))[:S]
+    model = m.GruModel.random(13, 20, seed=9, scale=0.1)
+    model.dense_b = 3.0
+    a = m.StreamBatch(model, S, chunk_samples=chunk, sensitivity=0.9, trigger_level=0)
+    b = m.StreamBatch(model, S, chunk_samples=chunk, sensitivity=0.9, trigger_level=0)
+    b.core.k1_mode(2)
+    worst = 0.0
+    for k in range(K):
+        c = cuda(np.ascontiguousarray(pcm[:, k * chunk:(k + 1) * chunk]))
+        ra, rb = a.update(c), b.update(c)
+        worst = max(worst, float((ra['raw'] - rb['raw']).abs().max().item()))
+        if k % 7 == 6 or k == K - 1:
+            wa, wb = a.core.read_window(S), b.core.read_window(S)
+            assert float((wa - wb).abs().max().item()) < 2e-4, k
+    assert worst < 1e-4
+    ca, cb = int(a.count.item()), int(b.count.item())
+    assert ca > 0 and abs(ca - cb) <= max(3, ca // 5000), (ca, cb)
+    a.core.close(); b.core.close()
 
 
 def test_detection_counter_overlapped_allreduce_single_rank():
