@@ -28,15 +28,37 @@ def main(argv=None):
     stdout = sys.stdout
     sys.stdout = sys.stderr                      # keep the wire clean (engine.py:55-56)
     try:
-        from .runner import B200Listener, B200Engine
-        if args.chunk_size > 0 and args.chunk_size % 2 == 0:
+        from .runner import B200Listener, B200Engine, _resolve_model
+        from .params import ListenerParams
+        pr = _resolve_model(args.model_name)[1] or ListenerParams()
+        # The stateful device tick (B200Engine) covers even chunk sizes that complete at most 8 frames per tick; anything else
+        # (odd sizes, very large chunks, CHUNK_SIZE = -1) goes through the stateless mirror of Listener.update.
+        samples = args.chunk_size // 2
+        if args.chunk_size > 0 and args.chunk_size % 2 == 0 and samples // pr.hop_samples + 2 <= 8:
             eng = B200Engine(args.model_name, args.chunk_size, device=args.device)
             eng.start()
+            # Audio the window still depends on, cut at a multiple of hop_samples from the start of the stream: a short last
+            # read (the reference's Listener.update still answers it, network_runner.py:132-153) is replayed through the mirror.
+            hist = bytearray()
+            keep = 2 * (pr.buffer_samples + pr.window_samples + pr.hop_samples)
+            state = {'dropped': 0}
 
             def step():
                 chunk = sys.stdin.buffer.read(args.chunk_size)
-                if len(chunk) < args.chunk_size:           # b'' or a ragged last read: the reference's
-                    raise EOFError                         # Listener would block/raise here as well
+                if len(chunk) == 0:
+                    raise EOFError
+                if len(chunk) < args.chunk_size:           # ragged last read: same answer as the reference, through the mirror
+                    lis = B200Listener(args.model_name, -1, device=args.device)
+                    if len(hist):
+                        lis.update(bytes(hist))
+                    return lis.update(chunk[:len(chunk) & ~1])
+                hist.extend(chunk)
+                if len(hist) > 2 * keep:
+                    cut = len(hist) - keep
+                    cut -= (state['dropped'] + cut) % (2 * pr.hop_samples)     # keep the frame grid aligned
+                    if cut > 0:
+                        del hist[:cut]
+                        state['dropped'] += cut
                 return eng.get_prediction(chunk)
         else:
             lis = B200Listener(args.model_name, args.chunk_size, device=args.device)

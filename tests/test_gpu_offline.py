@@ -78,11 +78,34 @@ def test_engine_wire_protocol(tmp_path):
     w = og.GruWeights(model.kernel, model.recurrent, model.bias, model.dense_w, model.dense_b)
     raw, conf, fired = run_streams(w, pcm[None], 1024)
     got = np.array([float(x) for x in lines])
-    assert np.max(np.abs(got - conf[0])) < 5e-3
+    from oracle.decoder import OracleDecoder
+    from oracle.params import OracleParams
+    d = OracleDecoder(OracleParams().threshold_config, OracleParams().threshold_center)
+    step = np.max(np.abs(np.diff(d.cd))) * 2.5                     # at most a neighbouring LUT bin
+    assert np.max(np.abs(got - conf[0])) <= step
+    assert np.mean(got != conf[0]) < 0.1
+    # a short last read still gets its answer (reference: Listener.update processes whatever stream.read returned)
+    tail = np.clip(rs.randn(700) * 3000, -32768, 32767).astype('<i2')
+    r = subprocess.run([sys.executable, '-m', 'mycroft_precise_b200.engine', path, '2048'], input=pcm.tobytes() + tail.tobytes(),
+                       capture_output=True, env=env, timeout=300)
+    assert r.returncode == 0, r.stderr.decode()[-2000:]
+    lines2 = r.stdout.split(b'\n')[:-1]
+    assert len(lines2) == 31 and lines2[:30] == lines
+    from oracle.listener import OracleListener
+    lis = OracleListener(w)
+    for k in range(30):
+        lis.update(pcm[k * 1024:(k + 1) * 1024].astype(np.float32) / 32768.0)
+    assert abs(float(lines2[30]) - lis.update(tail.astype(np.float32) / 32768.0)) <= step
+    # chunks that complete more than 8 frames per tick go through the stateless mirror: same numbers, chunking-independent state
+    r = subprocess.run([sys.executable, '-m', 'mycroft_precise_b200.engine', path, str(2 * 10240)], input=pcm.tobytes(),
+                       capture_output=True, env=env, timeout=300)
+    assert r.returncode == 0, r.stderr.decode()[-2000:]
+    big = [float(x) for x in r.stdout.split(b'\n')[:-1]]
+    assert len(big) == 3 and all(abs(big[i] - conf[0, 10 * i + 9]) <= step for i in range(3))
     # chunk_size = -1: read everything, one prediction (precise/scripts/engine.py: default)
     r = subprocess.run([sys.executable, '-m', 'mycroft_precise_b200.engine', path], input=pcm.tobytes(),
                        capture_output=True, env=env, timeout=300)
     assert r.returncode == 0 and len(r.stdout.split(b'\n')) == 2
-    assert abs(float(r.stdout) - conf[0, -1]) < 5e-3          # state is chunking-independent
+    assert abs(float(r.stdout) - conf[0, -1]) <= step          # state is chunking-independent
     r = subprocess.run([sys.executable, '-m', 'mycroft_precise_b200.engine', '-v'], capture_output=True, env=env, timeout=120)
     assert r.stdout.strip() == m.__version__.encode()
