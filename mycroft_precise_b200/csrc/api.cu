@@ -973,7 +973,8 @@ static int ensure_tc3_tables(pb_handle* h) {
     CK(cudaMalloc((void**)&h->d_tc3_recs, (size_t)h->cfg.max_streams * (size_t)std::max(1, h->max_new) * sizeof(Tc3Rec)));
     CK(cudaMalloc((void**)&h->d_tc3_counters, 2 * sizeof(unsigned int)));
     CK(cudaMemset(h->d_tc3_counters, 0, 2 * sizeof(unsigned int)));
-    CK(ensure_dyn_smem(mfcc_tc3_kernel<Tc2Geo20>, sizeof(Tc3Smem) + 128));
+    CK(ensure_dyn_smem(mfcc_tc3_kernel<Tc2Geo20, false>, sizeof(Tc3Smem) + 128));
+    CK(ensure_dyn_smem(mfcc_tc3_kernel<Tc2Geo20, true>, sizeof(Tc3Smem) + 128));
     CK(cudaMalloc((void**)&h->d_tc3_b1, b1.size() * sizeof(__half)));      // last: its presence marks the set as complete
     CK(cudaMemcpy(h->d_tc3_b1, b1.data(), b1.size() * sizeof(__half), cudaMemcpyHostToDevice));
     return PB_OK;
@@ -1000,8 +1001,11 @@ static int launch_stream_mfcc(pb_handle* h, const int16_t* d_pcm, const int32_t*
         mfcc_tc3_plan_kernel<<<(int)((n + TC3_PLAN_THREADS - 1) / TC3_PLAN_THREADS), TC3_PLAN_THREADS, 0, s>>>(
             d_pcm, d_ids, (int)n, h->cfg.chunk_samples, h->cfg.hop_samples, h->st, h->d_tc3_recs, h->d_tc3_counters, par);
         const int64_t max_tiles = (n * std::max(1, h->max_new) + TC3_TILE - 1) / TC3_TILE;
-        mfcc_tc3_kernel<Tc2Geo20><<<(int)std::min<int64_t>(max_tiles, h->sm_count), TC3_THREADS, sizeof(Tc3Smem) + 128, s>>>(
-            t, h->d_tc3_recs, h->d_tc3_counters, par, h->k1_mode >= 100 ? h->k1_mode : 1, h->d_dbg);
+        const int g3 = (int)std::min<int64_t>(max_tiles, h->sm_count);
+        if (h->k1_mode >= 100)          // phase timeline of one warp (pb_debug_counters): separate instantiation, the counters cost registers
+            mfcc_tc3_kernel<Tc2Geo20, true><<<g3, TC3_THREADS, sizeof(Tc3Smem) + 128, s>>>(t, h->d_tc3_recs, h->d_tc3_counters, par, h->k1_mode, h->d_dbg);
+        else
+            mfcc_tc3_kernel<Tc2Geo20, false><<<g3, TC3_THREADS, sizeof(Tc3Smem) + 128, s>>>(t, h->d_tc3_recs, h->d_tc3_counters, par, 0, nullptr);
     } else if (h->k1_mode == 4 && h->tc2_ok && (uintptr_t)d_pcm % 16 == 0 && !h->force_generic) {
         int rc = ensure_tcd_tables(h);
         if (rc != PB_OK) return rc;

@@ -23,7 +23,7 @@
 //     P(k)     warp 16     MMA2(k)   (MMA1(k+1) as soon as every worker has read tile k's stage-1 result, during INT(k))
 //              warps 0-7   EPI(k-1), then a quarter of CONV(k+2)
 //              warps 8-15  new tails of tile k+1, frame records of tile k+4 (+ L2 prefetch), three quarters of CONV(k+2)
-//              CONV = prefetched PCM registers -> stage-1 operand, then the prefetch of tile k+3
+//              CONV = raw PCM copied by cp.async into the stage-1 operand buffer (L2-prefetched four tiles earlier), split in place
 // with one barrier of the worker warps per tile (the MMA warp follows mbarriers only); the MMAs of a tile run under the CUDA-core phases of its neighbours.  The frame list
 // (which frames complete this tick, where their samples are, the split of the first sample, new tail) is built by
 // mfcc_tc3_plan_kernel with every pointer ready to use.
@@ -307,6 +307,7 @@ struct Tc3Smem {
     float lgm[TC3_TILE][TC3_LGM_STRIDE];                 // log-mel values of the tile's frames
     float c0v[TC3_TILE];
     float dct[TCD_MAX_OUT][24];
+    float tw[32][16];                                    // twiddles of input n2 = lane (tc3_build_tw)
     Tc3Rec rec[TC3_REC_RING][TC3_TILE];
     unsigned long long m1_done, m2_done, d1_free, a1_ready, a2_ready, d2_free[2];
     uint32_t tmem_base;
@@ -388,7 +389,7 @@ __device__ __forceinline__ void tc3_block_bins(uint32_t taddr, float x0f, float 
     });
 }
 
-template <class G>
+template <class G, bool TIMED = false>
 __global__ void __launch_bounds__(TC3_THREADS, 1)
 mfcc_tc3_kernel(Tc3Tables tab, const Tc3Rec* __restrict__ recs, unsigned int* __restrict__ counters, int parity, int dbg, long long* __restrict__ dbg_clk) {
     extern __shared__ __align__(128) unsigned char tc3_raw[];
@@ -413,9 +414,7 @@ mfcc_tc3_kernel(Tc3Tables tab, const Tc3Rec* __restrict__ recs, unsigned int* __
     for (int e = tid; e < 1024; e += TC3_THREADS) reinterpret_cast<uint4*>(&sm.b2[0][0][0][0])[e] = __ldg(tab.b2 + e);
     if (tid < 128) reinterpret_cast<uint4*>(&sm.b1[0][0][0][0])[tid] = __ldg(tab.b1 + tid);
     for (int e = tid; e < TCD_MAX_OUT * 24; e += TC3_THREADS) (&sm.dct[0][0])[e] = __ldg(tab.dct + e);
-    float tw[16];
-#pragma unroll
-    for (int e = 0; e < 16; ++e) tw[e] = __ldg(tab.tw + lane * 16 + e);
+    for (int e = tid; e < 32 * 16; e += TC3_THREADS) (&sm.tw[0][0])[e] = __ldg(tab.tw + e);
     fence_proxy_async();
     tc5_fence_before();
     __syncthreads();
@@ -442,41 +441,49 @@ mfcc_tc3_kernel(Tc3Tables tab, const Tc3Rec* __restrict__ recs, unsigned int* __
         int4* p = reinterpret_cast<int4*>(&sm.rec[k & (TC3_REC_RING - 1)][f]);
         p[0] = a; p[1] = b;
     };
-    // CONV: warp 8 + w8 converts frames 3 w8 .. 3 w8 + 2 of a tile, warp w < 8 (after its epilogue share) frame 24 + w; lane (c4, l8)
-    // owns chunks 4 l8 + c4 and 32 + 4 l8 + c4 (8 samples each).
+    // CONV: warp 8 + w8 converts frames 3 w8 .. 3 w8 + 2 of a tile, warp w < 8 frame 24 + w; lane (c4, l8) owns chunks 4 l8 + c4 and
+    // 32 + 4 l8 + c4 (8 samples each).  The raw PCM is first copied asynchronously (cp.async: no registers, no waiting) into the
+    // lo-piece position of the stage-1 operand it will become; conv_tile later splits it in place.
     const int c4 = lane >> 3, l8 = lane & 7, cch = 4 * l8 + c4;
     const int cv_n = warp < 8 ? 1 : 3, cv_f0 = warp < 8 ? 24 + warp : 3 * (warp - 8);
-    uint4 pf[3][2];
-    auto prefetch_tile = [&](int k) {
+    auto a1_lo = [&](int fi) { return &sm.a1[fi >> 2][1][0] + (4 * (fi & 3) + c4) * 128 + l8 * 16; };
+    auto stage_tile = [&](int k) {
 #pragma unroll
         for (int m = 0; m < 3; ++m) {
             if (m < cv_n) {
-                pf[m][0] = make_uint4(0u, 0u, 0u, 0u); pf[m][1] = pf[m][0];
-                if (k < K) {
-                    const Tc3Rec& r = sm.rec[k & (TC3_REC_RING - 1)][cv_f0 + m];
-                    const int16_t* fp = r.frame;
-                    if (fp != nullptr) {
-                        const int l0 = r.len0c;
-                        const int16_t* tp = r.tail;
-                        pf[m][0] = *reinterpret_cast<const uint4*>((cch < l0 ? tp : fp) + 8 * cch);
-                        pf[m][1] = *reinterpret_cast<const uint4*>((cch + 32 < l0 ? tp : fp) + 8 * (cch + 32));
-                    }
+                const int fi = cv_f0 + m;
+                const Tc3Rec& r = sm.rec[k & (TC3_REC_RING - 1)][fi];
+                const int16_t* fp = r.frame;
+                unsigned char* dst = a1_lo(fi);
+                if (fp != nullptr) {
+                    const int l0 = r.len0c;
+                    const int16_t* tp = r.tail;
+                    const int16_t* s0 = (cch < l0 ? tp : fp) + 8 * cch;
+                    const int16_t* s1 = (cch + 32 < l0 ? tp : fp) + 8 * (cch + 32);
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(s0) : "memory");
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst + 2048)), "l"(s1) : "memory");
+                } else {                                         // padding of the last tile: zero samples (split constants of x0 = 0)
+                    *reinterpret_cast<uint4*>(dst) = make_uint4(0u, 0u, 0u, 0u);
+                    *reinterpret_cast<uint4*>(dst + 2048) = make_uint4(0u, 0u, 0u, 0u);
                 }
             }
         }
+        asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    // prefetch registers -> stage-1 operand tiles (exact split of x - x0 into fp16 pieces)
+    // staged PCM -> the two fp16 pieces of x - x0 (exact), in place
     auto conv_tile = [&](int k) {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
 #pragma unroll
         for (int m = 0; m < 3; ++m) {
             if (m < cv_n) {
                 const int fi = cv_f0 + m;
                 const uint32_t cc = *reinterpret_cast<const uint32_t*>(&sm.rec[k & (TC3_REC_RING - 1)][fi].c_lo);     // c_lo | c_hi << 16
                 const uint32_t c_lo = __byte_perm(cc, 0, 0x1010), c_hi = __byte_perm(cc, 0, 0x3232);
-                unsigned char* dst = &sm.a1[fi >> 2][0][0] + (4 * (fi & 3) + c4) * 128 + l8 * 16;
+                unsigned char* dst = a1_lo(fi);
 #pragma unroll
                 for (int hf = 0; hf < 2; ++hf) {
-                    const uint32_t w[4] = {pf[m][hf].x, pf[m][hf].y, pf[m][hf].z, pf[m][hf].w};
+                    const uint4 raw = *reinterpret_cast<const uint4*>(dst + hf * 2048);
+                    const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
                     uint32_t ah[4], al[4];
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
@@ -488,8 +495,8 @@ mfcc_tc3_kernel(Tc3Tables tab, const Tc3Rec* __restrict__ recs, unsigned int* __
                         const uint32_t t = tc3_hfma2(hi_magic, 0x20002000u, c_hi);            // (hi_floor - hi0) / 128   (0x2000 = 2^-7)
                         ah[e] = tc3_hfma2(mb, 0x64006400u, t);                                // + carry / 128            (0x6400 = 1024)
                     }
-                    *reinterpret_cast<uint4*>(dst + hf * 2048) = make_uint4(ah[0], ah[1], ah[2], ah[3]);
-                    *reinterpret_cast<uint4*>(dst + hf * 2048 + TC3_A1_TILE) = make_uint4(al[0], al[1], al[2], al[3]);
+                    *reinterpret_cast<uint4*>(dst + hf * 2048 - TC3_A1_TILE) = make_uint4(ah[0], ah[1], ah[2], ah[3]);
+                    *reinterpret_cast<uint4*>(dst + hf * 2048) = make_uint4(al[0], al[1], al[2], al[3]);
                 }
             }
         }
@@ -502,7 +509,6 @@ mfcc_tc3_kernel(Tc3Tables tab, const Tc3Rec* __restrict__ recs, unsigned int* __
         store_rec(tid >> 5, lane, a, b);
     }
     __syncthreads();
-    if (warp < 16) prefetch_tile(0);
 
     // Per-lane stage-2 store offset (INT): input n2 = lane -> K half (lane >> 4), K-group ((lane >> 2) & 3), 4-byte word (lane & 3)
     const uint32_t int_lane_off = (uint32_t)((lane >> 4) * (TC3_SLOTS * TC3_A2_TILE) + ((lane >> 2) & 3) * TC3_A2_LBO + (lane & 3) * 4);
@@ -512,7 +518,7 @@ mfcc_tc3_kernel(Tc3Tables tab, const Tc3Rec* __restrict__ recs, unsigned int* __
         // ================= the MMA-issuing warp: after INT(k), stage 1 of tile k + 1 and stage 2 of tile k
         const uint32_t idesc1 = tc3_idesc(16, true), idesc2 = tc3_idesc(64, false);
         const uint32_t a_lbo = 2048u, a_sbo = 128u;             // MN-major operand: K-group stride, 8-row-group stride
-        const bool itimed = dbg_clk != nullptr && blockIdx.x == 0 && lane == 0 && dbg == 116;
+        const bool itimed = TIMED && dbg_clk != nullptr && blockIdx.x == 0 && lane == 0 && dbg == 116;
         long long ti1 = 0, ti2 = 0, tq = 0;
         // Decoupled from the workers' barrier: it waits only for the data of the MMAs it is about to issue.
         //   MMA1(t): operand written (a1_ready: CONV(t)) and tile t - 1's stage-1 result read (d1_free: INT(t - 1))
@@ -572,7 +578,7 @@ mfcc_tc3_kernel(Tc3Tables tab, const Tc3Rec* __restrict__ recs, unsigned int* __
         if (itimed) { dbg_clk[0] = ti1; dbg_clk[1] = ti2; dbg_clk[2] = 0; dbg_clk[3] = K; }
     } else {
         // optional timeline of one warp of CTA 0 (pb_debug_counters): cycles in INT, waiting at (A), in P, waiting at (B)
-        const bool timed = dbg_clk != nullptr && dbg >= 100 && blockIdx.x == 0 && lane == 0 && warp == dbg - 100;
+        const bool timed = TIMED && dbg_clk != nullptr && dbg >= 100 && blockIdx.x == 0 && lane == 0 && warp == dbg - 100;
         long long t_int = 0, t_wa = 0, t_p = 0, t_wb = 0, t0 = 0, t1 = 0;
 #pragma unroll 1
         for (int k = -2; k <= K; ++k) {
@@ -581,7 +587,6 @@ mfcc_tc3_kernel(Tc3Tables tab, const Tc3Rec* __restrict__ recs, unsigned int* __
             if (k >= 0 && k < K) {
                 mbar_wait(&sm.m1_done, k & 1);
                 tc5_fence_after();
-                uint32_t wh[2][9], wl[2][9];
                 uint32_t yv[2][16];
                 tc3_ld16(tmem + ((uint32_t)(q4 * 32) << 16) + 32 * wg, yv[0]);
                 tc3_ld16(tmem + ((uint32_t)(q4 * 32) << 16) + 32 * wg + 16, yv[1]);
@@ -589,31 +594,29 @@ mfcc_tc3_kernel(Tc3Tables tab, const Tc3Rec* __restrict__ recs, unsigned int* __
                 tc3_wait_ld16(yv[1]);
                 tc5_fence_before();
                 mbar_arrive(&sm.d1_free);                        // the stage-1 accumulators may be overwritten
+                if (k >= 1) mbar_wait(&sm.m2_done, (k - 1) & 1); // the tensor core has read the previous tile's operands (long ago)
+                float tw[16];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float4 t4 = *reinterpret_cast<const float4*>(&sm.tw[lane][4 * q]);
+                    tw[4 * q] = t4.x; tw[4 * q + 1] = t4.y; tw[4 * q + 2] = t4.z; tw[4 * q + 3] = t4.w;
+                }
 #pragma unroll
                 for (int u = 0; u < 2; ++u) {
                     float y[16], zr[9], zi[9];
 #pragma unroll
                     for (int e = 0; e < 16; ++e) y[e] = __uint_as_float(yv[u][e]);
                     tc3_twiddle(y, tw, zr, zi);
+                    const int fr = 4 * (2 * wg + u) + q4;
+                    unsigned char* base = &sm.a2[0][0][0][0] + int_lane_off + fr * 16;
 #pragma unroll
                     for (int b = 0; b < TCD_BLOCKS; ++b) {
                         const __half2 hh = __floats2half2_rn(zr[b], zi[b]);
                         const float2 hf = __half22float2(hh);
                         const __half2 ll = __floats2half2_rn(zr[b] - hf.x, zi[b] - hf.y);
-                        wh[u][b] = *reinterpret_cast<const uint32_t*>(&hh);
-                        wl[u][b] = *reinterpret_cast<const uint32_t*>(&ll);
-                    }
-                }
-                if (k >= 1) mbar_wait(&sm.m2_done, (k - 1) & 1); // the tensor core has read the previous tile's operands
-#pragma unroll
-                for (int u = 0; u < 2; ++u) {
-                    const int fr = 4 * (2 * wg + u) + q4;
-                    unsigned char* base = &sm.a2[0][0][0][0] + int_lane_off + fr * 16;
-#pragma unroll
-                    for (int b = 0; b < TCD_BLOCKS; ++b) {
                         const int o = tc3_blk_s(b) * TC3_A2_TILE + 32 * tc3_blk_h(b) * 16;
-                        *reinterpret_cast<uint32_t*>(base + o) = wh[u][b];
-                        *reinterpret_cast<uint32_t*>(base + A2_PIECE + o) = wl[u][b];
+                        *reinterpret_cast<uint32_t*>(base + o) = *reinterpret_cast<const uint32_t*>(&hh);
+                        *reinterpret_cast<uint32_t*>(base + A2_PIECE + o) = *reinterpret_cast<const uint32_t*>(&ll);
                     }
                 }
                 fence_proxy_async();
@@ -648,6 +651,8 @@ mfcc_tc3_kernel(Tc3Tables tab, const Tc3Rec* __restrict__ recs, unsigned int* __
                     }
                     tc5_fence_before();
                     mbar_arrive(&sm.d2_free[ke & 1]);            // this accumulator buffer may be overwritten (by tile ke + 2)
+                    // PCM of tile k + 2 on its way (the copies land under the rest of the epilogue)
+                    if (k + 2 < K) { mbar_wait(&sm.m1_done, (k + 1) & 1); stage_tile(k + 2); }
                     // this thread's share of the 20 mel sums and of the total power: one row of the exchange buffer, six 16-byte stores
                     {
                         float pv[24];
@@ -740,14 +745,17 @@ mfcc_tc3_kernel(Tc3Tables tab, const Tc3Rec* __restrict__ recs, unsigned int* __
                     store_rec(k + 4, lane, a, b);
                 }
             }
-            // ---- CONV(k + 2) (every worker its share), then the PCM of tile k + 3 into the prefetch registers
+            // ---- CONV(k + 2), every worker its share.  Stage 1 of tile k + 1 must have read the operand buffer before the raw PCM
+            // of tile k + 2 is copied into it (epilogue warps with an epilogue to run have staged already, see above).
             if (k + 2 < K) {
-                if (k + 2 >= 1) mbar_wait(&sm.m1_done, (k + 1) & 1);         // stage 1 of tile k + 1 has read the operand buffer
+                if (!(warp < 8 && k >= 1)) {
+                    if (k + 2 >= 1) mbar_wait(&sm.m1_done, (k + 1) & 1);
+                    stage_tile(k + 2);
+                }
                 conv_tile(k + 2);
                 fence_proxy_async();
                 mbar_arrive(&sm.a1_ready);                       // the stage-1 operand of tile k + 2 is complete once all workers are here
             }
-            prefetch_tile(k + 3);
             if (timed) { t1 = clock64(); t_p += t1 - t0; }
             asm volatile("bar.sync 2, 512;" ::: "memory");       // workers only: frame records and exchange buffers change hands
             if (timed) t_wb += clock64() - t1;
