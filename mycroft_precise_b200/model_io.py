@@ -115,8 +115,16 @@ def model_from_keras_h5(f) -> GruModel:
         if len(hits) != 1:
             raise ValueError('expected one %r among %r' % (stem, sorted(ds)))
         return hits[0]
-    return GruModel(pick(g, 'kernel'), pick(g, 'recurrent_kernel'), pick(g, 'bias'),
-                    pick(d, 'kernel').reshape(-1), pick(d, 'bias'), act, ract)
+    k, u, b, dw, db = pick(g, 'kernel'), pick(g, 'recurrent_kernel'), pick(g, 'bias'), pick(d, 'kernel'), pick(d, 'bias')
+    # strict shape / dtype check: a mis-parsed file must not load plausible-looking garbage
+    H = u.shape[0] if u.ndim == 2 else -1
+    ok = (k.ndim == 2 and u.ndim == 2 and k.shape[1] == 3 * H and u.shape == (H, 3 * H) and b.shape == (3 * H,)
+          and dw.shape in ((H, 1), (H,)) and db.shape in ((1,), ()))
+    if not ok or any(a.dtype.kind != 'f' for a in (k, u, b, dw, db)):
+        raise ValueError('unexpected GRU / Dense dataset shapes or types in the Keras file: kernel %s %s, recurrent_kernel %s %s, '
+                         'bias %s %s, dense kernel %s %s, dense bias %s %s' % (k.shape, k.dtype, u.shape, u.dtype, b.shape, b.dtype,
+                                                                              dw.shape, dw.dtype, db.shape, db.dtype))
+    return GruModel(k, u, b, dw.reshape(-1), db, act, ract)
 
 
 def load_net(path: str) -> GruModel:
@@ -128,7 +136,10 @@ def load_net(path: str) -> GruModel:
     try:
         import h5py
     except ImportError:
+        import warnings
         from .h5_import import H5File
+        warnings.warn('h5py is not installed: reading %s with the built-in HDF5 reader (validated against spec-following test files '
+                      'only, not against Keras-written files); convert once where h5py exists if in doubt' % path, RuntimeWarning)
         with H5File(path) as f:
             return model_from_keras_h5(f)
     with h5py.File(path, 'r') as f:
