@@ -432,7 +432,7 @@ PB_API int pb_create(const pb_config* cfg, pb_handle** out) {
     CKH(cudaMemset(h->st.n_samples, 0, S * sizeof(long long)));
     CKH(cudaMemset(h->st.tail, 0, S * h->tail_cap * sizeof(int16_t)));
     CKH(cudaMemset(h->st.ring, 0, S * h->ring_rows * h->row_stride * sizeof(float)));
-    if (h->has_proj) CKH(cudaMalloc((void**)&h->d_proj_ring, S * h->ring_rows * PROJ_STRIDE * sizeof(float)));
+    if (h->has_proj) CKH(cudaMalloc((void**)&h->d_proj_ring, ((S + 15) / 16) * h->ring_rows * PROJ_BLOCK * sizeof(float)));
     CKH(cudaMemset(h->st.trig, 0, S * sizeof(int)));
     CKH(cudaMalloc((void**)&h->d_count, sizeof(unsigned long long)));
     CKH(cudaMemset(h->d_count, 0, sizeof(unsigned long long)));
@@ -1056,7 +1056,8 @@ static int rebuild_projections_if_dirty(pb_handle* h, cudaStream_t s) {
     ProfScope ps(h, 3, s);
     const long long rows = (long long)h->cfg.max_streams * h->ring_rows;
     const int grid = (int)std::min<long long>((rows + PROJ_FRAMES_PER_CTA - 1) / PROJ_FRAMES_PER_CTA, (long long)h->sm_count * 16);
-    input_proj_all_kernel<13><<<grid, 64 * PROJ_FRAMES_PER_CTA, 0, s>>>(h->d_proj_w, h->d_proj_b, rows, h->st.ring, h->row_stride, h->d_proj_ring);
+    input_proj_all_kernel<13><<<grid, 64 * PROJ_FRAMES_PER_CTA, 0, s>>>(h->d_proj_w, h->d_proj_b, rows, h->st.ring, h->ring_rows, h->row_stride, h->d_proj_ring,
+                                                                       (h->cfg.max_streams + 15) / 16);
     CK(cudaGetLastError());
     h->proj_dirty = false;
     return PB_OK;
@@ -1083,7 +1084,8 @@ PB_API int pb_update(pb_handle* h, const int16_t* d_pcm, const int32_t* d_ids, i
         const long long items = (long long)n * h->max_new;
         const int grid = (int)((items + PROJ_THREADS - 1) / PROJ_THREADS);     // 32 frames per warp
         input_proj_kernel<13><<<grid, PROJ_THREADS, 0, s>>>(h->d_bfrag, h->d_proj_b, h->st.n_samples, d_ids, (int)n,
-            h->cfg.chunk_samples, h->used, h->cfg.hop_samples, h->max_new, h->st.ring, h->ring_rows, h->row_stride, h->d_proj_ring);
+            h->cfg.chunk_samples, h->used, h->cfg.hop_samples, h->max_new, h->st.ring, h->ring_rows, h->row_stride, h->d_proj_ring,
+            (h->cfg.max_streams + 15) / 16);
         CK(cudaGetLastError());
     } else if (h->has_proj && h->small_path) {
         h->proj_dirty = true;                                  // this tick's frames get no projection
@@ -1095,6 +1097,7 @@ PB_API int pb_update(pb_handle* h, const int16_t* d_pcm, const int32_t* d_ids, i
     in.T = h->cfg.n_features; in.F_base = h->n_out; in.use_delta = h->cfg.use_delta;
     K2Out o{};
     in.proj = use_proj ? h->d_proj_ring : nullptr;
+    in.proj_tiles = (h->cfg.max_streams + 15) / 16;
     in.chunk = h->cfg.chunk_samples;
     o.raw = d_raw; o.conf = d_conf; o.fired = d_fired; o.count = d_count; o.trig = h->st.trig;
     return launch_gru(h, in, true, n, decode_params(h), o, s);

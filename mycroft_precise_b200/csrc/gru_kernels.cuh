@@ -47,7 +47,8 @@ struct K2In {
     int ring_rows, row_stride, window, hop;
     int T, F_base;                   // F_base = MFCC width (without deltas)
     int use_delta;
-    const float* proj;               // non-null: cached input projections x.W + b, [max_streams][ring_rows][PROJ_STRIDE], same slots as ring
+    const float* proj;               // non-null: cached input projections x.W + b, tile-major [ring_rows][proj_tiles] blocks of PROJ_BLOCK floats (see proj_off), same slots as ring
+    int proj_tiles;                  // ceil(max_streams / 16)
     int chunk;                       // samples added by this tick (to tell which window rows are new)
 };
 
@@ -137,15 +138,16 @@ struct RingCursor {
         rows = in.ring_rows; stride = in.row_stride;
         base = in.ring + (long long)sid * in.ring_rows * in.row_stride;
     }
-    // same window over the projection ring (rows of `pstride` floats)
-    __device__ __forceinline__ void init_proj(const K2In& in, int sid, long long released, int pstride) {
+    // same window over the projection cache: next() returns the 16-stream block of this stream's tile at the step's slot
+    // (blocks of `pblock` floats, slot-major); the row's position inside the block is proj_off(nt, sid & 15, t)
+    __device__ __forceinline__ void init_proj(const K2In& in, int sid, long long released, int pblock) {
         init(in, sid, released);
-        stride = pstride;
-        base = in.proj + (long long)sid * in.ring_rows * pstride;
+        stride = in.proj_tiles * pblock;
+        base = in.proj + (long long)(sid >> 4) * pblock;
     }
     // row of step t (call with t = 0, 1, 2, ... in order), nullptr for a zero row
     __device__ __forceinline__ const float* next(int t) {
-        const float* r = t >= lead ? base + slot * stride : nullptr;
+        const float* r = t >= lead ? base + (long long)slot * stride : nullptr;
         slot = slot + 1 == rows ? 0 : slot + 1;
         return r;
     }
@@ -397,10 +399,17 @@ gru_warp_kernel(const __grid_constant__ GruSmallW<H, F> P, K2In in, long long n,
 // units 8*tile + 2t, 2t+1).  The weight fragments are permuted once on the host to match; turning h
 // (C layout) into the next step's A operand then needs no shuffle at all.
 constexpr int PROJ_COLS = 72;        // padded gate columns of the fragment layout: 24 * gate + unit
-constexpr int PROJ_STRIDE = 60;      // stored projection row: 20 * gate + unit (the padding units are not stored)
+constexpr int PROJ_STRIDE = 60;      // projection values per frame: 20 * gate + unit (the padding units are not stored)
+constexpr int PROJ_BLOCK = 16 * PROJ_STRIDE;    // floats of one (slot, 16-stream tile) block of the cache
 constexpr int PROJ_FRAMES_PER_CTA = 4;
-// position in a stored projection row of accumulator columns (2t, 2t+1) of n-tile nt (gate nt / 3, units 8 (nt % 3) + 2t, +1)
-__device__ __forceinline__ int proj_col(int nt, int t) { return 20 * (nt / 3) + 8 * (nt % 3) + 2 * t; }
+// Layout of a block: the scan's accumulator-fragment order, so that one LDG.64 of a warp (n-tile nt, row half hf; lane = 4 g + t reads
+// columns 2t, 2t + 1 of row g + 8 hf) is 256 contiguous bytes when the tile's 16 streams sit at the same ring slot -- 2 cache lines
+// per request instead of 8 scattered 32-byte sectors (round 2: the row-major cache kept the scan bound by L1 line requests,
+// 144 per warp and step).  Full n-tiles (nt % 3 != 2, 8 units) first: [6][16 rows][4 t][2]; then the half n-tiles (units 16..19 of
+// a gate, t < 2): [3][16 rows][2 t][2].
+__host__ __device__ __forceinline__ int proj_off(int nt, int r16, int t) {
+    return nt % 3 != 2 ? ((nt / 3) * 2 + nt % 3) * 128 + r16 * 8 + 2 * t : 768 + (nt / 3) * 64 + r16 * 4 + 2 * t;
+}
 
 constexpr int MMA_KT = 5;            // k tiles: 2 for x (F <= 16), 3 for h (H <= 24)
 constexpr int MMA_NT = 9;            // n tiles: z, r, h gates x 3 tiles of 8 units
@@ -487,7 +496,7 @@ gru_mma_kernel(GruMmaW W, K2In in, long long n, DecodeParams dp, K2Out out) {
                 sid[mb][hf] = in.ids ? in.ids[idx[mb][hf]] : (int)idx[mb][hf];
                 const long long ns = in.n_samples[sid[mb][hf]];
                 rel[mb][hf] = ns >= in.window ? (ns - in.window) / in.hop + 1 : 0;
-                if (PROJ) cur[mb][hf].init_proj(in, sid[mb][hf], rel[mb][hf], PROJ_STRIDE);
+                if (PROJ) cur[mb][hf].init_proj(in, sid[mb][hf], rel[mb][hf], PROJ_BLOCK);
                 else cur[mb][hf].init(in, sid[mb][hf], rel[mb][hf]);
             }
         }
@@ -514,7 +523,7 @@ gru_mma_kernel(GruMmaW W, K2In in, long long n, DecodeParams dp, K2Out out) {
                     for (int nt = 0; nt < MMA_NT; ++nt) {
                         float2 v;
                         if (row == nullptr) v = make_float2(sBias[8 * nt + 2 * t], sBias[8 * nt + 2 * t + 1]);
-                        else if (nt % 3 != 2 || t < 2) v = __ldg(reinterpret_cast<const float2*>(row + proj_col(nt, t)));
+                        else if (nt % 3 != 2 || t < 2) v = __ldg(reinterpret_cast<const float2*>(row + proj_off(nt, sid[mb][hf] & 15, t)));
                         else v = make_float2(0.f, 0.f);                  // padding units 20..23 of a gate: not stored
                         acc[mb][nt][2 * hf] = v.x; acc[mb][nt][2 * hf + 1] = v.y;
                     }
@@ -648,7 +657,7 @@ template <int F>
 __global__ void __launch_bounds__(PROJ_THREADS, 6)
 input_proj_kernel(const float4* __restrict__ bfrag, const float* __restrict__ bias, const long long* __restrict__ n_samples,
                   const int* __restrict__ ids, int n, int chunk, int need, int hop, int max_new,
-                  const float* __restrict__ ring, int ring_rows, int row_stride, float* __restrict__ proj) {
+                  const float* __restrict__ ring, int ring_rows, int row_stride, float* __restrict__ proj, int proj_tiles) {
     __shared__ float4 sB[2 * MMA_NT * 32];
     __shared__ float sBias[PROJ_COLS];
     for (int e = threadIdx.x; e < 2 * MMA_NT * 32; e += blockDim.x) sB[e] = __ldg(bfrag + e);
@@ -660,11 +669,12 @@ input_proj_kernel(const float4* __restrict__ bfrag, const float* __restrict__ bi
     if (base >= items) return;
     const float* rows[MMA_MB][2];
     float* prow[MMA_MB][2];
+    int r16[MMA_MB][2];
 #pragma unroll
     for (int mb = 0; mb < MMA_MB; ++mb)
 #pragma unroll
         for (int hf = 0; hf < 2; ++hf) {
-            rows[mb][hf] = nullptr; prow[mb][hf] = nullptr;
+            rows[mb][hf] = nullptr; prow[mb][hf] = nullptr; r16[mb][hf] = 0;
             const long long item = base + 16 * mb + g + 8 * hf;
             if (item < items) {
                 const int j = (int)(item / n);
@@ -673,9 +683,10 @@ input_proj_kernel(const float4* __restrict__ bfrag, const float* __restrict__ bi
                 const long long n1 = n_samples[sid], n0 = n1 - chunk;
                 const long long c0 = n0 >= need ? (n0 - need) / hop + 1 : 0, c1 = n1 >= need ? (n1 - need) / hop + 1 : 0;
                 if (j < c1 - c0) {
-                    const long long r = (long long)sid * ring_rows + (int)((c0 + j) % ring_rows);
-                    rows[mb][hf] = ring + r * row_stride;
-                    prow[mb][hf] = proj + r * PROJ_STRIDE;
+                    const int slot = (int)((c0 + j) % ring_rows);
+                    rows[mb][hf] = ring + ((long long)sid * ring_rows + slot) * row_stride;
+                    prow[mb][hf] = proj + ((long long)slot * proj_tiles + (sid >> 4)) * PROJ_BLOCK;
+                    r16[mb][hf] = sid & 15;
                 }
             }
         }
@@ -729,7 +740,7 @@ input_proj_kernel(const float4* __restrict__ bfrag, const float* __restrict__ bi
 #pragma unroll
                     for (int q = 0; q < 3; ++q)
                         if (q < 2 || t < 2)                          // ng is a multiple of 3: q == 2 is the half-empty tile of the gate
-                            *reinterpret_cast<float2*>(prow[mb][hf] + proj_col(ng + q, t)) = make_float2(acc[mb][q][2 * hf], acc[mb][q][2 * hf + 1]);
+                            *reinterpret_cast<float2*>(prow[mb][hf] + proj_off(ng + q, r16[mb][hf], t)) = make_float2(acc[mb][q][2 * hf], acc[mb][q][2 * hf + 1]);
                 }
     }
 }
@@ -739,7 +750,7 @@ input_proj_kernel(const float4* __restrict__ bfrag, const float* __restrict__ bi
 template <int F>
 __global__ void __launch_bounds__(64 * PROJ_FRAMES_PER_CTA)
 input_proj_all_kernel(const float* __restrict__ wx, const float* __restrict__ bias, long long total_rows,
-                      const float* __restrict__ ring, int row_stride, float* __restrict__ proj) {
+                      const float* __restrict__ ring, int ring_rows, int row_stride, float* __restrict__ proj, int proj_tiles) {
     __shared__ float sW[F * PROJ_COLS];
     for (int e = threadIdx.x; e < F * PROJ_COLS; e += blockDim.x) sW[e] = __ldg(wx + e);
     __syncthreads();
@@ -751,7 +762,9 @@ input_proj_all_kernel(const float* __restrict__ wx, const float* __restrict__ bi
         float a = __ldg(bias + col);
 #pragma unroll
         for (int f = 0; f < F; ++f) a = fmaf(row[f], sW[f * PROJ_COLS + col], a);
-        proj[r * PROJ_STRIDE + c] = a;
+        const long long sid = r / ring_rows;
+        const int slot = (int)(r - sid * ring_rows), unit = c % 20, nt = 3 * (c / 20) + unit / 8;
+        proj[((long long)slot * proj_tiles + (sid >> 4)) * PROJ_BLOCK + proj_off(nt, (int)(sid & 15), (unit & 7) >> 1) + (unit & 1)] = a;
     }
 }
 

@@ -180,7 +180,7 @@ gru_tc5_kernel(GruTc5W W, K2In in, long long n, DecodeParams dp, K2Out out) {
         sid = in.ids ? in.ids[i] : (int)i;
         const long long ns = in.n_samples[sid];
         const long long rel = ns >= in.window ? (ns - in.window) / in.hop + 1 : 0;
-        if (PROJ) cur.init_proj(in, sid, rel, PROJ_STRIDE);
+        if (PROJ) cur.init_proj(in, sid, rel, PROJ_BLOCK);
         else cur.init(in, sid, rel);
     }
     float h[24];
@@ -218,13 +218,14 @@ gru_tc5_kernel(GruTc5W W, K2In in, long long n, DecodeParams dp, K2Out out) {
 #pragma unroll
         for (int j = 0; j < 24; ++j) { pz[j] = sm.bias[j]; pr[j] = sm.bias[24 + j]; ph[j] = sm.bias[TC5_N1 + j]; }
         if (PROJ && prow != nullptr) {
+            // the cache is laid out for the mma.sync scan's fragments (proj_off): unit pairs (2u, 2u + 1) of a gate are adjacent
 #pragma unroll
-            for (int q = 0; q < 5; ++q) {
-                const float4 a = __ldg(reinterpret_cast<const float4*>(prow) + q), b = __ldg(reinterpret_cast<const float4*>(prow + 20) + q),
-                             c = __ldg(reinterpret_cast<const float4*>(prow + 40) + q);
-                pz[4 * q] = a.x; pz[4 * q + 1] = a.y; pz[4 * q + 2] = a.z; pz[4 * q + 3] = a.w;
-                pr[4 * q] = b.x; pr[4 * q + 1] = b.y; pr[4 * q + 2] = b.z; pr[4 * q + 3] = b.w;
-                ph[4 * q] = c.x; ph[4 * q + 1] = c.y; ph[4 * q + 2] = c.z; ph[4 * q + 3] = c.w;
+            for (int u = 0; u < 10; ++u) {
+                const int nt0 = (2 * u) / 8, tt = ((2 * u) & 7) >> 1;
+                const float2 a = __ldg(reinterpret_cast<const float2*>(prow + proj_off(nt0, sid & 15, tt)));
+                const float2 b = __ldg(reinterpret_cast<const float2*>(prow + proj_off(3 + nt0, sid & 15, tt)));
+                const float2 c = __ldg(reinterpret_cast<const float2*>(prow + proj_off(6 + nt0, sid & 15, tt)));
+                pz[2 * u] = a.x; pz[2 * u + 1] = a.y; pr[2 * u] = b.x; pr[2 * u + 1] = b.y; ph[2 * u] = c.x; ph[2 * u + 1] = c.y;
             }
         }
         mbar_wait(&sm.bar[0], step & 1);
