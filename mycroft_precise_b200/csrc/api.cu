@@ -564,6 +564,7 @@ PB_API int pb_load_weights(pb_handle* h, const float* kernel, const float* recur
             for (int u = 0; u < H; ++u) { tb[u] = bias[u]; tb[24 + u] = bias[H + u]; tb[48 + u] = bias[2 * H + u]; tw[u] = dense_w[u]; }
             cudaFree(h->d_tc5); h->d_tc5 = nullptr;
             CK(upload(&h->d_tc5, t));
+            CK(ensure_dyn_smem(gru_mma_kernel<20, 13, true, true, 1, true>, (size_t)K2_STAGED_SMEM));
             CK(ensure_dyn_smem(gru_tc5_kernel<20, 13, true>, (size_t)(sizeof(Tc5Smem) + 128)));
             CK(ensure_dyn_smem(gru_tc5_kernel<20, 13, false>, (size_t)(sizeof(Tc5Smem) + 128)));
             CK(ensure_dyn_smem(gru_tc5_kernel<20, 13, true, true>, (size_t)(sizeof(Tc5Smem) + 128)));
@@ -860,7 +861,10 @@ static int launch_gru(pb_handle* h, const K2In& in, bool ring, int64_t n, const 
         // dependent chain); 16-stream tiles fit 5 CTAs/SM and leave a much shorter tail.
         if (ring && in.proj != nullptr && h->gru_mode != 7) {
             const int per1 = (MMA_THREADS / 32) * 16;
-            gru_mma_kernel<20, 13, true, true, 1><<<(int)((n + per1 - 1) / per1), MMA_THREADS, 0, s>>>(w, in, n, dp, o);
+            if (h->gru_mode == 9)            // A/B: the scan without bulk-copy staging of the projection blocks
+                gru_mma_kernel<20, 13, true, true, 1><<<(int)((n + per1 - 1) / per1), MMA_THREADS, 0, s>>>(w, in, n, dp, o);
+            else
+                gru_mma_kernel<20, 13, true, true, 1, true><<<(int)((n + per1 - 1) / per1), MMA_THREADS, K2_STAGED_SMEM, s>>>(w, in, n, dp, o);
         } else if (ring && in.proj != nullptr) gru_mma_kernel<20, 13, true, true><<<grid, MMA_THREADS, 0, s>>>(w, in, n, dp, o);
         else if (ring) gru_mma_kernel<20, 13, true, false><<<grid, MMA_THREADS, 0, s>>>(w, in, n, dp, o);
         else gru_mma_kernel<20, 13, false, false><<<grid, MMA_THREADS, 0, s>>>(w, in, n, dp, o);
@@ -1047,7 +1051,7 @@ PB_API int pb_update_vectors(pb_handle* h, const int16_t* d_pcm, const int32_t* 
 
 // Does a tick of n streams run the scan that reads cached input projections (gru_mma_kernel<.., PROJ>)?
 static bool wants_projection(const pb_handle* h, int64_t n) {
-    return h->has_proj && h->small_path && n > K2_WARP_PATH_MAX && (h->gru_mode == 0 || h->gru_mode == 2 || h->gru_mode == 7 || h->gru_mode == 8);
+    return h->has_proj && h->small_path && n > K2_WARP_PATH_MAX && (h->gru_mode == 0 || h->gru_mode == 2 || h->gru_mode == 7 || h->gru_mode == 8 || h->gru_mode == 9);
 }
 
 // Recompute the projection of every ring row once (all streams), then the cache is maintained incrementally.

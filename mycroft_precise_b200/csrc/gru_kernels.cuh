@@ -16,6 +16,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "mfcc_fast.cuh"      // smem_u32, mbarrier and bulk-copy helpers (staged projection blocks of the tensor-core scan)
+
 namespace pb {
 
 struct DecodeParams {
@@ -465,10 +467,19 @@ __device__ __forceinline__ void split_tf32(const float (&v)[4], uint32_t (&hi)[4
 // 162 instead of 270 HMMA per step on the pipe that bounds this kernel.
 // MB = row blocks of 16 streams per warp.  2 halves the weight-fragment traffic per MMA; 1 halves the tile (and the
 // registers: 5 instead of 3 CTAs per SM), which matters for the tail of the grid -- see launch_gru.
-template <int H, int F, bool RING, bool PROJ, int MB = MMA_MB>
-__global__ void __launch_bounds__(MMA_THREADS, MB == 1 ? 5 : 3)
+// STAGED (PROJ, MB = 1): a warp whose 16 streams form one aligned tile at one ring slot (the common case: streams in lock step)
+// reads a step's projections as ONE contiguous 3840-byte block -- fetched by a bulk async copy (cp.async.bulk, SASS UBLKCP) into
+// a per-warp double buffer two steps ahead, completion on an mbarrier; the accumulators then start from conflict-free LDS.64.
+// No register and no scoreboard wait sits between DRAM and the MMAs.  Other warps (ragged ids / ages) keep the LDG path.
+constexpr int K2_STAGE_BYTES = PROJ_BLOCK * 4;                                       // 3840
+constexpr int K2_STAGED_SMEM = (MMA_THREADS / 32) * (2 * K2_STAGE_BYTES + 16);      // + two mbarriers per warp
+
+template <int H, int F, bool RING, bool PROJ, int MB = MMA_MB, bool STAGED = false>
+__global__ void __launch_bounds__(MMA_THREADS, MB == 1 ? (STAGED ? 4 : 5) : 3)
 gru_mma_kernel(GruMmaW W, K2In in, long long n, DecodeParams dp, K2Out out) {
     static_assert(H <= 24 && F <= 16, "tile counts are fixed");
+    static_assert(!STAGED || (PROJ && RING && MB == 1), "staging serves the stream scan over cached projections");
+    extern __shared__ __align__(128) unsigned char k2_stage_raw[];
     __shared__ float4 sB[MMA_KT * MMA_NT * 32];
     __shared__ float sBias[3 * 24];
     __shared__ float sWd[24];
@@ -509,10 +520,63 @@ gru_mma_kernel(GruMmaW W, K2In in, long long n, DecodeParams dp, K2Out out) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) hreg[mb][nt][e] = 0.f;
 
+    // ---- STAGED: is this warp's tile uniform?  Then its projection blocks arrive by bulk copies.
+    bool staged = false;
+    float* stg = nullptr;
+    unsigned long long* sbar = nullptr;
+    const float* sblock = nullptr;                      // block of the tile at slot 0
+    int s_slot0 = 0, s_lead = 0, s_rows = 1;
+    long long s_stride = 0;
+    uint32_t s_ph0 = 0, s_ph1 = 0;
+    if constexpr (STAGED) {
+        stg = reinterpret_cast<float*>(k2_stage_raw + warp * 2 * K2_STAGE_BYTES);
+        sbar = reinterpret_cast<unsigned long long*>(k2_stage_raw + (MMA_THREADS / 32) * 2 * K2_STAGE_BYTES) + 2 * warp;
+        const int sid0 = __shfl_sync(0xffffffffu, sid[0][0], 0);
+        const int sl0 = __shfl_sync(0xffffffffu, cur[0][0].slot, 0), ld0 = __shfl_sync(0xffffffffu, cur[0][0].lead, 0);
+        const bool same = ok[0][0] && ok[0][1] && (sid0 & 15) == 0 && sid[0][0] == sid0 + g && sid[0][1] == sid0 + g + 8 &&
+                          cur[0][0].slot == sl0 && cur[0][1].slot == sl0 && cur[0][0].lead == ld0 && cur[0][1].lead == ld0;
+        staged = __all_sync(0xffffffffu, same);
+        if (staged) {
+            s_slot0 = sl0; s_lead = ld0; s_rows = cur[0][0].rows; s_stride = cur[0][0].stride; sblock = cur[0][0].base;
+            if (lane == 0) { mbar_init(&sbar[0], 1); mbar_init(&sbar[1], 1); fence_mbar_init(); }
+            __syncwarp();
+        }
+    }
+    auto stage_issue = [&](int st) {                    // lane 0: the block of step st into buffer st & 1
+        int sl = s_slot0 + st;
+        if (sl >= s_rows) sl -= s_rows;
+        unsigned long long* bar = &sbar[st & 1];
+        mbar_expect_tx(bar, (uint32_t)K2_STAGE_BYTES);
+        bulk_g2s(stg + (st & 1) * PROJ_BLOCK, sblock + (long long)sl * s_stride, (uint32_t)K2_STAGE_BYTES, bar);
+    };
+    if (STAGED && staged && lane == 0) {
+        if (s_lead < in.T) stage_issue(s_lead);
+        if (s_lead + 1 < in.T) stage_issue(s_lead + 1);
+    }
+
 #pragma unroll 1
     for (int step = 0; step < in.T; ++step) {
         float acc[MB][MMA_NT][4];
-        if (PROJ) {
+        if (STAGED && staged) {
+            // ---- accumulators from the staged block (bias for the rows before the stream's first frame)
+            const bool real = step >= s_lead;
+            const float* blk = stg + (step & 1) * PROJ_BLOCK;
+            if (real) {
+                if (step & 1) { mbar_wait(&sbar[1], s_ph1); s_ph1 ^= 1u; } else { mbar_wait(&sbar[0], s_ph0); s_ph0 ^= 1u; }
+            }
+#pragma unroll
+            for (int mb = 0; mb < MB; ++mb)
+#pragma unroll
+                for (int hf = 0; hf < 2; ++hf)
+#pragma unroll
+                    for (int nt = 0; nt < MMA_NT; ++nt) {
+                        float2 v;
+                        if (!real) v = make_float2(sBias[8 * nt + 2 * t], sBias[8 * nt + 2 * t + 1]);
+                        else if (nt % 3 != 2 || t < 2) v = *reinterpret_cast<const float2*>(blk + proj_off(nt, g + 8 * hf, t));
+                        else v = make_float2(0.f, 0.f);
+                        acc[mb][nt][2 * hf] = v.x; acc[mb][nt][2 * hf + 1] = v.y;
+                    }
+        } else if (PROJ) {
             // ---- accumulators start from the cached projection (bias included); rows before the stream's first frame: bias
 #pragma unroll
             for (int mb = 0; mb < MB; ++mb)
@@ -621,6 +685,10 @@ gru_mma_kernel(GruMmaW W, K2In in, long long n, DecodeParams dp, K2Out out) {
                     const float z = hard_sigmoid(acc[mb][nt][e]);
                     hreg[mb][nt][e] = z * hreg[mb][nt][e] + (1.f - z) * acc[mb][6 + nt][e];      // linear candidate
                 }
+        if (STAGED && staged && step >= s_lead && step + 2 < in.T) {     // this step's buffer has been consumed by every lane: refill it
+            __syncwarp();
+            if (lane == 0) stage_issue(step + 2);
+        }
     }
     // ---- Dense(1): per-thread partial over its 6 units per row, reduced over the quad
 #pragma unroll
