@@ -11,6 +11,7 @@
 
 #include <algorithm>
 #include <map>
+#include <cuda_fp16.h>
 #include <mutex>
 #include <new>
 #include <utility>
@@ -104,6 +105,7 @@ struct pb_handle {
     GruSmallW<20, 13> w_small;
     float *d_wcat = nullptr, *d_bias = nullptr, *d_wd = nullptr;
     float4* d_bfrag = nullptr;       // tensor-core GRU: pre-split, fragment-ordered weights
+    uint4* d_bfrag16 = nullptr;      // ... recurrent part as fp16 hi / lo fragments (gru_mma16_kernel)
     float *d_mma_bias = nullptr, *d_mma_wd = nullptr;
     long long* d_dbg = nullptr;       // optional debug counters (pb_debug_counters)
     float *d_tcb = nullptr;           // tcgen05 wide-network GRU: [b1 tiles | b2 tiles | bias(384) | wd(128)]
@@ -264,7 +266,7 @@ PB_API void pb_destroy(pb_handle* h) {
     cudaFree(h->d_tw_stage); cudaFree(h->d_tw_post); cudaFree(h->d_tw_any); cudaFree(h->d_cd); cudaFree(h->d_ptab); cudaFree(h->d_ctab); cudaFree(h->d_dct_t);
     cudaFree(h->st.n_samples); cudaFree(h->st.tail); cudaFree(h->st.ring); cudaFree(h->st.trig);
     cudaFree(h->d_wcat); cudaFree(h->d_bias); cudaFree(h->d_wd); cudaFree(h->d_count);
-    cudaFree(h->d_bfrag); cudaFree(h->d_mma_bias); cudaFree(h->d_mma_wd); cudaFree(h->d_proj_w); cudaFree(h->d_proj_b); cudaFree(h->d_proj_ring); cudaFree(h->d_tc5); cudaFree(h->d_tcb); cudaFree(h->d_dbg);
+    cudaFree(h->d_bfrag16); cudaFree(h->d_bfrag); cudaFree(h->d_mma_bias); cudaFree(h->d_mma_wd); cudaFree(h->d_proj_w); cudaFree(h->d_proj_b); cudaFree(h->d_proj_ring); cudaFree(h->d_tc5); cudaFree(h->d_tcb); cudaFree(h->d_dbg);
     if (h->h_count_pinned) cudaFreeHost(h->h_count_pinned);
     for (int i = 0; i < HOST_PIPE; ++i) {
         cudaFree(h->d_stage_pcm[i]); cudaFree(h->d_stage_ids[i]); cudaFree(h->d_stage_raw[i]);
@@ -519,6 +521,32 @@ PB_API int pb_load_weights(pb_handle* h, const float* kernel, const float* recur
                     const float b0h = tf32(b[0]), b1h = tf32(b[1]);
                     bf[((size_t)kt * MMA_NT + nt) * 32 + lane] = make_float4(b0h, b1h, tf32(b[0] - b0h), tf32(b[1] - b1h));
                 }
+        {   // fp16 fragments of the recurrent weights (gru_mma16_kernel): k-tile 0 = hidden units 0..15 as an m16n8k16 B fragment
+            // (b0: k = 2t, 2t + 1; b1: k = 2t + 8, 2t + 9), k-tile 1 = units 16..23 as an m16n8k8 one (b0 only); column (nt, g) as above.
+            auto h2 = [](float lo16, float hi16) {
+                const __half a = __float2half_rn(lo16), b = __float2half_rn(hi16);
+                uint16_t ua, ub; memcpy(&ua, &a, 2); memcpy(&ub, &b, 2);
+                return (uint32_t)ua | ((uint32_t)ub << 16);
+            };
+            auto res = [](float v) { return v - __half2float(__float2half_rn(v)); };
+            std::vector<uint4> bf16((size_t)2 * MMA_NT * 32);
+            for (int kt = 0; kt < 2; ++kt)
+                for (int nt = 0; nt < MMA_NT; ++nt)
+                    for (int lane = 0; lane < 32; ++lane) {
+                        const int g = lane >> 2, t = lane & 3, gate = nt / 3, unit = 8 * (nt % 3) + g;
+                        float b[2][2];
+                        for (int r = 0; r < 2; ++r)
+                            for (int j = 0; j < 2; ++j) {
+                                const int hu = 16 * kt + 8 * r + 2 * t + j;
+                                b[r][j] = (unit < H && hu < H && !(kt == 1 && r == 1)) ? recurrent[(size_t)hu * H3 + gate * H + unit] : 0.f;
+                            }
+                        bf16[((size_t)kt * MMA_NT + nt) * 32 + lane] = make_uint4(h2(b[0][0], b[0][1]), h2(b[1][0], b[1][1]),
+                                                                                  h2(res(b[0][0]), res(b[0][1])), h2(res(b[1][0]), res(b[1][1])));
+                    }
+            cudaFree(h->d_bfrag16); h->d_bfrag16 = nullptr;
+            CK(upload(&h->d_bfrag16, bf16));
+            CK(ensure_dyn_smem(gru_mma16_kernel<20>, (size_t)K2_STAGED_SMEM));
+        }
         {   // input projection table: wx[f][col], col = gate * 24 + unit (same column order as the accumulator tiles)
             std::vector<float> pw((size_t)F * PROJ_COLS, 0.f), pbias(PROJ_COLS, 0.f);
             for (int gate = 0; gate < 3; ++gate)
@@ -861,10 +889,15 @@ static int launch_gru(pb_handle* h, const K2In& in, bool ring, int64_t n, const 
         // dependent chain); 16-stream tiles fit 5 CTAs/SM and leave a much shorter tail.
         if (ring && in.proj != nullptr && h->gru_mode != 7) {
             const int per1 = (MMA_THREADS / 32) * 16;
-            if (h->gru_mode == 9)            // A/B: the scan without bulk-copy staging of the projection blocks
+            if (h->gru_mode == 9)            // A/B: 3xTF32 scan without bulk-copy staging of the projection blocks
                 gru_mma_kernel<20, 13, true, true, 1><<<(int)((n + per1 - 1) / per1), MMA_THREADS, 0, s>>>(w, in, n, dp, o);
-            else
+            else if (h->gru_mode == 10)      // A/B: 3xTF32 scan with staging
                 gru_mma_kernel<20, 13, true, true, 1, true><<<(int)((n + per1 - 1) / per1), MMA_THREADS, K2_STAGED_SMEM, s>>>(w, in, n, dp, o);
+            else {                           // default: fp16x3 recurrent products (half the tensor-pipe time), staged projection blocks
+                GruMma16W w16;
+                w16.bfrag = h->d_bfrag16; w16.bias = h->d_mma_bias; w16.wd = h->d_mma_wd; w16.bd = h->bd;
+                gru_mma16_kernel<20><<<(int)((n + per1 - 1) / per1), MMA_THREADS, K2_STAGED_SMEM, s>>>(w16, in, n, dp, o);
+            }
         } else if (ring && in.proj != nullptr) gru_mma_kernel<20, 13, true, true><<<grid, MMA_THREADS, 0, s>>>(w, in, n, dp, o);
         else if (ring) gru_mma_kernel<20, 13, true, false><<<grid, MMA_THREADS, 0, s>>>(w, in, n, dp, o);
         else gru_mma_kernel<20, 13, false, false><<<grid, MMA_THREADS, 0, s>>>(w, in, n, dp, o);
@@ -1051,7 +1084,7 @@ PB_API int pb_update_vectors(pb_handle* h, const int16_t* d_pcm, const int32_t* 
 
 // Does a tick of n streams run the scan that reads cached input projections (gru_mma_kernel<.., PROJ>)?
 static bool wants_projection(const pb_handle* h, int64_t n) {
-    return h->has_proj && h->small_path && n > K2_WARP_PATH_MAX && (h->gru_mode == 0 || h->gru_mode == 2 || h->gru_mode == 7 || h->gru_mode == 8 || h->gru_mode == 9);
+    return h->has_proj && h->small_path && n > K2_WARP_PATH_MAX && (h->gru_mode == 0 || h->gru_mode == 2 || h->gru_mode == 7 || h->gru_mode == 8 || h->gru_mode == 9 || h->gru_mode == 10);
 }
 
 // Recompute the projection of every ring row once (all streams), then the cache is maintained incrementally.

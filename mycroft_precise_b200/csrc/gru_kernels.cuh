@@ -13,6 +13,7 @@
 //   ([x,h] x [Wz|Wr], then [x,r*h] x Wh) with activations in shared memory and weights streamed
 //   through L1/L2.
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -708,6 +709,204 @@ gru_mma_kernel(GruMmaW W, K2In in, long long n, DecodeParams dp, K2Out out) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// ------------------------------------------------------------------------------------------------
+// The steady-state stream scan over cached projections with the recurrent products in fp16 x 3 (hi / lo split of both operands,
+// fp32 accumulate: a_lo b_hi + a_hi b_lo + a_hi b_hi) on mma.sync m16n8k16 / m16n8k8: one k16 + one k8 MMA per n-tile and pass
+// cover the 24 (padded) hidden units that the TF32 kernel above needs three k8 MMAs for -- half the tensor-pipe time, which is
+// what bounds the scan once its loads are staged (ncu: math_pipe_throttle).  Hidden units sit in the k index in natural order
+// (thread t of a quad holds units 8 tile + 2t, 2t + 1 in its accumulators = the (2t, 2t + 1) and (2t + 8, 2t + 9) k pairs of the
+// A fragment), so h turns into the next step's A operand with two F2FP packs per n-tile and no data movement.
+// Accuracy: pieces of 11 bits each, 22 bits per product like 3xTF32 (CPU emulation on the default network: 7.6e-8 vs 4.7e-8).
+struct GruMma16W {
+    const uint4* bfrag;              // [2 k-tiles][MMA_NT][32 lanes] (b0_hi, b1_hi, b0_lo, b1_lo) as half2; k-tile 1 uses b0 only (units 16..23)
+    const float* bias;               // [3][24] padded per gate
+    const float* wd;                 // [24] padded
+    float bd;
+};
+
+__device__ __forceinline__ void mma_f16_k16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void mma_f16_k8(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t b0) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a0), "r"(a1), "r"(b0));
+}
+// (x, y) -> fp16 hi pair and the pair of residuals
+__device__ __forceinline__ void split_f16(float x, float y, uint32_t& hi, uint32_t& lo) {
+    const __half2 h = __floats2half2_rn(x, y);
+    const float2 f = __half22float2(h);
+    const __half2 l = __floats2half2_rn(x - f.x, y - f.y);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+// A fragments of a 24-unit vector held in accumulator layout v[tile][e]: k-tile 0 (units 0..15) as a k16 fragment, units 16..23 as a k8 one
+__device__ __forceinline__ void frag_f16(const float (&v)[3][4], uint32_t (&ah)[4], uint32_t (&al)[4], uint32_t (&bh)[2], uint32_t (&bl)[2]) {
+    split_f16(v[0][0], v[0][1], ah[0], al[0]);       // row g,     k 2t, 2t + 1
+    split_f16(v[0][2], v[0][3], ah[1], al[1]);       // row g + 8
+    split_f16(v[1][0], v[1][1], ah[2], al[2]);       // row g,     k 2t + 8, 2t + 9
+    split_f16(v[1][2], v[1][3], ah[3], al[3]);
+    split_f16(v[2][0], v[2][1], bh[0], bl[0]);       // units 16 + 2t, + 1: the k8 fragment
+    split_f16(v[2][2], v[2][3], bh[1], bl[1]);
+}
+// acc[nt0 .. nt0 + 2] += v . B over the 24 units, three passes
+__device__ __forceinline__ void mma3_f16(float (*acc)[4], int nt0, const uint32_t (&ah)[4], const uint32_t (&al)[4], const uint32_t (&ch)[2],
+                                         const uint32_t (&cl)[2], const uint4* sB, int lane) {
+    uint4 w0[3], w1[3];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) { w0[q] = sB[(nt0 + q) * 32 + lane]; w1[q] = sB[(MMA_NT + nt0 + q) * 32 + lane]; }
+#pragma unroll
+    for (int q = 0; q < 3; ++q) { mma_f16_k16(acc[nt0 + q], al, w0[q].x, w0[q].y); mma_f16_k8(acc[nt0 + q], cl[0], cl[1], w1[q].x); }
+#pragma unroll
+    for (int q = 0; q < 3; ++q) { mma_f16_k16(acc[nt0 + q], ah, w0[q].z, w0[q].w); mma_f16_k8(acc[nt0 + q], ch[0], ch[1], w1[q].z); }
+#pragma unroll
+    for (int q = 0; q < 3; ++q) { mma_f16_k16(acc[nt0 + q], ah, w0[q].x, w0[q].y); mma_f16_k8(acc[nt0 + q], ch[0], ch[1], w1[q].x); }
+}
+
+template <int H>
+__global__ void __launch_bounds__(MMA_THREADS, 5)
+gru_mma16_kernel(GruMma16W W, K2In in, long long n, DecodeParams dp, K2Out out) {
+    static_assert(H <= 24, "tile counts are fixed");
+    extern __shared__ __align__(128) unsigned char k2_stage_raw[];
+    __shared__ uint4 sB[2 * MMA_NT * 32];
+    __shared__ float sBias[3 * 24];
+    __shared__ float sWd[24];
+    for (int e = threadIdx.x; e < 2 * MMA_NT * 32; e += blockDim.x) sB[e] = __ldg(W.bfrag + e);
+    for (int e = threadIdx.x; e < 72; e += blockDim.x) sBias[e] = __ldg(W.bias + e);
+    for (int e = threadIdx.x; e < 24; e += blockDim.x) sWd[e] = __ldg(W.wd + e);
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+    const long long base = ((long long)blockIdx.x * (MMA_THREADS / 32) + warp) * 16;
+    if (base >= n) return;
+    long long idx[2];
+    int sid[2];
+    RingCursor cur[2];
+    bool ok[2];
+#pragma unroll
+    for (int hf = 0; hf < 2; ++hf) {
+        idx[hf] = base + g + 8 * hf;
+        ok[hf] = idx[hf] < n;
+        sid[hf] = 0;
+        if (ok[hf]) {
+            sid[hf] = in.ids ? in.ids[idx[hf]] : (int)idx[hf];
+            const long long ns = in.n_samples[sid[hf]];
+            cur[hf].init_proj(in, sid[hf], ns >= in.window ? (ns - in.window) / in.hop + 1 : 0, PROJ_BLOCK);
+        }
+    }
+    float hreg[3][4];
+#pragma unroll
+    for (int nt = 0; nt < 3; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) hreg[nt][e] = 0.f;
+
+    // ---- uniform tile: projection blocks by bulk copy (see gru_mma_kernel<.., STAGED>)
+    float* stg = reinterpret_cast<float*>(k2_stage_raw + warp * 2 * K2_STAGE_BYTES);
+    unsigned long long* sbar = reinterpret_cast<unsigned long long*>(k2_stage_raw + (MMA_THREADS / 32) * 2 * K2_STAGE_BYTES) + 2 * warp;
+    const int sid0 = __shfl_sync(0xffffffffu, sid[0], 0);
+    const int sl0 = __shfl_sync(0xffffffffu, cur[0].slot, 0), ld0 = __shfl_sync(0xffffffffu, cur[0].lead, 0);
+    const bool same = ok[0] && ok[1] && (sid0 & 15) == 0 && sid[0] == sid0 + g && sid[1] == sid0 + g + 8 &&
+                      cur[0].slot == sl0 && cur[1].slot == sl0 && cur[0].lead == ld0 && cur[1].lead == ld0;
+    const bool staged = __all_sync(0xffffffffu, same);
+    const float* sblock = cur[0].base;
+    const int s_rows = cur[0].rows;
+    const long long s_stride = cur[0].stride;
+    uint32_t s_ph0 = 0, s_ph1 = 0;
+    auto stage_issue = [&](int st) {
+        int sl = sl0 + st;
+        if (sl >= s_rows) sl -= s_rows;
+        unsigned long long* bar = &sbar[st & 1];
+        mbar_expect_tx(bar, (uint32_t)K2_STAGE_BYTES);
+        bulk_g2s(stg + (st & 1) * PROJ_BLOCK, sblock + (long long)sl * s_stride, (uint32_t)K2_STAGE_BYTES, bar);
+    };
+    if (staged) {
+        if (lane == 0) { mbar_init(&sbar[0], 1); mbar_init(&sbar[1], 1); fence_mbar_init(); }
+        __syncwarp();
+        if (lane == 0) {
+            if (ld0 < in.T) stage_issue(ld0);
+            if (ld0 + 1 < in.T) stage_issue(ld0 + 1);
+        }
+    }
+
+#pragma unroll 1
+    for (int step = 0; step < in.T; ++step) {
+        float acc[MMA_NT][4];
+        if (staged) {
+            const bool real = step >= ld0;
+            const float* blk = stg + (step & 1) * PROJ_BLOCK;
+            if (real) {
+                if (step & 1) { mbar_wait(&sbar[1], s_ph1); s_ph1 ^= 1u; } else { mbar_wait(&sbar[0], s_ph0); s_ph0 ^= 1u; }
+            }
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf)
+#pragma unroll
+                for (int nt = 0; nt < MMA_NT; ++nt) {
+                    float2 v;
+                    if (!real) v = make_float2(sBias[8 * nt + 2 * t], sBias[8 * nt + 2 * t + 1]);
+                    else if (nt % 3 != 2 || t < 2) v = *reinterpret_cast<const float2*>(blk + proj_off(nt, g + 8 * hf, t));
+                    else v = make_float2(0.f, 0.f);
+                    acc[nt][2 * hf] = v.x; acc[nt][2 * hf + 1] = v.y;
+                }
+        } else {
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+                const float* row = ok[hf] ? cur[hf].next(step) : nullptr;
+#pragma unroll
+                for (int nt = 0; nt < MMA_NT; ++nt) {
+                    float2 v;
+                    if (row == nullptr) v = make_float2(sBias[8 * nt + 2 * t], sBias[8 * nt + 2 * t + 1]);
+                    else if (nt % 3 != 2 || t < 2) v = __ldg(reinterpret_cast<const float2*>(row + proj_off(nt, sid[hf] & 15, t)));
+                    else v = make_float2(0.f, 0.f);
+                    acc[nt][2 * hf] = v.x; acc[nt][2 * hf + 1] = v.y;
+                }
+            }
+        }
+        // ---- h part for z and r
+        {
+            uint32_t ah[4], al[4], ch[2], cl[2];
+            frag_f16(hreg, ah, al, ch, cl);
+            mma3_f16(acc, 0, ah, al, ch, cl, sB, lane);
+            mma3_f16(acc, 3, ah, al, ch, cl, sB, lane);
+        }
+        // ---- gates; r * h is the A operand of the candidate product
+        {
+            float rh[3][4];
+#pragma unroll
+            for (int nt = 0; nt < 3; ++nt)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) rh[nt][e] = hard_sigmoid(acc[3 + nt][e]) * hreg[nt][e];
+            uint32_t ah[4], al[4], ch[2], cl[2];
+            frag_f16(rh, ah, al, ch, cl);
+            mma3_f16(acc, 6, ah, al, ch, cl, sB, lane);
+        }
+#pragma unroll
+        for (int nt = 0; nt < 3; ++nt)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float z = hard_sigmoid(acc[nt][e]);
+                hreg[nt][e] = z * hreg[nt][e] + (1.f - z) * acc[6 + nt][e];      // linear candidate
+            }
+        if (staged && step >= ld0 && step + 2 < in.T) {          // this step's buffer has been consumed by every lane: refill it
+            __syncwarp();
+            if (lane == 0) stage_issue(step + 2);
+        }
+    }
+    // ---- Dense(1): per-thread partial over its 6 units per row, reduced over the quad
+#pragma unroll
+    for (int hf = 0; hf < 2; ++hf) {
+        float part = 0.f;
+#pragma unroll
+        for (int nt = 0; nt < 3; ++nt) {
+            part = fmaf(hreg[nt][2 * hf], sWd[8 * nt + 2 * t], part);
+            part = fmaf(hreg[nt][2 * hf + 1], sWd[8 * nt + 2 * t + 1], part);
+        }
+        part += __shfl_xor_sync(0xffffffffu, part, 1);
+        part += __shfl_xor_sync(0xffffffffu, part, 2);
+        epilogue(part + W.bd, t == 0 && ok[hf], idx[hf], sid[hf], dp, out);
+    }
+}
+
 // Cached input projection (default network, stream mode): a = b + x . [Wz|Wr|Wh] (60 floats per frame) is kept in a second
 // ring with the same slot numbering as the MFCC ring.  A steady-state scan reads 29 x 240 B of it per stream -- the scan is
 // bound by that traffic, which is why the rows are stored compact (no padding units) and apart from the MFCC rows.

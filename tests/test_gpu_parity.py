@@ -248,8 +248,9 @@ def test_cached_projection_path_large_batch():
     model = m.GruModel.random(13, 20, seed=8, scale=0.1)
     model.dense_b = 3.0
     res = []
-    # 0: tensor-core scan over cached projections, 16-stream warp tiles; 7: the same with 32-stream tiles; 1: CUDA cores
-    for mode in (0, 7, 1):
+    # 0: default scan over cached projections (fp16x3 recurrent products, bulk-copy staged blocks); 10: 3xTF32 products, staged,
+    # 16-stream warp tiles; 9: the same without staging; 7: 3xTF32 with 32-stream tiles; 1: CUDA cores
+    for mode in (0, 10, 9, 7, 1):
         sb = m.StreamBatch(model, S, chunk_samples=chunk)
         sb.core.gru_mode(mode)
         raws = []
@@ -270,9 +271,11 @@ def test_cached_projection_path_large_batch():
     for r, c in res[:-1]:
         assert np.max(np.abs(r - res[-1][0])) < 1e-5
         assert c > 0 and abs(c - res[-1][1]) <= 3
-    a, b = res[0][0].copy(), res[1][0].copy()                        # same arithmetic per stream, different tiling ...
-    a[25, :5] = b[25, :5] = 0                                        # ... except the 5-stream tick (warp-per-stream kernel vs forced MMA)
-    assert np.array_equal(a, b)
+    for i, j in ((1, 2), (1, 3)):                                    # the 3xTF32 variants: same arithmetic per stream, different tiling / staging ...
+        a, b = res[i][0].copy(), res[j][0].copy()
+        a[25, :5] = b[25, :5] = 0                                    # ... except the 5-stream tick (warp-per-stream kernel vs forced MMA)
+        assert np.array_equal(a, b), (i, j)
+    print('max |raw - CUDA-core kernel|: fp16x3 %.3g, 3xTF32 %.3g' % (np.max(np.abs(res[0][0] - res[-1][0])), np.max(np.abs(res[1][0] - res[-1][0]))))
 
 
 def _generic_case(pr_kw, H, act='linear', ract='hard_sigmoid', N=200, seed=5, mode=0):
