@@ -106,6 +106,7 @@ struct pb_handle {
     float *d_wcat = nullptr, *d_bias = nullptr, *d_wd = nullptr;
     float4* d_bfrag = nullptr;       // tensor-core GRU: pre-split, fragment-ordered weights
     uint4* d_bfrag16 = nullptr;      // ... recurrent part as fp16 hi / lo fragments (gru_mma16_kernel)
+    uint4* d_xfrag16 = nullptr;      // ... and the input part (the scan projects a tick's new frames itself)
     float *d_mma_bias = nullptr, *d_mma_wd = nullptr;
     long long* d_dbg = nullptr;       // optional debug counters (pb_debug_counters)
     float *d_tcb = nullptr;           // tcgen05 wide-network GRU: [b1 tiles | b2 tiles | bias(384) | wd(128)]
@@ -266,7 +267,7 @@ PB_API void pb_destroy(pb_handle* h) {
     cudaFree(h->d_tw_stage); cudaFree(h->d_tw_post); cudaFree(h->d_tw_any); cudaFree(h->d_cd); cudaFree(h->d_ptab); cudaFree(h->d_ctab); cudaFree(h->d_dct_t);
     cudaFree(h->st.n_samples); cudaFree(h->st.tail); cudaFree(h->st.ring); cudaFree(h->st.trig);
     cudaFree(h->d_wcat); cudaFree(h->d_bias); cudaFree(h->d_wd); cudaFree(h->d_count);
-    cudaFree(h->d_bfrag16); cudaFree(h->d_bfrag); cudaFree(h->d_mma_bias); cudaFree(h->d_mma_wd); cudaFree(h->d_proj_w); cudaFree(h->d_proj_b); cudaFree(h->d_proj_ring); cudaFree(h->d_tc5); cudaFree(h->d_tcb); cudaFree(h->d_dbg);
+    cudaFree(h->d_bfrag16); cudaFree(h->d_xfrag16); cudaFree(h->d_bfrag); cudaFree(h->d_mma_bias); cudaFree(h->d_mma_wd); cudaFree(h->d_proj_w); cudaFree(h->d_proj_b); cudaFree(h->d_proj_ring); cudaFree(h->d_tc5); cudaFree(h->d_tcb); cudaFree(h->d_dbg);
     if (h->h_count_pinned) cudaFreeHost(h->h_count_pinned);
     for (int i = 0; i < HOST_PIPE; ++i) {
         cudaFree(h->d_stage_pcm[i]); cudaFree(h->d_stage_ids[i]); cudaFree(h->d_stage_raw[i]);
@@ -545,7 +546,23 @@ PB_API int pb_load_weights(pb_handle* h, const float* kernel, const float* recur
                     }
             cudaFree(h->d_bfrag16); h->d_bfrag16 = nullptr;
             CK(upload(&h->d_bfrag16, bf16));
-            CK(ensure_dyn_smem(gru_mma16_kernel<20>, (size_t)K2_STAGED_SMEM));
+            // ... and of the input weights: features 0..15 as one k16 fragment (b0: k = 2t, 2t + 1; b1: k = 2t + 8, 2t + 9)
+            std::vector<uint4> xf16((size_t)MMA_NT * 32);
+            for (int nt = 0; nt < MMA_NT; ++nt)
+                for (int lane = 0; lane < 32; ++lane) {
+                    const int g = lane >> 2, t = lane & 3, gate = nt / 3, unit = 8 * (nt % 3) + g;
+                    float b[2][2];
+                    for (int r = 0; r < 2; ++r)
+                        for (int j = 0; j < 2; ++j) {
+                            const int f = 8 * r + 2 * t + j;
+                            b[r][j] = (unit < H && f < F) ? kernel[(size_t)f * H3 + gate * H + unit] : 0.f;
+                        }
+                    xf16[(size_t)nt * 32 + lane] = make_uint4(h2(b[0][0], b[0][1]), h2(b[1][0], b[1][1]),
+                                                              h2(res(b[0][0]), res(b[0][1])), h2(res(b[1][0]), res(b[1][1])));
+                }
+            cudaFree(h->d_xfrag16); h->d_xfrag16 = nullptr;
+            CK(upload(&h->d_xfrag16, xf16));
+            CK(ensure_dyn_smem(gru_mma16_kernel<20, 13>, (size_t)K2_STAGED_SMEM));
         }
         {   // input projection table: wx[f][col], col = gate * 24 + unit (same column order as the accumulator tiles)
             std::vector<float> pw((size_t)F * PROJ_COLS, 0.f), pbias(PROJ_COLS, 0.f);
@@ -895,8 +912,8 @@ static int launch_gru(pb_handle* h, const K2In& in, bool ring, int64_t n, const 
                 gru_mma_kernel<20, 13, true, true, 1, true><<<(int)((n + per1 - 1) / per1), MMA_THREADS, K2_STAGED_SMEM, s>>>(w, in, n, dp, o);
             else {                           // default: fp16x3 recurrent products (half the tensor-pipe time), staged projection blocks
                 GruMma16W w16;
-                w16.bfrag = h->d_bfrag16; w16.bias = h->d_mma_bias; w16.wd = h->d_mma_wd; w16.bd = h->bd;
-                gru_mma16_kernel<20><<<(int)((n + per1 - 1) / per1), MMA_THREADS, K2_STAGED_SMEM, s>>>(w16, in, n, dp, o);
+                w16.bfrag = h->d_bfrag16; w16.xfrag = h->d_xfrag16; w16.bias = h->d_mma_bias; w16.wd = h->d_mma_wd; w16.bd = h->bd;
+                gru_mma16_kernel<20, 13><<<(int)((n + per1 - 1) / per1), MMA_THREADS, K2_STAGED_SMEM, s>>>(w16, in, n, dp, o);
             }
         } else if (ring && in.proj != nullptr) gru_mma_kernel<20, 13, true, true><<<grid, MMA_THREADS, 0, s>>>(w, in, n, dp, o);
         else if (ring) gru_mma_kernel<20, 13, true, false><<<grid, MMA_THREADS, 0, s>>>(w, in, n, dp, o);
@@ -1116,7 +1133,11 @@ PB_API int pb_update(pb_handle* h, const int16_t* d_pcm, const int32_t* d_ids, i
     if (want_proj) { rc = rebuild_projections_if_dirty(h, s); if (rc != PB_OK) return rc; }
     rc = launch_stream_mfcc(h, d_pcm, d_ids, n, s);
     if (rc != PB_OK) return rc;
-    if (want_proj || (h->host_tick_proj && !h->proj_dirty)) {    // the second case: a short sub-batch of a large host tick
+    // The default scan (gru_mma16_kernel, gru_mode 0) projects the frames a tick has added itself, in its prologue; the separate
+    // projection kernel serves the other scans (A/B modes) and short sub-batches of a large host tick (second case below), whose
+    // warp-per-stream kernel does not touch the cache.
+    const bool scan_projects = want_proj && h->gru_mode == 0;
+    if ((want_proj && !scan_projects) || (!want_proj && h->host_tick_proj && !h->proj_dirty)) {
         ProfScope ps(h, 3, s);
         const long long items = (long long)n * h->max_new;
         const int grid = (int)((items + PROJ_THREADS - 1) / PROJ_THREADS);     // 32 frames per warp
@@ -1135,6 +1156,7 @@ PB_API int pb_update(pb_handle* h, const int16_t* d_pcm, const int32_t* d_ids, i
     K2Out o{};
     in.proj = use_proj ? h->d_proj_ring : nullptr;
     in.proj_tiles = (h->cfg.max_streams + 15) / 16;
+    in.used = h->used;
     in.chunk = h->cfg.chunk_samples;
     o.raw = d_raw; o.conf = d_conf; o.fired = d_fired; o.count = d_count; o.trig = h->st.trig;
     return launch_gru(h, in, true, n, decode_params(h), o, s);

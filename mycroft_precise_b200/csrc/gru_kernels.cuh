@@ -52,6 +52,7 @@ struct K2In {
     int use_delta;
     const float* proj;               // non-null: cached input projections x.W + b, tile-major [ring_rows][proj_tiles] blocks of PROJ_BLOCK floats (see proj_off), same slots as ring
     int proj_tiles;                  // ceil(max_streams / 16)
+    int used;                        // samples a frame needs before it is computed (min(window, n_fft)): tells which ring rows a tick has added
     int chunk;                       // samples added by this tick (to tell which window rows are new)
 };
 
@@ -719,6 +720,7 @@ gru_mma_kernel(GruMmaW W, K2In in, long long n, DecodeParams dp, K2Out out) {
 // Accuracy: pieces of 11 bits each, 22 bits per product like 3xTF32 (CPU emulation on the default network: 7.6e-8 vs 4.7e-8).
 struct GruMma16W {
     const uint4* bfrag;              // [2 k-tiles][MMA_NT][32 lanes] (b0_hi, b1_hi, b0_lo, b1_lo) as half2; k-tile 1 uses b0 only (units 16..23)
+    const uint4* xfrag;              // [MMA_NT][32 lanes]: the input weights (features 0..15 as one k16 fragment), same packing
     const float* bias;               // [3][24] padded per gate
     const float* wd;                 // [24] padded
     float bd;
@@ -765,12 +767,17 @@ __device__ __forceinline__ void mma3_f16(float (*acc)[4], int nt0, const uint32_
     for (int q = 0; q < 3; ++q) { mma_f16_k16(acc[nt0 + q], ah, w0[q].x, w0[q].y); mma_f16_k8(acc[nt0 + q], ch[0], ch[1], w1[q].x); }
 }
 
-template <int H>
+// The kernel also keeps the cache itself: before the scan, every warp projects the frames this tick has added for its 16 streams
+// (x . [Wz|Wr|Wh] + b, one k16 MMA per n-tile and pass) and writes them into the cache blocks -- the separate projection
+// kernel of the other variants (39 us per tick) is not launched on this path.
+template <int H, int F>
 __global__ void __launch_bounds__(MMA_THREADS, 5)
 gru_mma16_kernel(GruMma16W W, K2In in, long long n, DecodeParams dp, K2Out out) {
-    static_assert(H <= 24, "tile counts are fixed");
+    static_assert(H <= 24 && F <= 16, "tile counts are fixed");
     extern __shared__ __align__(128) unsigned char k2_stage_raw[];
     __shared__ uint4 sB[2 * MMA_NT * 32];
+    __shared__ uint4 sX[MMA_NT * 32];
+    for (int e = threadIdx.x; e < MMA_NT * 32; e += blockDim.x) sX[e] = __ldg(W.xfrag + e);
     __shared__ float sBias[3 * 24];
     __shared__ float sWd[24];
     for (int e = threadIdx.x; e < 2 * MMA_NT * 32; e += blockDim.x) sB[e] = __ldg(W.bfrag + e);
@@ -800,6 +807,78 @@ gru_mma16_kernel(GruMma16W W, K2In in, long long n, DecodeParams dp, K2Out out) 
     for (int nt = 0; nt < 3; ++nt)
 #pragma unroll
         for (int e = 0; e < 4; ++e) hreg[nt][e] = 0.f;
+
+    // ---- the frames this tick has added to the ring (cf. input_proj_kernel): project them and store them into the cache
+    {
+        int slot0[2], cnt[2];
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+            slot0[hf] = 0; cnt[hf] = 0;
+            if (ok[hf]) {
+                const long long n1 = in.n_samples[sid[hf]], n0 = n1 - in.chunk;
+                const long long c0 = n0 >= in.used ? (n0 - in.used) / in.hop + 1 : 0, c1 = n1 >= in.used ? (n1 - in.used) / in.hop + 1 : 0;
+                slot0[hf] = (int)(c0 % in.ring_rows); cnt[hf] = (int)(c1 - c0);
+            }
+        }
+        int maxc = max(cnt[0], cnt[1]);
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) maxc = max(maxc, __shfl_xor_sync(0xffffffffu, maxc, d));
+        float* pw = const_cast<float*>(in.proj);
+#pragma unroll 1
+        for (int j = 0; j < maxc; ++j) {
+            float xv[2][4];
+            float* blk[2];
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+                blk[hf] = nullptr;
+                xv[hf][0] = xv[hf][1] = xv[hf][2] = xv[hf][3] = 0.f;
+                if (j < cnt[hf]) {
+                    int sl = slot0[hf] + j;
+                    if (sl >= in.ring_rows) sl -= in.ring_rows;
+                    const float* row = in.ring + ((long long)sid[hf] * in.ring_rows + sl) * in.row_stride;
+                    blk[hf] = pw + ((long long)sl * in.proj_tiles + (sid[hf] >> 4)) * PROJ_BLOCK;
+                    if (2 * t < F) xv[hf][0] = row[2 * t];
+                    if (2 * t + 1 < F) xv[hf][1] = row[2 * t + 1];
+                    if (2 * t + 8 < F) xv[hf][2] = row[2 * t + 8];
+                    if (2 * t + 9 < F) xv[hf][3] = row[2 * t + 9];
+                }
+            }
+            uint32_t ah[4], al[4];
+            split_f16(xv[0][0], xv[0][1], ah[0], al[0]);
+            split_f16(xv[1][0], xv[1][1], ah[1], al[1]);
+            split_f16(xv[0][2], xv[0][3], ah[2], al[2]);
+            split_f16(xv[1][2], xv[1][3], ah[3], al[3]);
+#pragma unroll 1
+            for (int ng = 0; ng < MMA_NT; ng += 3) {
+                float a3[3][4];
+                uint4 w[3];
+#pragma unroll
+                for (int q = 0; q < 3; ++q) {
+                    const float b0 = sBias[8 * (ng + q) + 2 * t], b1 = sBias[8 * (ng + q) + 2 * t + 1];
+                    a3[q][0] = b0; a3[q][1] = b1; a3[q][2] = b0; a3[q][3] = b1;
+                    w[q] = sX[(ng + q) * 32 + lane];
+                }
+#pragma unroll
+                for (int q = 0; q < 3; ++q) mma_f16_k16(a3[q], al, w[q].x, w[q].y);
+#pragma unroll
+                for (int q = 0; q < 3; ++q) mma_f16_k16(a3[q], ah, w[q].z, w[q].w);
+#pragma unroll
+                for (int q = 0; q < 3; ++q) mma_f16_k16(a3[q], ah, w[q].x, w[q].y);
+#pragma unroll
+                for (int hf = 0; hf < 2; ++hf)
+                    if (blk[hf] != nullptr) {
+#pragma unroll
+                        for (int q = 0; q < 3; ++q)
+                            if (q < 2 || t < 2)
+                                *reinterpret_cast<float2*>(blk[hf] + proj_off(ng + q, sid[hf] & 15, t)) = make_float2(a3[q][2 * hf], a3[q][2 * hf + 1]);
+                    }
+            }
+        }
+        // the scan reads these rows through the async proxy (bulk copies) or with plain loads: order them after the stores
+        asm volatile("fence.proxy.async.global;" ::: "memory");
+        __threadfence_block();
+        __syncwarp();
+    }
 
     // ---- uniform tile: projection blocks by bulk copy (see gru_mma_kernel<.., STAGED>)
     float* stg = reinterpret_cast<float*>(k2_stage_raw + warp * 2 * K2_STAGE_BYTES);
