@@ -42,8 +42,8 @@ PRIME = 24                # ticks that fill a 29-frame window: (24 * 1024 - 1600
 ALG_BYTES_PER_UPDATE = 2048 + 1.28 * 13 * 4           # 2114.56 B (F=13)
 ALG_FLOP_PER_UPDATE_GRU = 2 * (29 * (13 + 20) * 60 + 20)   # 114 880
 FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12     # 74.4 (148 SMs x 128 lanes x 2 x max clock)
-K2_BYTES_PER_UPDATE = 29 * 240 + 4 + 8 + 1 + 8        # 29 cached projection rows + raw, conf, fired, trigger state
-K2_MMA_FLOP_PER_UPDATE = 29 * 81 * 2048 // 16         # 81 HMMA.1688 (2048 FLOP) per 16-stream tile and step, 3xTF32 split included
+K2_BYTES_PER_UPDATE = 29 * 240 + 4 + 8 + 1 + 8 + 1.28 * (52 + 240)   # 29 cached projection rows + raw, conf, fired, trigger state + the tick's new frames (MFCC row in, projection out)
+K2_MMA_FLOP_PER_UPDATE = 29 * 27 * (4096 + 2048) // 16   # per 16-stream tile and step 27 m16n8k16 + 27 m16n8k8 fp16 MMAs (fp16x3 split included)
 K1_NAMES = {0: 'mfcc_tc3_plan_kernel + mfcc_tc3_kernel (K1: int16 split exactly into fp16 pieces, both DFT stages on tcgen05 / TMEM) -- default from 49152 streams per tick',
             2: 'mfcc_fast_stream_kernel<LEAN> (K1, FFT on the CUDA cores)', 3: 'mfcc_fast_stream_kernel (K1, FFT, 64-bit set-up)',
             4: 'mfcc_tc2_stream_kernel (K1, DFT stage 2 on tcgen05)', 5: 'mfcc_tc3_plan_kernel + mfcc_tc3_kernel (K1, both DFT stages on tcgen05)'}
@@ -599,7 +599,7 @@ def run_b200(args):
     k1_ms = kms[0] / max(1, klaunch[0])
     k2_ms = kms[1] / max(1, klaunch[1])
     k1_gbs = S * ALG_BYTES_PER_UPDATE / (k1_ms * 1e-3) / 1e9 if k1_ms > 0 else None
-    proj_ms = (kms[3] / klaunch[3]) if klaunch[3] else 0.0
+    proj_ms = (kms[3] / klaunch[3]) if klaunch[3] > 1 else 0.0          # slot 3 = the separate projection kernels (one launch = the initial rebuild of the cache)
     bf16_peak = None
     try:
         bf16_peak = float(json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))['bf16_tflops_sustained'])
@@ -626,16 +626,17 @@ def run_b200(args):
                      'traffic_source': 'profiles/k1_traffic.json (one ncu --set full capture of this kernel, not a live counter)' if traffic else None,
                      'algorithmic_bytes_per_launch': S * ALG_BYTES_PER_UPDATE, 'ms_per_launch': k1_ms, 'launches': klaunch[0],
                      'note': 'ms_per_launch = one tick of K1 (for the tcgen05 path: plan kernel + main kernel, both inside the CUDA-event bracket)'},
-        # K2 (scan over cached projections) against both of its ceilings: HBM for the bytes it must read (29 cached projection rows of
-        # 240 B per update + 21 B of results) and the tensor pipe for the MMA FLOPs it executes (3xTF32 split, 81 m16n8k8 HMMA per 16
-        # streams and step = 300 672 FLOP per update; TF32 dense peak taken as half the measured sustained bf16 rate)
-        'roofline_k2': {'kernel': 'gru_mma_kernel<20,13,PROJ,MB=1> (K2+K3; mma.sync TF32x3) after input_proj_kernel', 'ms_per_launch': k2_ms, 'launches': klaunch[1],
-                        'input_projection_ms_per_launch': proj_ms or None,
+        # K2 (scan over cached projections) against both of its ceilings: HBM for the bytes it must move (29 cached projection rows of
+        # 240 B per update, the results, and the new frames' MFCC rows in / projections out) and the tensor pipe for the MMA FLOPs it
+        # executes (fp16 x 3 split: 27 m16n8k16 + 27 m16n8k8 per 16 streams and step = 300 672 FLOP per update) against the measured
+        # sustained fp16/bf16 tensor rate
+        'roofline_k2': {'kernel': 'gru_mma16_kernel<20,13> (K2+K3: fp16x3 mma.sync scan over bulk-copy-staged cached projections, projects the tick\'s new frames itself)',
+                        'ms_per_launch': k2_ms, 'launches': klaunch[1], 'input_projection_ms_per_launch': proj_ms or None,
                         'hbm': {'algorithmic_bytes_per_update': K2_BYTES_PER_UPDATE, 'achieved': S * K2_BYTES_PER_UPDATE / (k2_ms * 1e-3) / 1e9 if k2_ms > 0 else None,
                                 'peak': hbm_peak, 'unit': 'GB/s', 'frac': S * K2_BYTES_PER_UPDATE / (k2_ms * 1e-3) / 1e9 / hbm_peak if k2_ms > 0 else None},
                         'tensor': {'executed_flop_per_update': K2_MMA_FLOP_PER_UPDATE, 'achieved': S * K2_MMA_FLOP_PER_UPDATE / (k2_ms * 1e-3) / 1e12 if k2_ms > 0 else None,
-                                   'peak': (bf16_peak / 2) if bf16_peak else None, 'unit': 'TFLOP/s (TF32, executed incl. the 3x split)',
-                                   'frac': (S * K2_MMA_FLOP_PER_UPDATE / (k2_ms * 1e-3) / 1e12 / (bf16_peak / 2)) if (bf16_peak and k2_ms > 0) else None},
+                                   'peak': bf16_peak, 'unit': 'TFLOP/s (fp16 MMA, executed incl. the 3x split)',
+                                   'frac': (S * K2_MMA_FLOP_PER_UPDATE / (k2_ms * 1e-3) / 1e12 / bf16_peak) if (bf16_peak and k2_ms > 0) else None},
                         'algorithmic_flop_per_update': ALG_FLOP_PER_UPDATE_GRU},
         'e2e': e2e,
         'gpu_launches': int(sum(klaunch)) + (int(klaunch[0]) if (args.k1_mode in (0, 5) and S >= 49152) else 0),     # K1 on the tcgen05 path = plan kernel + main kernel

@@ -1145,7 +1145,7 @@ PB_API int pb_update(pb_handle* h, const int16_t* d_pcm, const int32_t* d_ids, i
             h->cfg.chunk_samples, h->used, h->cfg.hop_samples, h->max_new, h->st.ring, h->ring_rows, h->row_stride, h->d_proj_ring,
             (h->cfg.max_streams + 15) / 16);
         CK(cudaGetLastError());
-    } else if (h->has_proj && h->small_path) {
+    } else if (!scan_projects && h->has_proj && h->small_path) {
         h->proj_dirty = true;                                  // this tick's frames get no projection
     }
     const bool use_proj = want_proj;
