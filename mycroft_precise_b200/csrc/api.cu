@@ -314,7 +314,8 @@ PB_API int pb_create(const pb_config* cfg, pb_handle** out) {
     h->feat = h->n_out * (c.use_delta ? 2 : 1);
     h->row_stride = (h->n_out + 3) & ~3;
     // default-sized networks cache the input projection of every frame in a second ring (gru_mma_kernel<.., PROJ>)
-    h->has_proj = c.hidden == 20 && h->n_out == 13 && !c.use_delta && c.vectorizer == PB_VEC_MFCCS;
+    h->has_proj = c.hidden == 20 && h->n_out == 13 && !c.use_delta && c.vectorizer == PB_VEC_MFCCS &&
+                  c.chunk_samples / c.hop_samples + 2 <= 8;      // long chunks (fed as sub-chunks, launch_stream_mfcc) may add more rows than the cache logic tracks
     h->ring_rows = c.n_features + (c.window_samples - h->used) / c.hop_samples + 2;
     h->tail_cap = (h->used + 7) & ~7;            // rows stay 16-byte aligned
     h->max_new = c.chunk_samples / c.hop_samples + 2;
@@ -977,7 +978,6 @@ static int check_tick(pb_handle* h, const void* pcm, int64_t n) {
     if (!h) return fail(PB_ERR_INVALID, "null handle");
     if (n < 0 || n > h->cfg.max_streams) return fail(PB_ERR_INVALID, "n = %lld outside [0, max_streams = %d]", (long long)n, h->cfg.max_streams);
     if (n > 0 && !pcm) return fail(PB_ERR_INVALID, "null pcm");
-    if (h->max_new > 8) return fail(PB_ERR_UNSUPPORTED, "chunk_samples %d yields up to %d frames per tick (> 8): feed smaller chunks", h->cfg.chunk_samples, h->max_new);
     return PB_OK;
 }
 
@@ -1071,7 +1071,7 @@ static int launch_stream_mfcc(pb_handle* h, const int16_t* d_pcm, const int32_t*
         const int groups = (int)((n + sg - 1) / sg);
         mfcc_tc2_stream_kernel<Tc2Geo20><<<std::min(groups, h->sm_count), TC2_THREADS, sizeof(Tc2Smem) + 128, s>>>(
             d_pcm, d_ids, (int)n, sg, h->cfg.chunk_samples, h->cfg.hop_samples, t, h->st);
-    } else if (h->fast_ok && h->cfg.chunk_samples % 8 == 0 && (uintptr_t)d_pcm % 16 == 0 && !h->force_generic) {
+    } else if (h->fast_ok && h->max_new <= 8 && h->cfg.chunk_samples % 8 == 0 && (uintptr_t)d_pcm % 16 == 0 && !h->force_generic) {
         // streams per warp tile: 16 at scale; fewer when the batch cannot fill the machine's warps
         const int64_t warps_total = (int64_t)h->sm_count * 4 * K1F_WARPS;
         const int spw = (int)std::max<int64_t>(1, std::min<int64_t>(K1F_STREAMS_PER_WARP, (n + warps_total - 1) / warps_total));
@@ -1083,10 +1083,18 @@ static int launch_stream_mfcc(pb_handle* h, const int16_t* d_pcm, const int32_t*
         else
             mfcc_fast_stream_kernel<false><<<gridf, K1F_THREADS, h->k1_fast_smem, s>>>(d_pcm, d_ids, (int)n, h->cfg.chunk_samples, h->cfg.hop_samples, spw, scale,
                                                                                        mel_tables(h), fast_tables(h), h->st);
+    } else if (h->max_new > 8) {
+        // A chunk that completes more than 8 frames per stream: consecutive sub-chunks of at most 6 hops (<= 8 frames each) through the
+        // generic kernel -- to the state machine they are separate ticks (Listener.update_vectors is chunking-independent); the network
+        // runs once, after the last one.
+        const int sub = std::max(1, 6 * h->cfg.hop_samples);
+        for (int off = 0; off < h->cfg.chunk_samples; off += sub)
+            mfcc_stream_kernel<false><<<grid, K1_THREADS, h->k1_stream_smem, s>>>(d_pcm + off, d_ids, (int)n, std::min(sub, h->cfg.chunk_samples - off),
+                                                                                    h->cfg.chunk_samples, h->cfg.hop_samples, h->used, scale, mel_tables(h), h->st);
     } else if (pairs)
-        mfcc_stream_kernel<true><<<grid, K1_THREADS, h->k1_stream_smem, s>>>(d_pcm, d_ids, (int)n, h->cfg.chunk_samples, h->cfg.hop_samples, h->used, scale, mel_tables(h), h->st);
+        mfcc_stream_kernel<true><<<grid, K1_THREADS, h->k1_stream_smem, s>>>(d_pcm, d_ids, (int)n, h->cfg.chunk_samples, h->cfg.chunk_samples, h->cfg.hop_samples, h->used, scale, mel_tables(h), h->st);
     else
-        mfcc_stream_kernel<false><<<grid, K1_THREADS, h->k1_stream_smem, s>>>(d_pcm, d_ids, (int)n, h->cfg.chunk_samples, h->cfg.hop_samples, h->used, scale, mel_tables(h), h->st);
+        mfcc_stream_kernel<false><<<grid, K1_THREADS, h->k1_stream_smem, s>>>(d_pcm, d_ids, (int)n, h->cfg.chunk_samples, h->cfg.chunk_samples, h->cfg.hop_samples, h->used, scale, mel_tables(h), h->st);
     CK(cudaGetLastError());
     return PB_OK;
 }

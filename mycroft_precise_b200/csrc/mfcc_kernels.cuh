@@ -283,11 +283,12 @@ struct K1StreamSmem {
     long long st_c0[K1_STREAMS_PER_CTA];
 };
 
-// One tick: stream ids[i] (or i) receives pcm[i][0..chunk).  A stream completes at most 8 frames
-// per tick (host-checked).
+// One tick: stream ids[i] (or i) receives pcm[i * pcm_stride + 0 .. chunk).  A stream completes at most 8 frames per launch: the
+// host feeds longer chunks as consecutive sub-chunks of the same rows (pcm_stride = the full chunk length), which the state machine
+// cannot tell from separate ticks (Listener.update_vectors is chunking-independent).
 template <bool PAIRS>
 __global__ void __launch_bounds__(K1_THREADS, 4)
-mfcc_stream_kernel(const int16_t* __restrict__ pcm, const int* __restrict__ ids, int n, int chunk,
+mfcc_stream_kernel(const int16_t* __restrict__ pcm, const int* __restrict__ ids, int n, int chunk, int pcm_stride,
                    int hop, int used, float scale, MelTables tab, StreamState st) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     K1StreamSmem& sm = *reinterpret_cast<K1StreamSmem*>(smem_raw);
@@ -329,7 +330,7 @@ mfcc_stream_kernel(const int16_t* __restrict__ pcm, const int* __restrict__ ids,
                 for (int slot = warp; slot < nr; slot += K1_WARPS) {               // generic n_fft: one frame per warp at a time
                     const int t = sm.fr_stream[r0 + slot];
                     const long long a0 = (sm.st_c0[t] + sm.fr_sub[r0 + slot]) * hop, n0 = sm.st_n0[t];
-                    const int16_t* chunk_p = pcm + (long long)(base + t) * chunk;
+                    const int16_t* chunk_p = pcm + (long long)(base + t) * pcm_stride;
                     FrameSrc<int16_t> src;
                     src.used = used;
                     if (a0 >= n0) { src.len0 = 0; src.p0 = chunk_p; src.p1 = chunk_p + (a0 - n0); }
@@ -350,7 +351,7 @@ mfcc_stream_kernel(const int16_t* __restrict__ pcm, const int* __restrict__ ids,
                     const int t = sm.fr_stream[r0 + slot];
                     const long long a0 = (sm.st_c0[t] + sm.fr_sub[r0 + slot]) * hop;     // absolute first sample
                     const long long n0 = sm.st_n0[t];
-                    const int16_t* chunk_p = pcm + (long long)(base + t) * chunk;
+                    const int16_t* chunk_p = pcm + (long long)(base + t) * pcm_stride;
                     FrameSrc<int16_t> src;
                     src.used = used;
                     if (a0 >= n0) { src.len0 = 0; src.p0 = chunk_p; src.p1 = chunk_p + (a0 - n0); }
@@ -387,7 +388,7 @@ mfcc_stream_kernel(const int16_t* __restrict__ pcm, const int* __restrict__ ids,
             const int len1 = (int)(n1 - ts1);
             const int n_old = ts1 < n0 ? (int)(n0 - ts1) : 0;       // part that comes from the old tail
             int16_t* tl = st.tail + (long long)sid * st.tail_cap;
-            const int16_t* chunk_p = pcm + (long long)(base + t) * chunk;
+            const int16_t* chunk_p = pcm + (long long)(base + t) * pcm_stride;
             if (n_old > 0) {
                 int16_t keep[64];                                    // tail_cap <= 2048 = 64 * 32
                 const int off = (int)(ts1 - ts0);

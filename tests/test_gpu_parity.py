@@ -597,6 +597,28 @@ def test_generic_n_fft(kw):
     assert np.max(np.abs(raw - oraw)) < 1e-4 and np.array_equal(fired, ofired)
 
 
+@pytest.mark.parametrize('kw,chunk', [(dict(hop_t=0.005), 1024), (dict(), 8000), (dict(), 12345), (dict(hop_t=0.02, window_t=0.05), 3000)],
+                         ids=['hop80_chunk1024', 'chunk8000', 'chunk12345_odd', 'hop320_chunk3000'])
+def test_many_frames_per_tick(kw, chunk):
+    """Chunks that complete more than 8 frames per stream and tick (the reference featurises whatever its carry buffer holds,
+    network_runner.py:139-144): fed as sub-chunks through the generic kernel, the network once per tick.  Windows, raw outputs
+    and detections against independent oracle Listeners, including the 13-frames-per-tick geometry hop_t = 0.005 / chunk 1024."""
+    m = _mod()
+    pr = m.ListenerParams(**kw)
+    opr = OracleParams(**pr.to_dict())
+    S, K = 5, max(6, 40000 // chunk)
+    pcm = noise(S, K * chunk, seed=chunk)
+    pcm[3] = 0
+    model = m.GruModel.random(pr.feature_size, 20, seed=5, scale=0.1)
+    raw, conf, fired, wins, count = _run_gpu_streams(m, model, pcm, chunk, pr=pr, sens=0.8, lvl=1)
+    owins = _oracle_windows(pcm, chunk, opr)
+    assert np.max(np.abs(wins - owins)) < 2e-4
+    w = og.GruWeights(model.kernel, model.recurrent, model.bias, model.dense_w, model.dense_b)
+    oraw, oconf, ofired = run_streams(w, pcm, chunk, pr=opr, sensitivity=0.8, trigger_level=1)
+    assert np.max(np.abs(raw - oraw)) < 1e-4 and np.array_equal(fired, ofired)
+    assert count == fired.sum()
+
+
 def test_unsupported_and_errors():
     m = _mod()
     with pytest.raises(NotImplementedError):
