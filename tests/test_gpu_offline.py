@@ -109,3 +109,41 @@ def test_engine_wire_protocol(tmp_path):
     assert abs(float(r.stdout) - conf[0, -1]) <= step          # state is chunking-independent
     r = subprocess.run([sys.executable, '-m', 'mycroft_precise_b200.engine', '-v'], capture_output=True, env=env, timeout=120)
     assert r.stdout.strip() == m.__version__.encode()
+
+
+def test_model_formats_through_drop_in_classes(tmp_path):
+    """The three model file formats the reference's Listener.find_runner dispatches on (network_runner.py:111-119: .net Keras HDF5,
+    .pb frozen graph) plus this package's .npz, each through B200Runner, B200Engine and the precise-engine CLI: same numbers as
+    the in-memory model.  (.net written by tests/h5_writer.py, .pb by the GraphDef writer of tests/test_model_io.py -- files from
+    Keras / TensorFlow themselves cannot be produced in this image.)"""
+    import mycroft_precise_b200 as m
+    sys.path.insert(0, os.path.dirname(__file__))
+    from h5_writer import keras_model_file
+    from test_model_io import _const_node, _ld, _model_config
+    model = m.GruModel.random(13, 20, seed=12, scale=0.1)
+    paths = {}
+    paths['npz'] = str(tmp_path / 'model.npz')
+    m.save_weights(paths['npz'], model)
+    paths['pb'] = str(tmp_path / 'model.pb')
+    open(paths['pb'], 'wb').write(_ld(1, _ld(1, b'import/net_input') + _ld(2, b'Placeholder')) + _const_node('net/kernel', model.kernel)
+                                   + _const_node('net/recurrent_kernel', model.recurrent) + _const_node('net/bias', model.bias)
+                                   + _const_node('dense_1/kernel', model.dense_w.reshape(20, 1)) + _const_node('dense_1/bias', np.float32([model.dense_b])))
+    paths['net'] = str(tmp_path / 'model.net')
+    open(paths['net'], 'wb').write(keras_model_file(model.kernel, model.recurrent, model.bias, model.dense_w, model.dense_b, _model_config()))
+    rs = np.random.RandomState(3)
+    x = rs.randn(7, 29, 13).astype(np.float32)
+    pcm = np.clip(rs.randn(1024 * 28) * 3000, -32768, 32767).astype('<i2')
+    want_p = m.B200Runner(model).predict(x)
+    eng = m.B200Engine(model, 2048); eng.start()
+    want_e = [eng.get_prediction(pcm[k * 1024:(k + 1) * 1024].tobytes()) for k in range(28)]
+    eng.stop()
+    env = dict(os.environ, PYTHONPATH=ROOT)
+    for kind, path in paths.items():
+        assert np.array_equal(m.B200Runner(path).predict(x), want_p), kind
+        eng = m.B200Engine(path, 2048); eng.start()
+        got_e = [eng.get_prediction(pcm[k * 1024:(k + 1) * 1024].tobytes()) for k in range(28)]
+        eng.stop()
+        assert got_e == want_e, kind
+        r = subprocess.run([sys.executable, '-m', 'mycroft_precise_b200.engine', path, '2048'], input=pcm.tobytes(), capture_output=True, env=env, timeout=300)
+        assert r.returncode == 0, (kind, r.stderr.decode()[-1500:])
+        assert [float(v) for v in r.stdout.split(b'\n')[:-1]] == want_e, kind
