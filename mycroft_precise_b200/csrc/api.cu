@@ -563,7 +563,8 @@ PB_API int pb_load_weights(pb_handle* h, const float* kernel, const float* recur
                 }
             cudaFree(h->d_xfrag16); h->d_xfrag16 = nullptr;
             CK(upload(&h->d_xfrag16, xf16));
-            CK(ensure_dyn_smem(gru_mma16_kernel<20, 13>, (size_t)K2_STAGED_SMEM));
+            CK(ensure_dyn_smem(gru_mma16_kernel<20, 13, 4>, (size_t)K2_STAGED_SMEM));
+            CK(ensure_dyn_smem(gru_mma16_kernel<20, 13, 5>, (size_t)K2_STAGED_SMEM));
         }
         {   // input projection table: wx[f][col], col = gate * 24 + unit (same column order as the accumulator tiles)
             std::vector<float> pw((size_t)F * PROJ_COLS, 0.f), pbias(PROJ_COLS, 0.f);
@@ -914,7 +915,10 @@ static int launch_gru(pb_handle* h, const K2In& in, bool ring, int64_t n, const 
             else {                           // default: fp16x3 recurrent products (half the tensor-pipe time), staged projection blocks
                 GruMma16W w16;
                 w16.bfrag = h->d_bfrag16; w16.xfrag = h->d_xfrag16; w16.bias = h->d_mma_bias; w16.wd = h->d_mma_wd; w16.bd = h->bd;
-                gru_mma16_kernel<20, 13><<<(int)((n + per1 - 1) / per1), MMA_THREADS, K2_STAGED_SMEM, s>>>(w16, in, n, dp, o);
+                if (h->gru_mode == 11)       // A/B: 5 CTAs per SM (96 registers, a small spill): 215 vs 211 us
+                    gru_mma16_kernel<20, 13, 5><<<(int)((n + per1 - 1) / per1), MMA_THREADS, K2_STAGED_SMEM, s>>>(w16, in, n, dp, o);
+                else                         // 4 CTAs per SM, 128 registers
+                    gru_mma16_kernel<20, 13, 4><<<(int)((n + per1 - 1) / per1), MMA_THREADS, K2_STAGED_SMEM, s>>>(w16, in, n, dp, o);
             }
         } else if (ring && in.proj != nullptr) gru_mma_kernel<20, 13, true, true><<<grid, MMA_THREADS, 0, s>>>(w, in, n, dp, o);
         else if (ring) gru_mma_kernel<20, 13, true, false><<<grid, MMA_THREADS, 0, s>>>(w, in, n, dp, o);
@@ -1109,7 +1113,7 @@ PB_API int pb_update_vectors(pb_handle* h, const int16_t* d_pcm, const int32_t* 
 
 // Does a tick of n streams run the scan that reads cached input projections (gru_mma_kernel<.., PROJ>)?
 static bool wants_projection(const pb_handle* h, int64_t n) {
-    return h->has_proj && h->small_path && n > K2_WARP_PATH_MAX && (h->gru_mode == 0 || h->gru_mode == 2 || h->gru_mode == 7 || h->gru_mode == 8 || h->gru_mode == 9 || h->gru_mode == 10);
+    return h->has_proj && h->small_path && n > K2_WARP_PATH_MAX && (h->gru_mode == 0 || h->gru_mode == 2 || h->gru_mode == 7 || h->gru_mode == 8 || h->gru_mode == 9 || h->gru_mode == 10 || h->gru_mode == 11);
 }
 
 // Recompute the projection of every ring row once (all streams), then the cache is maintained incrementally.
@@ -1144,7 +1148,7 @@ PB_API int pb_update(pb_handle* h, const int16_t* d_pcm, const int32_t* d_ids, i
     // The default scan (gru_mma16_kernel, gru_mode 0) projects the frames a tick has added itself, in its prologue; the separate
     // projection kernel serves the other scans (A/B modes) and short sub-batches of a large host tick (second case below), whose
     // warp-per-stream kernel does not touch the cache.
-    const bool scan_projects = want_proj && h->gru_mode == 0;
+    const bool scan_projects = want_proj && (h->gru_mode == 0 || h->gru_mode == 11);
     if ((want_proj && !scan_projects) || (!want_proj && h->host_tick_proj && !h->proj_dirty)) {
         ProfScope ps(h, 3, s);
         const long long items = (long long)n * h->max_new;

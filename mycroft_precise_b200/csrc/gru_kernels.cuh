@@ -770,8 +770,8 @@ __device__ __forceinline__ void mma3_f16(float (*acc)[4], int nt0, const uint32_
 // The kernel also keeps the cache itself: before the scan, every warp projects the frames this tick has added for its 16 streams
 // (x . [Wz|Wr|Wh] + b, one k16 MMA per n-tile and pass) and writes them into the cache blocks -- the separate projection
 // kernel of the other variants (39 us per tick) is not launched on this path.
-template <int H, int F>
-__global__ void __launch_bounds__(MMA_THREADS, 5)
+template <int H, int F, int CTAS = 4>
+__global__ void __launch_bounds__(MMA_THREADS, CTAS)
 gru_mma16_kernel(GruMma16W W, K2In in, long long n, DecodeParams dp, K2Out out) {
     static_assert(H <= 24 && F <= 16, "tile counts are fixed");
     extern __shared__ __align__(128) unsigned char k2_stage_raw[];
