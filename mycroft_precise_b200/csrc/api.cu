@@ -706,8 +706,8 @@ PB_API int pb_debug_gru_mode(pb_handle* h, int mode) { if (!h) return fail(PB_ER
 PB_API int pb_debug_k1_mode(pb_handle* h, int mode) {
     if (!h) return fail(PB_ERR_INVALID, "null handle");
     if (mode >= 100 && mode <= 116 && h->tc3_ok) { h->k1_mode = mode; return PB_OK; }      // mode 5 with the phase timeline of warp (mode - 100) in pb_debug_counters
-    if (mode < 0 || mode > 5 || mode == 1) return fail(PB_ERR_INVALID, "k1 mode must be 0 (automatic), 2 (FFT kernel, lean set-up), 3 (FFT kernel), 4 (tensor-core DFT kernel, stage 2 only) or 5 (both DFT stages on the tensor cores)");
-    if (mode >= 5 && !h->tc3_ok) return fail(PB_ERR_UNSUPPORTED, "the two-stage tensor-core MFCC tick needs the default mel geometry, hop >= 512 and chunk >= hop, a multiple of 8");
+    if (mode < 0 || mode > 6 || mode == 1) return fail(PB_ERR_INVALID, "k1 mode must be 0 (automatic), 2 (FFT kernel, lean set-up), 3 (FFT kernel), 4 (tensor-core DFT kernel, stage 2 only) or 5 (both DFT stages on the tensor cores)");
+    if (mode >= 5 && mode <= 6 && !h->tc3_ok) return fail(PB_ERR_UNSUPPORTED, "the two-stage tensor-core MFCC tick needs the default mel geometry, hop >= 512 and chunk >= hop, a multiple of 8");
     if (mode == 4 && !h->tc2_ok) return fail(PB_ERR_UNSUPPORTED, "the tensor-core MFCC tick needs the default mel geometry (20 filters, 16 kHz, n_fft 512), chunk >= 512 and a multiple of 8");
     if (mode == 2 && !h->fast_ok) return fail(PB_ERR_UNSUPPORTED, "k1 mode 2 needs the aligned geometry of the fast MFCC kernels");
     h->k1_mode = mode;
@@ -1049,7 +1049,7 @@ static int launch_stream_mfcc(pb_handle* h, const int16_t* d_pcm, const int32_t*
     // tensor cores (measured on B200: 116 vs 128 us at 65 536 streams, 208 vs 228 us at 131 072, 392 vs 414 us at 262 144; below
     // that its persistent pipeline does not fill and the FFT kernel wins: 71 vs 64 us at 32 768).
     const bool tc3_auto = h->k1_mode == 0 && n >= TC3_MIN_STREAMS;
-    if ((h->k1_mode == 5 || h->k1_mode >= 100 || tc3_auto) && h->tc3_ok && (uintptr_t)d_pcm % 16 == 0 && !h->force_generic) {
+    if ((h->k1_mode == 5 || h->k1_mode == 6 || h->k1_mode >= 100 || tc3_auto) && h->tc3_ok && (uintptr_t)d_pcm % 16 == 0 && !h->force_generic) {
         int rc = ensure_tc3_tables(h);
         if (rc != PB_OK) return rc;
         Tc3Tables t;
@@ -1063,7 +1063,7 @@ static int launch_stream_mfcc(pb_handle* h, const int16_t* d_pcm, const int32_t*
         if (h->k1_mode >= 100)          // phase timeline of one warp (pb_debug_counters): separate instantiation, the counters cost registers
             mfcc_tc3_kernel<Tc2Geo20, true><<<g3, TC3_THREADS, sizeof(Tc3Smem) + 128, s>>>(t, h->d_tc3_recs, h->d_tc3_counters, par, h->k1_mode, h->d_dbg);
         else
-            mfcc_tc3_kernel<Tc2Geo20, false><<<g3, TC3_THREADS, sizeof(Tc3Smem) + 128, s>>>(t, h->d_tc3_recs, h->d_tc3_counters, par, 0, nullptr);
+            mfcc_tc3_kernel<Tc2Geo20, false><<<g3, TC3_THREADS, sizeof(Tc3Smem) + 128, s>>>(t, h->d_tc3_recs, h->d_tc3_counters, par, h->k1_mode == 6 ? 8 : 0, nullptr);   // 6: A/B of the epilogue's shuffle-gather tail
     } else if (h->k1_mode == 4 && h->tc2_ok && (uintptr_t)d_pcm % 16 == 0 && !h->force_generic) {
         int rc = ensure_tcd_tables(h);
         if (rc != PB_OK) return rc;

@@ -669,42 +669,80 @@ mfcc_tc3_kernel(Tc3Tables tab, const Tc3Rec* __restrict__ recs, unsigned int* __
                         for (int q = 0; q < 6; ++q) pr[q] = make_float4(pv[4 * q], pv[4 * q + 1], pv[4 * q + 2], pv[4 * q + 3]);
                     }
                     asm volatile("bar.sync 1, 256;" ::: "memory");
-                    const int t8 = q4 + 4 * wg;                  // 0..7: thread t8 < 5 sums and logs filters 4 t8 .. 4 t8 + 3, thread 5 the total power
-                    if (t8 < 6) {
+                    if ((dbg & 8) && dbg < 100) {
+                        // Variant (A/B): after the exchange, warp w takes frames 4 w .. 4 w + 3 of the tile, eight lanes per frame: lane j8 < 5 sums the
+                        // eight partial sums of filters 4 j8 .. 4 j8 + 3 and takes their logs, lane 5 the total power; the 20 log-mels are gathered
+                        // inside the 8-lane group by shuffles, and lane j8 forms DCT rows j8 and j8 + 8.  No second barrier.
+                        const int fr = 4 * warp + (lane >> 3), j8 = lane & 7;
                         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (j8 < 6) {
 #pragma unroll
-                        for (int v = 0; v < 8; ++v) {
-                            const float4 a = *reinterpret_cast<const float4*>(&sm.part[32 * v + lane][4 * t8]);
-                            acc.x += a.x; acc.y += a.y; acc.z += a.z; acc.w += a.w;
-                        }
-                        if (t8 < 5) {
-                            float4 lg;
-                            lg.x = __logf(fmaxf(acc.x * tab.pscale, K1_EPS)); lg.y = __logf(fmaxf(acc.y * tab.pscale, K1_EPS));
-                            lg.z = __logf(fmaxf(acc.z * tab.pscale, K1_EPS)); lg.w = __logf(fmaxf(acc.w * tab.pscale, K1_EPS));
-                            *reinterpret_cast<float4*>(&sm.lgm[lane][4 * t8]) = lg;
-                        } else {
-                            sm.c0v[lane] = __logf(fmaxf(acc.x * tab.pscale, K1_EPS));
-                        }
-                    }
-                    asm volatile("bar.sync 1, 256;" ::: "memory");
-                    if (r.frame != nullptr) {
-                        float* rowp = r.row;
-                        float lg[G::n_filt];
-#pragma unroll
-                        for (int q = 0; q < G::n_filt / 4; ++q) {
-                            const float4 a = *reinterpret_cast<const float4*>(&sm.lgm[lane][4 * q]);
-                            lg[4 * q] = a.x; lg[4 * q + 1] = a.y; lg[4 * q + 2] = a.z; lg[4 * q + 3] = a.w;
-                        }
-                        for (int o = t8; o < tab.n_out; o += 8) {
-                            const float4* d4 = reinterpret_cast<const float4*>(sm.dct[o]);
-                            float v0 = 0.f, v1 = 0.f;
-#pragma unroll
-                            for (int q = 0; q < G::n_filt / 4; ++q) {
-                                const float4 dd = d4[q];
-                                v0 = fmaf(dd.x, lg[4 * q], v0); v1 = fmaf(dd.y, lg[4 * q + 1], v1);
-                                v0 = fmaf(dd.z, lg[4 * q + 2], v0); v1 = fmaf(dd.w, lg[4 * q + 3], v1);
+                            for (int v = 0; v < 8; ++v) {
+                                const float4 a = *reinterpret_cast<const float4*>(&sm.part[32 * v + fr][4 * j8]);
+                                acc.x += a.x; acc.y += a.y; acc.z += a.z; acc.w += a.w;
                             }
-                            rowp[o] = o == 0 ? sm.c0v[lane] : v0 + v1;
+                        }
+                        float lg4[4];
+                        lg4[0] = __logf(fmaxf(acc.x * tab.pscale, K1_EPS)); lg4[1] = __logf(fmaxf(acc.y * tab.pscale, K1_EPS));
+                        lg4[2] = __logf(fmaxf(acc.z * tab.pscale, K1_EPS)); lg4[3] = __logf(fmaxf(acc.w * tab.pscale, K1_EPS));
+                        float lg[G::n_filt];
+                        const int grp = lane & ~7;
+#pragma unroll
+                        for (int q = 0; q < G::n_filt; ++q) lg[q] = __shfl_sync(0xffffffffu, lg4[q & 3], grp | (q >> 2));
+                        const float c0 = __shfl_sync(0xffffffffu, lg4[0], grp | 5);
+                        const Tc3Rec& rr = sm.rec[ke & (TC3_REC_RING - 1)][fr];
+                        if (rr.frame != nullptr) {
+                            float* rowp = rr.row;
+                            for (int o = j8; o < tab.n_out; o += 8) {
+                                const float4* d4 = reinterpret_cast<const float4*>(sm.dct[o]);
+                                float v0 = 0.f, v1 = 0.f;
+#pragma unroll
+                                for (int q = 0; q < G::n_filt / 4; ++q) {
+                                    const float4 dd = d4[q];
+                                    v0 = fmaf(dd.x, lg[4 * q], v0); v1 = fmaf(dd.y, lg[4 * q + 1], v1);
+                                    v0 = fmaf(dd.z, lg[4 * q + 2], v0); v1 = fmaf(dd.w, lg[4 * q + 3], v1);
+                                }
+                                rowp[o] = o == 0 ? c0 : v0 + v1;
+                            }
+                        }
+                    } else {
+                        const int t8 = q4 + 4 * wg;                  // 0..7: thread t8 < 5 sums and logs filters 4 t8 .. 4 t8 + 3, thread 5 the total power
+                        if (t8 < 6) {
+                            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    #pragma unroll
+                            for (int v = 0; v < 8; ++v) {
+                                const float4 a = *reinterpret_cast<const float4*>(&sm.part[32 * v + lane][4 * t8]);
+                                acc.x += a.x; acc.y += a.y; acc.z += a.z; acc.w += a.w;
+                            }
+                            if (t8 < 5) {
+                                float4 lg;
+                                lg.x = __logf(fmaxf(acc.x * tab.pscale, K1_EPS)); lg.y = __logf(fmaxf(acc.y * tab.pscale, K1_EPS));
+                                lg.z = __logf(fmaxf(acc.z * tab.pscale, K1_EPS)); lg.w = __logf(fmaxf(acc.w * tab.pscale, K1_EPS));
+                                *reinterpret_cast<float4*>(&sm.lgm[lane][4 * t8]) = lg;
+                            } else {
+                                sm.c0v[lane] = __logf(fmaxf(acc.x * tab.pscale, K1_EPS));
+                            }
+                        }
+                        asm volatile("bar.sync 1, 256;" ::: "memory");
+                        if (r.frame != nullptr) {
+                            float* rowp = r.row;
+                            float lg[G::n_filt];
+    #pragma unroll
+                            for (int q = 0; q < G::n_filt / 4; ++q) {
+                                const float4 a = *reinterpret_cast<const float4*>(&sm.lgm[lane][4 * q]);
+                                lg[4 * q] = a.x; lg[4 * q + 1] = a.y; lg[4 * q + 2] = a.z; lg[4 * q + 3] = a.w;
+                            }
+                            for (int o = t8; o < tab.n_out; o += 8) {
+                                const float4* d4 = reinterpret_cast<const float4*>(sm.dct[o]);
+                                float v0 = 0.f, v1 = 0.f;
+    #pragma unroll
+                                for (int q = 0; q < G::n_filt / 4; ++q) {
+                                    const float4 dd = d4[q];
+                                    v0 = fmaf(dd.x, lg[4 * q], v0); v1 = fmaf(dd.y, lg[4 * q + 1], v1);
+                                    v0 = fmaf(dd.z, lg[4 * q + 2], v0); v1 = fmaf(dd.w, lg[4 * q + 3], v1);
+                                }
+                                rowp[o] = o == 0 ? sm.c0v[lane] : v0 + v1;
+                            }
                         }
                     }
                 }

@@ -696,7 +696,7 @@ def test_runner_plugin_predict_shape():
     assert abs(r.run(x[2]) - p[2, 0]) < 1e-7
 
 
-@pytest.mark.parametrize('k1_mode', [3, 4, 5], ids=['fft_64bit_setup', 'tensor_core', 'tensor_core_two_stage'])
+@pytest.mark.parametrize('k1_mode', [3, 4, 5, 6], ids=['fft_64bit_setup', 'tensor_core', 'tensor_core_two_stage', 'two_stage_shuffle_epilogue'])
 def test_alternative_mfcc_tick_kernels(k1_mode):
     """pb_debug_k1_mode against the default kernel (FFT on the CUDA cores, 32-bit per-pass set-up): 3 = the same kernel with its
     original 64-bit set-up (must be bit-identical: same arithmetic, different address computation), 4 = stage 2 of the DFT on
