@@ -195,9 +195,11 @@ int pb_set_cdf(pb_handle* h, const double* h_cd, int64_t len);
 /* Test hook: route the aligned default geometry through the generic (any-alignment) MFCC kernels
  * instead of the warp-autonomous fast kernels, so both implementations are covered by parity tests. */
 int pb_debug_force_generic(pb_handle* h, int on);
-/* Test hook for the default network (H=20, F=13): 0 = automatic choice (warp-per-stream kernel for small
- * batches, tensor-core scan otherwise), 1 = CUDA-core thread-per-stream kernel, 2 = tensor-core kernel,
- * 3 = tcgen05 scan, 7 = tensor-core kernel with 32-stream warp tiles. */
+/* Test / A-B hook for the default network (H=20, F=13): 0 = automatic choice (warp-per-stream kernel up to 8192 streams per tick; above,
+ * the fp16x3 mma.sync scan over bulk-copy-staged cached projections, which also projects the tick's new frames), 1 = CUDA-core
+ * thread-per-stream kernel, 2 = tensor-core kernel also for small batches, 3 = tcgen05 scan, 7 = 3xTF32 scan with 32-stream warp
+ * tiles, 8 = tcgen05 scan over cached projections, 9 = 3xTF32 scan over cached projections without staging, 10 = with staging,
+ * 11 = the default scan at 5 CTAs per SM.  All variants are parity-tested on B200 (tests/test_gpu_parity.py). */
 int pb_debug_gru_mode(pb_handle* h, int mode);
 /* Test / A-B hook for the stateful tick's MFCC kernel (aligned default geometry).  0 = automatic: from 49 152 streams per tick on the
  * kernel with both DFT stages on the tensor cores (csrc/mfcc_tc3.cuh: int16 samples split exactly into two fp16 pieces, tcgen05
