@@ -292,8 +292,8 @@ PB_API int pb_create(const pb_config* cfg, pb_handle** out) {
     if (c.vectorizer == PB_VEC_SPEECHPY_MFCCS)
         return fail(PB_ERR_UNSUPPORTED, "Vectorizer.speechpy_mfccs (legacy .params without 'vectorizer', precise/params.py:147) is not implemented");
     if (c.vectorizer != PB_VEC_MFCCS && c.vectorizer != PB_VEC_MELS) return fail(PB_ERR_INVALID, "unknown vectorizer %d", c.vectorizer);
-    if (!is_pow2(c.n_fft) || c.n_fft < 64 || c.n_fft > 512)
-        return fail(PB_ERR_UNSUPPORTED, "n_fft %d: powers of two in [64, 512] are implemented (512 is the reference default)", c.n_fft);
+    if (!is_pow2(c.n_fft) || c.n_fft < 64 || c.n_fft > 1024)
+        return fail(PB_ERR_UNSUPPORTED, "n_fft %d: powers of two in [64, 1024] are implemented (512 is the reference default)", c.n_fft);
     if (c.n_filt < 1 || c.n_filt > 64 || c.n_mfcc < 1 || c.n_mfcc > 64) return fail(PB_ERR_UNSUPPORTED, "n_filt and n_mfcc must be in [1, 64]");
     if (c.n_thresholds < 1 || c.n_thresholds > PB_MAX_THRESHOLDS) return fail(PB_ERR_INVALID, "n_thresholds must be in [1, %d]", PB_MAX_THRESHOLDS);
     if (c.activation < 0 || c.activation > 1 || c.recurrent_activation < 0 || c.recurrent_activation > 1)
@@ -320,8 +320,9 @@ PB_API int pb_create(const pb_config* cfg, pb_handle** out) {
     h->tail_cap = (h->used + 7) & ~7;            // rows stay 16-byte aligned
     h->max_new = c.chunk_samples / c.hop_samples + 2;
 
-    h->k1_batch_smem = sizeof(K1Smem) + (size_t)h->n_out * c.n_filt * sizeof(float);
-    h->k1_stream_smem = sizeof(K1StreamSmem) + (size_t)h->n_out * c.n_filt * sizeof(float);
+    const size_t k1_big = c.n_fft > 512 ? k1_big_smem + 16 : 0;      // n_fft = 1024: power rows and FFT scratch in the dynamic tail
+    h->k1_batch_smem = sizeof(K1Smem) + (size_t)h->n_out * c.n_filt * sizeof(float) + k1_big;
+    h->k1_stream_smem = sizeof(K1StreamSmem) + (size_t)h->n_out * c.n_filt * sizeof(float) + k1_big;
     std::vector<float> wrise, wfall;
     std::vector<int> grid;
     int rc = build_mel(h, wrise, wfall, grid);

@@ -79,7 +79,7 @@ __device__ __forceinline__ cpx load_elem(const FrameSrc<T>& s, int m) {
     return r;
 }
 
-// Any power-of-two n_fft <= 512 (the reference lets n_fft be configured, precise/params.py:49): a whole warp transforms
+// Any power-of-two n_fft <= 1024 (the reference lets n_fft be configured, precise/params.py:49; scratch: n_fft float2): a whole warp transforms
 // one frame with a plain radix-2 shared-memory FFT (real input as complex), then writes the scaled power bins.  Slow path.
 template <typename T>
 __device__ __forceinline__ void fft_any_power(const FrameSrc<T>& s, int n_fft, const float2* __restrict__ tw, float2* scratch,
@@ -107,7 +107,9 @@ __device__ __forceinline__ void fft_any_power(const FrameSrc<T>& s, int n_fft, c
 }
 
 // Per-CTA copy of the small tables (broadcast reads in phase B).
-constexpr int K1_MAX_BINS = 257;
+constexpr int K1_MAX_BINS = 513;          // n_fft <= 1024
+constexpr int K1_PSTRIDE_BIG = 513;       // power-row stride for n_fft = 1024 (rows and FFT scratch then live in the dynamic tail, see k1_big_smem)
+constexpr size_t k1_big_smem = (size_t)32 * K1_PSTRIDE_BIG * sizeof(float) + (size_t)4 * 1024 * sizeof(float2);   // K1_TILE rows + K1_WARPS scratches
 constexpr int K1_MAX_FILT = 64;
 struct K1Tables {
     float2 w[K1_MAX_BINS + 3];                 // (w_rise, w_fall) per bin
@@ -210,6 +212,12 @@ mfcc_batch_kernel(const T* __restrict__ pcm, long long samples_per_stream, long 
     load_lane_const(lc, tab.tw_stage, tab.tw_post, l16);
     float2* xch = sm.xch + (warp * 2 + half) * XCH_ELEMS;
     load_tables(sm.tab, tab, reinterpret_cast<float*>(smem_raw + sizeof(K1Smem)));
+    // n_fft = 1024: power rows (513 bins) and the warp FFT's scratch (1024 float2) do not fit the static arrays; they follow the DCT table
+    const bool big = tab.n_fft > 512;
+    unsigned char* big_base = smem_raw + ((sizeof(K1Smem) + (size_t)tab.n_out * tab.n_filt * sizeof(float) + 15) & ~(size_t)15);
+    float* const power = big ? reinterpret_cast<float*>(big_base) : sm.power;
+    const int ps = big ? K1_PSTRIDE_BIG : K1_PSTRIDE;
+    float2* const xany = big ? reinterpret_cast<float2*>(big_base + (size_t)K1_TILE * K1_PSTRIDE_BIG * sizeof(float)) + warp * 1024 : sm.xch + warp * 2 * XCH_ELEMS;
     __syncthreads();
     const long long n_tiles = (total_frames + K1_TILE - 1) / K1_TILE;
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -224,7 +232,7 @@ mfcc_batch_kernel(const T* __restrict__ pcm, long long samples_per_stream, long 
                 FrameSrc<T> src;
                 src.p0 = pcm + s * samples_per_stream + f * hop;
                 src.p1 = src.p0; src.len0 = used; src.used = used;
-                fft_any_power<T>(src, tab.n_fft, tab.tw_any, sm.xch + warp * 2 * XCH_ELEMS, sm.power + slot * K1_PSTRIDE, scale, lane);
+                fft_any_power<T>(src, tab.n_fft, tab.tw_any, xany, power + slot * ps, scale, lane);
             }
         } else
 #pragma unroll 1
@@ -250,7 +258,7 @@ mfcc_batch_kernel(const T* __restrict__ pcm, long long samples_per_stream, long 
         // ---- phase B: thread per frame
         if (threadIdx.x < K1_TILE) {
             const long long g = g_base + threadIdx.x;
-            if (g < total_frames) mel_log_dct<false>(sm.power + threadIdx.x * K1_PSTRIDE, sm.tab, tab, out + g * tab.n_out);
+            if (g < total_frames) mel_log_dct<false>(power + threadIdx.x * ps, sm.tab, tab, out + g * tab.n_out);
         }
         __syncthreads();
     }
@@ -297,6 +305,11 @@ mfcc_stream_kernel(const int16_t* __restrict__ pcm, const int* __restrict__ ids,
     load_lane_const(lc, tab.tw_stage, tab.tw_post, l16);
     float2* xch = sm.k1.xch + (warp * 2 + half) * XCH_ELEMS;
     load_tables(sm.k1.tab, tab, reinterpret_cast<float*>(smem_raw + sizeof(K1StreamSmem)));
+    const bool big = tab.n_fft > 512;                           // see mfcc_batch_kernel
+    unsigned char* big_base = smem_raw + ((sizeof(K1StreamSmem) + (size_t)tab.n_out * tab.n_filt * sizeof(float) + 15) & ~(size_t)15);
+    float* const power = big ? reinterpret_cast<float*>(big_base) : sm.k1.power;
+    const int ps = big ? K1_PSTRIDE_BIG : K1_PSTRIDE;
+    float2* const xany = big ? reinterpret_cast<float2*>(big_base + (size_t)K1_TILE * K1_PSTRIDE_BIG * sizeof(float)) + warp * 1024 : sm.k1.xch + warp * 2 * XCH_ELEMS;
     const int n_tiles = (n + K1_STREAMS_PER_CTA - 1) / K1_STREAMS_PER_CTA;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int base = tile * K1_STREAMS_PER_CTA;
@@ -339,7 +352,7 @@ mfcc_stream_kernel(const int16_t* __restrict__ pcm, const int* __restrict__ ids,
                         src.p0 = st.tail + (long long)sm.st_id[t] * st.tail_cap + (a0 - sm.st_ts0[t]);
                         src.p1 = chunk_p;
                     }
-                    fft_any_power<int16_t>(src, tab.n_fft, tab.tw_any, sm.k1.xch + warp * 2 * XCH_ELEMS, sm.k1.power + slot * K1_PSTRIDE, scale, lane);
+                    fft_any_power<int16_t>(src, tab.n_fft, tab.tw_any, xany, power + slot * ps, scale, lane);
                 }
             } else
 #pragma unroll 1
@@ -374,7 +387,7 @@ mfcc_stream_kernel(const int16_t* __restrict__ pcm, const int* __restrict__ ids,
                 const int t = sm.fr_stream[r0 + threadIdx.x];
                 const long long k = sm.st_c0[t] + sm.fr_sub[r0 + threadIdx.x];
                 float* row = st.ring + ((long long)sm.st_id[t] * st.ring_rows + (int)(k % st.ring_rows)) * st.row_stride;
-                mel_log_dct<true>(sm.k1.power + threadIdx.x * K1_PSTRIDE, sm.k1.tab, tab, row);
+                mel_log_dct<true>(power + threadIdx.x * ps, sm.k1.tab, tab, row);
             }
             __syncthreads();
         }

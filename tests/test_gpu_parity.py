@@ -572,9 +572,11 @@ def test_mels_vectorizer():
 
 
 @pytest.mark.parametrize('kw', [dict(n_fft=256), dict(n_fft=128, window_t=0.02, hop_t=0.01), dict(n_fft=64, n_filt=12, n_mfcc=8),
-                                dict(n_fft=256, window_t=0.01, hop_t=0.005)])
+                                dict(n_fft=256, window_t=0.01, hop_t=0.005), dict(n_fft=1024), dict(n_fft=1024, window_t=0.05, hop_t=0.02, n_filt=26),
+                                dict(n_fft=1024, hop_t=0.005)])
 def test_generic_n_fft(kw):
-    """n_fft is a ListenerParams field (precise/params.py:49); any power of two in [64, 512] runs through the radix-2 path.
+    """n_fft is a ListenerParams field (precise/params.py:49); any power of two in [64, 1024] other than 512 runs through the radix-2
+    path (1024: crop to 1024 of 1600 samples, zero-pad of an 800-sample window, and 13+ frames per tick at hop_t = 0.005).
     Covers crop (window > n_fft) and zero-pad (window < n_fft) framing, batch and streaming."""
     m = _mod()
     pr = m.ListenerParams(**kw)
@@ -588,7 +590,7 @@ def test_generic_n_fft(kw):
     print(kw, 'mfcc err', np.max(np.abs(got - want)))
     assert np.max(np.abs(got - want)) < 2e-4
     c.close()
-    chunk = min(1024, 4 * pr.hop_samples)          # a tick may release at most 8 frames
+    chunk = 1024 if pr.n_fft == 1024 else min(1024, 4 * pr.hop_samples)
     pcm = noise(4, 24 * chunk, seed=29)
     model = m.GruModel.random(pr.feature_size, 20, seed=5, scale=0.1)
     raw, conf, fired, wins, count = _run_gpu_streams(m, model, pcm, chunk, pr=pr)
@@ -622,7 +624,7 @@ def test_many_frames_per_tick(kw, chunk):
 def test_unsupported_and_errors():
     m = _mod()
     with pytest.raises(NotImplementedError):
-        m.PreciseB200(m.ListenerParams(n_fft=1024))
+        m.PreciseB200(m.ListenerParams(n_fft=2048))
     with pytest.raises(NotImplementedError):
         m.PreciseB200(m.ListenerParams(n_fft=384))
     with pytest.raises(NotImplementedError):
