@@ -44,7 +44,7 @@ typedef enum pb_status {
 } pb_status;
 
 /* Vectorizer ids, precise/params.py:121-133 */
-enum { PB_VEC_MELS = 1, PB_VEC_MFCCS = 2, PB_VEC_SPEECHPY_MFCCS = 3 /* unsupported */ };
+enum { PB_VEC_MELS = 1, PB_VEC_MFCCS = 2, PB_VEC_SPEECHPY_MFCCS = 3 /* legacy vectoriser (precise/vectorization.py:40-42); restated from speechpy's published algorithm, parity unpinned */ };
 /* activations of the GRU layer (precise/model.py:77-82 uses linear + Keras default hard_sigmoid) */
 enum { PB_ACT_LINEAR = 0, PB_ACT_TANH = 1 };
 enum { PB_RACT_HARD_SIGMOID = 0, PB_RACT_SIGMOID = 1 };

@@ -66,6 +66,7 @@ struct pb_handle {
     int sm_count = 148;
     // derived
     int used = 0, n_bins = 0, n_out = 0, feat = 0, ring_rows = 0, row_stride = 0, tail_cap = 0, max_new = 0;
+    int rel_window = 0;              // samples before frame 0 is released: window_samples (sonopy), window_samples + hop_samples (speechpy drops the last complete frame)
     bool has_proj = false;           // default network: a second ring caches the input projections (gru_kernels.cuh)
     float* d_proj_ring = nullptr;
     bool proj_dirty = true;          // some ring rows lack a valid cached projection (weights changed / projection skipped)
@@ -140,6 +141,17 @@ static int build_mel(pb_handle* h, std::vector<float>& wrise, std::vector<float>
     const double top = 1127.0 * log(1.0 + (double)c.sample_rate / 700.0);
     grid.assign(nf + 2, 0);
     long long shift = 0, prev = -1;
+    if (c.vectorizer == PB_VEC_SPEECHPY_MFCCS) {
+        // speechpy.feature.filterbanks as speechpy.feature.mfe calls it (precise/vectorization.py:40-42; the package itself is not in
+        // the reference tree: PARITY UNPINNED, its published algorithm is restated): mel points between 0 and sample_rate / 2, corner bins
+        // floor((coefficients + 1) * hz / sample_rate) with coefficients = n_fft / 2 + 1, triangles without de-duplication.
+        const double top2 = 1127.0 * log(1.0 + 0.5 * (double)c.sample_rate / 700.0);
+        for (int i = 0; i < nf + 2; ++i) {
+            const double m = (i == nf + 1) ? top2 : (double)i * (top2 / (double)(nf + 1));
+            const double hz = 700.0 * (exp(m / 1127.0) - 1.0);
+            grid[i] = (int)floor((double)(nb + 1) * hz / (double)c.sample_rate);
+        }
+    } else
     for (int i = 0; i < nf + 2; ++i) {
         // np.linspace(0, top, nf + 2): i * step, last element forced to stop
         double m = (i == nf + 1) ? top : (double)i * (top / (double)(nf + 1));
@@ -289,9 +301,7 @@ PB_API int pb_create(const pb_config* cfg, pb_handle** out) {
     if (c.chunk_samples < 1) return fail(PB_ERR_INVALID, "chunk_samples must be >= 1");
     if (c.sample_rate < 1 || c.window_samples < 1 || c.hop_samples < 1 || c.n_features < 1 || c.hidden < 1)
         return fail(PB_ERR_INVALID, "sample_rate, window_samples, hop_samples, n_features, hidden must be positive");
-    if (c.vectorizer == PB_VEC_SPEECHPY_MFCCS)
-        return fail(PB_ERR_UNSUPPORTED, "Vectorizer.speechpy_mfccs (legacy .params without 'vectorizer', precise/params.py:147) is not implemented");
-    if (c.vectorizer != PB_VEC_MFCCS && c.vectorizer != PB_VEC_MELS) return fail(PB_ERR_INVALID, "unknown vectorizer %d", c.vectorizer);
+    if (c.vectorizer != PB_VEC_MFCCS && c.vectorizer != PB_VEC_MELS && c.vectorizer != PB_VEC_SPEECHPY_MFCCS) return fail(PB_ERR_INVALID, "unknown vectorizer %d", c.vectorizer);
     if (!is_pow2(c.n_fft) || c.n_fft < 64 || c.n_fft > 1024)
         return fail(PB_ERR_UNSUPPORTED, "n_fft %d: powers of two in [64, 1024] are implemented (512 is the reference default)", c.n_fft);
     if (c.n_filt < 1 || c.n_filt > 64 || c.n_mfcc < 1 || c.n_mfcc > 64) return fail(PB_ERR_UNSUPPORTED, "n_filt and n_mfcc must be in [1, 64]");
@@ -316,7 +326,9 @@ PB_API int pb_create(const pb_config* cfg, pb_handle** out) {
     // default-sized networks cache the input projection of every frame in a second ring (gru_mma_kernel<.., PROJ>)
     h->has_proj = c.hidden == 20 && h->n_out == 13 && !c.use_delta && c.vectorizer == PB_VEC_MFCCS &&
                   c.chunk_samples / c.hop_samples + 2 <= 8;      // long chunks (fed as sub-chunks, launch_stream_mfcc) may add more rows than the cache logic tracks
-    h->ring_rows = c.n_features + (c.window_samples - h->used) / c.hop_samples + 2;
+    // speechpy's stack_frames yields floor((len - window) / hop) frames, one fewer than sonopy's framing: frame k is released one hop later
+    h->rel_window = c.window_samples + (c.vectorizer == PB_VEC_SPEECHPY_MFCCS ? c.hop_samples : 0);
+    h->ring_rows = c.n_features + (h->rel_window - h->used) / c.hop_samples + 2;
     h->tail_cap = (h->used + 7) & ~7;            // rows stay 16-byte aligned
     h->max_new = c.chunk_samples / c.hop_samples + 2;
 
@@ -457,7 +469,7 @@ PB_API int pb_create(const pb_config* cfg, pb_handle** out) {
 
 PB_API int64_t pb_mfcc_frames(const pb_handle* h, int64_t n) {
     if (!h) return 0;
-    return n < h->cfg.window_samples ? 0 : (n - h->cfg.window_samples) / h->cfg.hop_samples + 1;
+    return n < h->rel_window ? 0 : (n - h->rel_window) / h->cfg.hop_samples + 1;
 }
 PB_API int32_t pb_feature_size(const pb_handle* h) { return h ? h->feat : 0; }
 PB_API int32_t pb_mfcc_width(const pb_handle* h) { return h ? h->n_out : 0; }
@@ -1164,7 +1176,7 @@ PB_API int pb_update(pb_handle* h, const int16_t* d_pcm, const int32_t* d_ids, i
     const bool use_proj = want_proj;
     K2In in{};
     in.ring = h->st.ring; in.n_samples = h->st.n_samples; in.ids = d_ids;
-    in.ring_rows = h->ring_rows; in.row_stride = h->row_stride; in.window = h->cfg.window_samples; in.hop = h->cfg.hop_samples;
+    in.ring_rows = h->ring_rows; in.row_stride = h->row_stride; in.window = h->rel_window; in.hop = h->cfg.hop_samples;
     in.T = h->cfg.n_features; in.F_base = h->n_out; in.use_delta = h->cfg.use_delta;
     K2Out o{};
     in.proj = use_proj ? h->d_proj_ring : nullptr;
@@ -1200,7 +1212,7 @@ PB_API int pb_read_window(pb_handle* h, const int32_t* d_ids, int64_t n, float* 
     CK(cudaSetDevice(h->cfg.device));
     K2In in{};
     in.ring = h->st.ring; in.n_samples = h->st.n_samples; in.ids = d_ids;
-    in.ring_rows = h->ring_rows; in.row_stride = h->row_stride; in.window = h->cfg.window_samples; in.hop = h->cfg.hop_samples;
+    in.ring_rows = h->ring_rows; in.row_stride = h->row_stride; in.window = h->rel_window; in.hop = h->cfg.hop_samples;
     in.T = h->cfg.n_features; in.F_base = h->n_out;
     long long total = n * in.T * in.F_base;
     read_window_kernel<<<(int)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(in, d_ids, n, d_out);

@@ -114,8 +114,47 @@ def mfcc_spec(audio, sample_rate, window, hop, n_fft, n_filt, n_mfcc) -> np.ndar
     return out
 
 
+def speechpy_grid(sample_rate: int, n_filt: int, n_bins: int) -> np.ndarray:
+    """Corner bins of speechpy.feature.filterbanks as speechpy.feature.mfe calls it: mel points between 0 and sample_rate / 2,
+    floor((coefficients + 1) * hz / sample_rate) with coefficients = n_bins (the power spectrum's width)."""
+    mels = np.linspace(0.0, 1127.0 * np.log(1.0 + 0.5 * sample_rate / 700.0), n_filt + 2)
+    hz = 700.0 * (np.exp(mels / 1127.0) - 1.0)
+    return np.floor((n_bins + 1) * hz / sample_rate).astype(np.int64)
+
+
+def speechpy_mfcc(audio, sample_rate, window, hop, n_fft, n_filt, n_mfcc) -> np.ndarray:
+    """Vectorizer.speechpy_mfccs (reference precise/vectorization.py:40-42 -> speechpy.feature.mfcc(x, sample_rate, window_t, hop_t,
+    n_mfcc, n_filt, n_fft)).  ** PARITY UNPINNED **: speechpy-fast (setup.py:86) is absent from the reference tree and from this
+    image; this restates its published algorithm: stack_frames without zero padding yields floor((len - window) / hop) frames (the
+    last complete frame is dropped), rectangular frames, power = |rfft(frame, n_fft)|^2 / n_fft (a longer frame is cropped),
+    triangular filters on speechpy_grid (triangle(): rising on (left, middle), falling on [middle, right)), zeros replaced by eps
+    before the log, DCT-II (norm='ortho') truncated to n_mfcc, coefficient 0 replaced by the log of the frame energy."""
+    audio = np.asarray(audio, dtype=np.float64)
+    n_frames = int(np.floor((len(audio) - window) / hop)) if len(audio) >= window else 0
+    n_out = min(n_filt, n_mfcc)
+    if n_frames <= 0:
+        return np.empty((0, n_out))
+    p = power_frames(audio[:(n_frames - 1) * hop + window], window, hop, n_fft)
+    assert p.shape[0] == n_frames
+    grid = speechpy_grid(sample_rate, n_filt, p.shape[1])
+    bank = np.zeros((n_filt, p.shape[1]))
+    for i in range(n_filt):
+        lo, mid, hi = int(grid[i]), int(grid[i + 1]), int(grid[i + 2])
+        for k in range(lo + 1, mid):
+            bank[i, k] = (k - lo) / (mid - lo)
+        for k in range(mid, hi):
+            bank[i, k] = (hi - k) / (hi - mid)
+    feat = p @ bank.T
+    feat[feat == 0] = EPS64
+    energy = p.sum(axis=1)
+    energy[energy == 0] = EPS64
+    out = np.log(feat) @ dct2_ortho_matrix(n_filt, n_out).T
+    out[:, 0] = np.log(energy)
+    return out
+
+
 def vectorize_raw(audio, pr) -> np.ndarray:
-    """reference precise/vectorization.py:46-50 for Vectorizer.mfccs / Vectorizer.mels."""
+    """reference precise/vectorization.py:46-50 for Vectorizer.mfccs / Vectorizer.mels / Vectorizer.speechpy_mfccs."""
     if len(audio) == 0:
         raise ValueError('Cannot vectorize empty audio!')   # InvalidAudio is a ValueError (util.py:25)
     if pr.vectorizer == 2:
@@ -124,7 +163,9 @@ def vectorize_raw(audio, pr) -> np.ndarray:
     if pr.vectorizer == 1:
         return mel_spec(audio, pr.sample_rate, pr.window_samples, pr.hop_samples,
                         pr.n_fft, pr.n_filt)
-    raise ValueError('oracle implements Vectorizer.mfccs and Vectorizer.mels only')
+    if pr.vectorizer == 3:
+        return speechpy_mfcc(audio, pr.sample_rate, pr.window_samples, pr.hop_samples, pr.n_fft, pr.n_filt, pr.n_mfcc)
+    raise ValueError('unknown vectorizer %r' % (pr.vectorizer,))
 
 
 def add_deltas(features: np.ndarray) -> np.ndarray:

@@ -77,8 +77,11 @@ def test_argument_validation_without_gpu(lib):
     cfg = pb_config()
     lib.pb_config_default(C.byref(cfg))
     h = C.c_void_p()
-    cfg.vectorizer = 3
-    assert lib.pb_create(C.byref(cfg), C.byref(h)) == -2          # speechpy: unsupported, before any CUDA call
+    cfg.n_fft = 2048
+    assert lib.pb_create(C.byref(cfg), C.byref(h)) == -2          # n_fft > 1024: unsupported, reported before any CUDA call
+    cfg.n_fft = 512
+    cfg.vectorizer = 7
+    assert lib.pb_create(C.byref(cfg), C.byref(h)) == -1          # unknown vectorizer
     cfg.vectorizer = 2
     cfg.abi_version = 99
     assert lib.pb_create(C.byref(cfg), C.byref(h)) == -1

@@ -621,14 +621,40 @@ def test_many_frames_per_tick(kw, chunk):
     assert count == fired.sum()
 
 
+@pytest.mark.parametrize('kw', [dict(), dict(n_filt=26, n_mfcc=13), dict(window_t=0.05, hop_t=0.02)], ids=['default', 'filt26', 'window800'])
+def test_speechpy_vectorizer(kw):
+    """Vectorizer.speechpy_mfccs (legacy .params files, precise/params.py:147; precise/vectorization.py:40-42), PARITY UNPINNED: against the
+    oracle's restatement of speechpy's published algorithm (mel corners up to sample_rate / 2 on floor((n_bins + 1) hz / sr), one frame
+    fewer than sonopy's framing).  Batch featuriser, then the stateful tick against oracle Listeners (windows, raw, detections)."""
+    m = _mod()
+    pr = m.ListenerParams(vectorizer=m.Vectorizer.speechpy_mfccs, **kw)
+    opr = OracleParams(**pr.to_dict())
+    c = m.PreciseB200(pr)
+    pcm = noise(5, 9000, seed=41)
+    pcm[4] = 0
+    got = c.mfcc(cuda(pcm)).cpu().numpy()
+    want = np.stack([om.speechpy_mfcc(r.astype(np.float32) / 32768.0, 16000, pr.window_samples, pr.hop_samples, pr.n_fft, pr.n_filt, pr.n_mfcc)
+                     for r in pcm])
+    assert got.shape == want.shape and got.shape[1] > 0
+    assert np.max(np.abs(got - want)) < 2e-4
+    c.close()
+    chunk = 1024
+    pcm = noise(4, 30 * chunk, seed=43)
+    model = m.GruModel.random(pr.feature_size, 20, seed=5, scale=0.1)
+    raw, conf, fired, wins, count = _run_gpu_streams(m, model, pcm, chunk, pr=pr, sens=0.8, lvl=1)
+    owins = _oracle_windows(pcm, chunk, opr)
+    assert np.max(np.abs(wins - owins)) < 2e-4
+    w = og.GruWeights(model.kernel, model.recurrent, model.bias, model.dense_w, model.dense_b)
+    oraw, oconf, ofired = run_streams(w, pcm, chunk, pr=opr, sensitivity=0.8, trigger_level=1)
+    assert np.max(np.abs(raw - oraw)) < 1e-4 and np.array_equal(fired, ofired)
+
+
 def test_unsupported_and_errors():
     m = _mod()
     with pytest.raises(NotImplementedError):
         m.PreciseB200(m.ListenerParams(n_fft=2048))
     with pytest.raises(NotImplementedError):
         m.PreciseB200(m.ListenerParams(n_fft=384))
-    with pytest.raises(NotImplementedError):
-        m.PreciseB200(m.ListenerParams(vectorizer=m.Vectorizer.speechpy_mfccs))
     c = m.PreciseB200(max_streams=4)
     with pytest.raises(m.PBError):
         c.predict(torch.zeros((1, 29, 13), device='cuda'))           # weights not loaded
