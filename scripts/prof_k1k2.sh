@@ -1,4 +1,4 @@
-# Round-1 profiling recipe (run under gpurun, 1 GPU).  Outputs land in gpurun_out/.
+# Round-1 profiling recipe (run under gpurun, 1 GPU); superseded by scripts/prof_r2.sh (three kernels per tick), kept for the round-1 profiles.  Outputs land in gpurun_out/.
 # bench.py primes every stream with 24 untimed ticks (K1, projection, K2 each); the -s counts below skip them and the warm-up so that the
 # captured launches are steady-state updates (full 29-frame windows).
 set -x
