@@ -172,3 +172,35 @@ def test_gru_fp32_close_to_fp64_and_shapes():
     assert np.max(np.abs(p32[:, 0] - p64)) < 1e-5
     assert abs(og.run(w, x[3]) - p32[3, 0]) < 1e-7
     assert 0.02 < p64.min() and p64.max() < 0.98          # weights at this scale are unsaturated
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Vectorizer.speechpy_mfccs restatement (PARITY UNPINNED: speechpy is not in the reference tree): the properties of its published
+# algorithm that the restatement and the CUDA path rely on
+def test_speechpy_restatement_framing_and_grid():
+    from oracle import mfcc as om
+    from oracle.listener import OracleListener
+    from oracle.gru import GruWeights
+    from oracle.params import OracleParams
+    x = np.random.RandomState(1).randn(5000) * 0.1
+    for n, want in ((1599, 0), (1600, 0), (2399, 0), (2400, 1), (3200, 2), (5000, 4)):       # floor((n - window) / hop): one fewer than sonopy
+        assert om.speechpy_mfcc(x[:n], 16000, 1600, 800, 512, 20, 13).shape == (want, 13), n
+    assert om.mfcc_spec(x[:2400], 16000, 1600, 800, 512, 20, 13).shape[0] == 2
+    g = om.speechpy_grid(16000, 20, 257)
+    assert g[0] == 0 and g[-1] in (128, 129) and np.all(np.diff(g) >= 1)                     # corners up to sample_rate / 2 on (n_bins + 1) hz / sr (floor of 128.99..)
+    # coefficient 0 = log of the frame energy; silence hits the eps floor everywhere before the DCT
+    m = om.speechpy_mfcc(x, 16000, 1600, 800, 512, 20, 13)
+    p = om.power_frames(x[:4 * 800 + 1600 - 800], 1600, 800, 512)
+    assert np.allclose(m[:, 0], np.log(p.sum(axis=1)))
+    z = om.speechpy_mfcc(np.zeros(4000), 16000, 1600, 800, 512, 20, 13)
+    assert np.allclose(z[:, 0], np.log(om.EPS64)) and np.allclose(z[:, 1:], 0.0, atol=1e-9)
+    # the listener state machine is chunking-independent with this framing too
+    pr = OracleParams(vectorizer=3)
+    w = GruWeights.random(13, 20, seed=0, scale=0.1)
+    a, b = OracleListener(w, pr), OracleListener(w, pr)
+    sig = (np.random.RandomState(2).randn(1024 * 40) * 0.1).astype(np.float32)
+    for k in range(40):
+        wa = a.update_vectors(sig[k * 1024:(k + 1) * 1024])
+    for k in range(0, len(sig), 333):
+        wb = b.update_vectors(sig[k:k + 333])
+    assert np.allclose(wa, wb)
