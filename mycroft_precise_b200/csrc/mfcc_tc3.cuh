@@ -10,7 +10,7 @@
 //            pieces (x - x0 = 256 hi + lo, |lo| <= 128, balanced so that a quiet signal has hi = 0), which needs no floating-point
 //            work: bytes are dropped into the mantissa of 1024.0h and the bias removed by one half2 add.  The operand is the PCM
 //            in its natural order (MN-major A: 8 consecutive samples = 8 rows of one K index); rows of an MMA = (frame, n2).
-//   between (CUDA cores):    Z_r[n2] = Y_r[n2] w512^(n2 r) (the lane owns n2: its eight twiddles live in registers), fp16 hi / lo
+//   between (CUDA cores):    Z_r[n2] = Y_r[n2] w512^(n2 r) (the lane owns n2: its eight twiddles come from a 2 KB table), fp16 hi / lo
 //            split, one 4-byte store per block and piece into the stage-2 operand.
 //   stage 2 (tensor cores):  X[16 m + r] = sum_n2 Z_r[n2] w32^(n2 m), X[16 m + 16 - r] from conj(Z_r): nine 64-column blocks
 //            sharing one 64 x 64 matrix (mfcc_tc.cuh); rows of an MMA = (frame, h), four rows per frame.
@@ -19,14 +19,15 @@
 // Organisation: a persistent CTA per SM, 16 worker warps that all walk the same phases (no warp specialisation of the heavy
 // loops: the instruction cache sees one small loop at a time -- the warp-specialised predecessor, mfcc_tc2.cuh, spent 40 % of
 // its issue slots waiting for instructions) plus one warp that only issues the MMAs.  Per tile of 32 frames:
-//     INT(k)   workers     tcgen05.ld of stage 1's result, twiddle, split, stores
-//     P(k)     warp 16     MMA2(k)   (MMA1(k+1) as soon as every worker has read tile k's stage-1 result, during INT(k))
-//              warps 0-7   EPI(k-1), then a quarter of CONV(k+2)
+//     INT(k)   workers     tcgen05.ld of stage 1's result, twiddle, split, stores into the stage-2 operand
+//     P(k)     warps 0-7   EPI(k-1), then a quarter of CONV(k+2)
 //              warps 8-15  new tails of tile k+1, frame records of tile k+4 (+ L2 prefetch), three quarters of CONV(k+2)
 //              CONV = raw PCM copied by cp.async into the stage-1 operand buffer (L2-prefetched four tiles earlier), split in place
-// with one barrier of the worker warps per tile (the MMA warp follows mbarriers only); the MMAs of a tile run under the CUDA-core phases of its neighbours.  The frame list
-// (which frames complete this tick, where their samples are, the split of the first sample, new tail) is built by
-// mfcc_tc3_plan_kernel with every pointer ready to use.
+//     warp 16  follows mbarriers only: MMA1(k+1) once CONV(k+1) is complete and every worker has read tile k's stage-1 result,
+//              MMA2(k) once INT(k)'s operand is complete and the epilogue has drained the accumulator buffer
+// with one barrier of the worker warps per tile; the MMAs of a tile run under the CUDA-core phases of its neighbours.  The
+// frame list (which frames complete this tick, where their samples are, the split of the first sample, new tail) is built
+// by mfcc_tc3_plan_kernel with every pointer ready to use.  Measurements and the history of this organisation: DESIGN.md.
 #pragma once
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
