@@ -66,7 +66,7 @@ typedef struct pb_config {
     int32_t sample_rate;       /* 16000 */
     int32_t window_samples;    /* 1600  */
     int32_t hop_samples;       /* 800   */
-    int32_t n_fft;             /* 512; power of two in [64, 512]                             */
+    int32_t n_fft;             /* 512; power of two in [64, 1024]                            */
     int32_t n_filt;            /* 20;  <= 64                                                 */
     int32_t n_mfcc;            /* 13;  <= 64                                                 */
     int32_t n_features;        /* 29 rows per network input                                  */
